@@ -1,0 +1,190 @@
+/*
+ * millieye_b200 — C-ABI of the B200 (sm_100a) detection-and-fusion hot path.
+ *
+ * Every entry point replaces one stretch of the reference's PyTorch forward
+ * (sxontheway/milliEye, paths relative to /root/reference/module3_our_dataset):
+ * the reference has no FFI of its own (it is pure Python calling torch / torchvision),
+ * so each function cites the Python lines whose arithmetic it takes over.
+ *
+ * Conventions
+ *  - plain pointers + sizes, no torch types; all pointers are DEVICE pointers unless
+ *    a parameter is named host_*; the library never allocates or frees on the hot path
+ *    (workspaces are passed in) and never synchronises: work is enqueued on `stream`
+ *    (a cudaStream_t passed as void*), so calls are CUDA-graph capturable.
+ *  - activations are NHWC fp16 with a row pitch (elements between consecutive pixels),
+ *    so route/concat is a pitch + channel offset, not a copy.
+ *  - return value: ME_OK or an ME_ERR_* code; me_last_error() gives the text.
+ */
+#ifndef MILLIEYE_B200_H_
+#define MILLIEYE_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define ME_OK 0
+#define ME_ERR_ARG 1
+#define ME_ERR_CUDA 2
+#define ME_ERR_UNSUPPORTED 3
+
+#define ME_ACT_LINEAR 0
+#define ME_ACT_LEAKY 1   /* LeakyReLU(0.1): yolov3/models.py:40-41 */
+#define ME_ACT_SIGMOID 2 /* my_models.py:153-157 (radar score map) */
+
+typedef void* me_stream_t; /* cudaStream_t */
+
+/* ---- library ---------------------------------------------------------------------- */
+int me_version(void);
+/* Copies the calling thread's last error text into buf (NUL-terminated); returns its length. */
+int me_last_error(char* buf, size_t n);
+/* SM count / compute capability of the current device (fails loudly off sm_100). */
+int me_device_info(int* sm_count, int* cc_major, int* cc_minor);
+/* Debug word written by a kernel whose pipeline wait timed out (0 = never). */
+int me_debug_status(unsigned long long* host_word);
+
+/* ---- conv + BN + activation (A2/A8/A9 of SURVEY §8a) ------------------------------ */
+/* K-block (channels per pipeline stage) the GEMM uses for `cin` input channels; the packed
+ * weight's per-tap channel count is cin rounded up to it. */
+int me_conv_k_block(int cin);
+int me_conv_cin_pad(int cin);
+
+/* Folds eval-mode BatchNorm into the conv and packs OIHW fp32 weights into the kernel's
+ * K-major fp16 layout  w_packed[cout_pad][ksize*ksize*cin_pad]  (tap-major, then channel);
+ * bias_out[cout_pad] fp32 = beta - mean*gamma/sqrt(var+eps) (+ conv bias).
+ * Replaces nn.Conv2d + nn.BatchNorm2d parameter use at yolov3/models.py:27-39 and
+ * my_models.py:62-73,133-150.  Any of conv_bias / bn_* may be NULL. */
+int me_pack_conv_weights(const float* w_oihw, const float* conv_bias, const float* bn_gamma,
+                         const float* bn_beta, const float* bn_mean, const float* bn_var, float bn_eps,
+                         int cout, int cin, int ksize, int cout_pad, void* w_packed, float* bias_out,
+                         me_stream_t stream);
+
+typedef struct me_conv_desc {
+  int n, h, w;       /* input batch / height / width                                      */
+  int cin;           /* input channels read (view width)                                  */
+  int in_pitch;      /* elements between consecutive input pixels (>= cin, multiple of 8) */
+  int cout;          /* output channels written (multiple of 16; padded channels get 0+bias) */
+  int out_pitch;     /* elements between consecutive output pixels                        */
+  int ksize;         /* 1 or 3; padding is (ksize-1)/2 as in models.py:25                 */
+  int stride;        /* 1 or 2                                                            */
+  int act;           /* ME_ACT_*                                                          */
+  int out_f32;       /* 0: fp16 output, 1: fp32 output (YOLO head logits)                 */
+  int res_pitch;     /* >0: add residual[pixel][cout] (fp16, this pitch) AFTER the activation
+                        (shortcut layer, models.py:258-260); 0: none                      */
+} me_conv_desc;
+
+/* y = act(conv(x, w) + bias) (+ residual).  Implicit GEMM on tcgen05 tensor cores: TMA
+ * (im2col mode for 3x3, tiled for 1x1) -> swizzled smem -> tcgen05.mma -> TMEM -> epilogue
+ * -> TMA store.  Replaces the convolutional branch of Darknet.forward (models.py:252-253),
+ * cnn_layers_1 (my_models.py:76-77), cnn_layers_3 (my_models.py:152-157) and, with
+ * ksize=1,h=w=1, the Linear 490->256 of refinement_head.net0 (my_models.py:263). */
+int me_conv_gemm(const me_conv_desc* d, const void* x, const void* w_packed, const float* bias,
+                 const void* residual, void* y, me_stream_t stream);
+
+/* First layer: 3x3 / stride 1 / pad 1 conv straight from the caller's NCHW fp32 image
+ * (cin <= 4) to NHWC fp16, BN folded, activation applied.  w_first is fp32 [cout][cin][3][3]
+ * already BN-folded (me_fold_first_weights).  models.py:252 for module 0, my_models.py:133. */
+int me_fold_first_weights(const float* w_oihw, const float* conv_bias, const float* bn_gamma,
+                          const float* bn_beta, const float* bn_mean, const float* bn_var, float bn_eps,
+                          int cout, int cin, float* w_folded, float* bias_out, me_stream_t stream);
+int me_conv_first(const float* x_nchw, const float* w_folded, const float* bias, void* y_nhwc, int n, int h,
+                  int w, int cin, int cout, int out_pitch, int act, me_stream_t stream);
+
+/* ---- glue layers (A3) -------------------------------------------------------------- */
+/* MaxPool2d(2, stride) on NHWC fp16; stride 1 uses the right/bottom zero pad of
+ * models.py:46-49 (ZeroPad2d((0,1,0,1)) then pool). */
+int me_maxpool2(const void* x, void* y, int n, int h, int w, int c, int in_pitch, int out_pitch, int stride,
+                me_stream_t stream);
+/* Nearest x2 upsample (models.py:82-92) written into a channel slice of a concat buffer. */
+int me_upsample2(const void* x, void* y, int n, int h, int w, int c, int in_pitch, int out_pitch,
+                 me_stream_t stream);
+/* Strided channel-slice copy (route of a tensor that could not be produced in place). */
+int me_copy_channels(const void* x, void* y, long long pixels, int c, int in_pitch, int out_pitch,
+                     me_stream_t stream);
+/* NHWC fp16 (pitch) -> NCHW fp32 contiguous: the featuremap handed back to PyTorch callers
+ * (models.py:254-255). */
+int me_nhwc_to_nchw_f32(const void* x, float* y, int n, int h, int w, int c, int in_pitch, me_stream_t stream);
+/* NCHW fp32 -> NHWC fp16 (pitch, zero padded channels). */
+int me_nchw_f32_to_nhwc(const float* x, void* y, int n, int h, int w, int c, int out_pitch, me_stream_t stream);
+
+/* ---- YOLO decode (A4) -------------------------------------------------------------- */
+/* logits: NHWC fp32 [n][g][g][pitch] holding A*(5+C) head channels; out: fp32
+ * [n][rows_total][5+C], this head's rows start at row_offset, ordered anchor-major, then gy,
+ * then gx (YOLOLayer.forward, models.py:142-177).  anchors_wh: host array of 2*A floats in
+ * pixels.  stride = img_dim / g. */
+int me_yolo_decode(const float* logits, int pitch, float* out, int n, int g, int num_anchors, int num_classes,
+                   const float* host_anchors_wh, float stride, int rows_total, int row_offset,
+                   me_stream_t stream);
+
+/* ---- confidence filter + class arg-max + per-class NMS (A6) ------------------------ */
+/* Bytes of workspace me_filter_nms needs for a (n, rows, 5+C) prediction tensor. */
+size_t me_filter_nms_workspace(int n, int rows, int num_classes);
+/* pred: fp32 [n][rows][5+C] rows [cx,cy,w,h,conf,cls...].  Reproduces
+ * non_max_suppression_cpp (utils/utils.py:337-378) incl. torchvision.batched_nms's two code
+ * paths (coordinate trick for <= 1000 candidates, per-class otherwise).  Output:
+ * det [n][max_det][7+C] = [x1,y1,x2,y2,conf,class_conf,class_pred,cls...], det_count[n],
+ * det_index [n][max_det] = source row of every survivor (score-descending).
+ * If xyxy_inplace != 0 the first four columns of pred are rewritten to x1y1x2y2 as the
+ * reference does (utils.py:354).  nms_thresh is a double because torchvision compares the fp32
+ * IoU against the Python float as a double. */
+int me_filter_nms(float* pred, int n, int rows, int num_classes, float conf_thresh, double nms_thresh,
+                  int max_det, int xyxy_inplace, float* det, int* det_count, int* det_index, void* workspace,
+                  size_t workspace_bytes, me_stream_t stream);
+
+/* ---- RoI gathers (A10/A11) ---------------------------------------------------------- */
+/* rois: fp32 [cap][5] = [batch_idx,x1,y1,x2,y2]; only the first *roi_count rows are live.
+ * feat: NHWC fp16 [n][h][w][pitch].  Output fp16 [cap][out_pitch] with element
+ * c*pooled*pooled + ph*pooled + pw (the flatten order of my_models.py:262), zero padded. */
+int me_psroi_align(const void* feat, int n, int h, int w, int pitch, int out_channels, int pooled,
+                   float spatial_scale, const float* rois, const int* roi_count, int cap, void* out,
+                   int out_pitch, me_stream_t stream);
+int me_roi_align(const void* feat, int n, int h, int w, int pitch, int channels, int pooled, float spatial_scale,
+                 const float* rois, const int* roi_count, int cap, void* out, int out_pitch,
+                 me_stream_t stream);
+
+/* ---- proposal assembly, heads, output (A7, A12-A14) -------------------------------- */
+typedef struct me_head_weights {
+  /* refinement_head (my_models.py:213-258), fp32 device pointers, row-major [out][in] */
+  const float* net1_w; const float* net1_b;   /* 4 x 256  box regression          */
+  const float* net2_w; const float* net2_b;   /* 13 x 256 class vector (sigmoid)  */
+  const float* radar_w; const float* radar_b; /* 10 x 490 = 7x7 conv, BN folded   */
+  const float* radar2_w; const float* radar2_b; /* 1 x 10 1x1 conv                */
+  /* ensemble_head (my_models.py:176-210) */
+  const float* fc1_w; const float* fc1_b;     /* 32 x 2  */
+  const float* fc2_w; const float* fc2_b;     /* 2 x 64  */
+} me_head_weights;
+
+/* Builds the RoI list of Network.forward (my_models.py:459-492): per-image NMS survivors
+ * with class_pred == class_idx (image proposals, image-major order) followed by the radar
+ * boxes scaled by img_size.  img_boxes: fp32 [cap][9] = [i,x1,y1,x2,y2,conf,class_conf,
+ * class_pred,cls[class_idx]] for the image proposals; rois [cap][5]; counts[0] = image
+ * proposals, counts[1] = image + radar proposals. */
+int me_build_proposals(const float* det, const int* det_count, int n, int max_det, int det_cols, int class_idx,
+                       const float* radar_boxes, int num_radar, float img_size, float* img_boxes, float* rois,
+                       int* counts, int cap, me_stream_t stream);
+
+/* refinement_head tail + ensemble_head + masks (my_models.py:264-284, 498-514): from
+ * hidden = leaky(net0(psroi)) [cap][hidden_pitch] fp16 and the radar crop [cap][radar_pitch]
+ * fp16, computes regress[cap][4], refine[cap][2] (confidence, class score) and mask[cap]
+ * (foreground probability: ensemble column 0 for image proposals, refinement confidence for
+ * radar proposals). */
+int me_fusion_heads(const void* hidden, int hidden_pitch, const void* radar_crop, int radar_pitch,
+                    const me_head_weights* hw, const float* img_boxes, const int* counts, int cap, float* regress,
+                    float* refine, float* mask, me_stream_t stream);
+
+/* Threshold, box regression, priority sort (my_models.py:516-539, box_regress :378-391).
+ * out [cap][8] = [i,x1,y1,x2,y2,new_conf,class_score,class_pred] sorted by mask descending with
+ * radar masks divided by 5; out_count[0] = rows.  regress_boxes = 0 skips the regression
+ * (model_mode 2).  workspace >= me_finalize_workspace(cap) bytes. */
+size_t me_finalize_workspace(int cap);
+int me_finalize_output(const float* img_boxes, const float* rois, const float* refine, const float* regress,
+                       const float* mask, const int* counts, int cap, float thr_img, float thr_radar,
+                       int regress_boxes, float* out, int* out_count, void* workspace, size_t workspace_bytes,
+                       me_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MILLIEYE_B200_H_ */

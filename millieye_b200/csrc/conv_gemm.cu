@@ -1,0 +1,435 @@
+// Fused conv + (folded BN) bias + activation (+ residual) as an implicit GEMM on tcgen05.
+//
+//   D[M = N*Ho*Wo pixels][Cout] = A[M][K = taps*Cin] * W[Cout][K]^T
+//
+// One persistent CTA per SM walks 128 x BN output tiles.  Warp roles:
+//   warp 0   : TMA producer  - A tile: im2col-mode TMA (3x3, any stride, zero fill at the image
+//              border) or tiled TMA (1x1); B tile: tiled TMA over the packed weights.
+//   warp 1   : allocates TMEM, one elected lane issues tcgen05.mma (M=128, N=BN, K=16) and
+//              commits to the mbarriers that free smem stages / publish the accumulator.
+//   warps 2-5: epilogue - tcgen05.ld (lane quarter = warp % 4) -> +bias -> activation ->
+//              (+ residual, TMA-loaded into the staging tile) -> fp16/fp32 -> swizzled smem
+//              staging -> TMA store.  Accumulators are double-buffered in TMEM so the epilogue
+//              of tile i overlaps the main loop of tile i+1.
+//
+// Replaces the conv/BN/LeakyReLU Sequential of yolov3/models.py:22-41 executed at :252-253,
+// the shortcut add at :258-260, cnn_layers_1 (my_models.py:47-77), cnn_layers_3 (:130-157)
+// and refinement_head.net0 (:238-241).
+#include "common.cuh"
+#include "ptx.cuh"
+
+namespace me {
+namespace {
+
+constexpr int kBM = 128;
+constexpr int kThreads = 192;
+constexpr int kEpiThreads = 128;
+constexpr uint32_t kEpiBarrierId = 1;
+constexpr int kMaxStages = 8;
+
+struct ConvParams {
+  int M;
+  int Ho, Wo;
+  int stride, pad;
+  int kb_per_tap;  // K blocks per filter tap (= cin_pad / BK)
+  int num_kb;      // taps * kb_per_tap
+  int tiles_m, tiles_n;
+  int act;
+  int has_res;
+  int im2col;
+  int stages;
+  const float* bias;
+  unsigned long long* debug;  // host-mapped word, written before a watchdog trap
+};
+
+template <int BN, int BK, bool OUT_F32>
+struct Cfg {
+  static constexpr int A_BYTES = kBM * BK * 2;
+  static constexpr int B_BYTES = BN * BK * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int ESIZE = OUT_F32 ? 4 : 2;
+  static constexpr int SUB_ROW_BYTES = (BN * ESIZE >= 128) ? 128 : BN * ESIZE;
+  static constexpr int SUB_COLS = SUB_ROW_BYTES / ESIZE;
+  static constexpr int NUM_SUB = BN / SUB_COLS;
+  static constexpr int SUB_BYTES = kBM * SUB_ROW_BYTES;
+  static constexpr int STAGING_BYTES = NUM_SUB * SUB_BYTES;
+  static constexpr int SWZ_BITS = (SUB_ROW_BYTES == 128) ? 3 : (SUB_ROW_BYTES == 64) ? 2 : 1;
+  static constexpr int TMEM_COLS = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
+  static constexpr int TAIL_BYTES = BN * 4 + 64 * 8 + 16;  // bias + barriers + tmem ptr
+  static constexpr int smem_bytes(int stages) { return 1024 + stages * STAGE_BYTES + STAGING_BYTES + TAIL_BYTES; }
+  static_assert(BN % 32 == 0 && BN <= 256, "BN");
+  static_assert(BK == 16 || BK == 32 || BK == 64, "BK");
+  static_assert(A_BYTES % 1024 == 0 && B_BYTES % 1024 == 0, "tiles must keep 1024B alignment");
+};
+
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, unsigned long long* dbg, uint32_t tag) {
+  if (ptx::mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  uint32_t spins = 0;
+  while (!ptx::mbar_try_wait(bar, parity)) {
+    if ((++spins & 1023u) == 0 && clock64() - t0 > 4000000000LL) {
+      if (dbg) {
+        *reinterpret_cast<volatile unsigned long long*>(dbg) =
+            (static_cast<unsigned long long>(tag) << 32) | (static_cast<unsigned long long>(blockIdx.x) << 8) | parity | 0x80u;
+        __threadfence_system();
+      }
+      __trap();
+    }
+  }
+}
+
+__device__ __forceinline__ float apply_act(float v, int act) {
+  if (act == ME_ACT_LEAKY) return v > 0.f ? v : 0.1f * v;
+  if (act == ME_ACT_SIGMOID) return 1.f / (1.f + __expf(-v));
+  return v;
+}
+
+template <int BN, int BK, bool OUT_F32>
+__global__ void __launch_bounds__(kThreads, 1)
+conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                 const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmR,
+                 const ConvParams p) {
+  using C = Cfg<BN, BK, OUT_F32>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* stage_base = smem;
+  uint8_t* staging = smem + p.stages * C::STAGE_BYTES;
+  float* s_bias = reinterpret_cast<float*>(staging + C::STAGING_BYTES);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_bias + BN);
+  uint64_t* full_bar = bars;                     // [kMaxStages]
+  uint64_t* empty_bar = bars + kMaxStages;       // [kMaxStages]
+  uint64_t* tmem_full = bars + 2 * kMaxStages;   // [2]
+  uint64_t* tmem_empty = tmem_full + 2;          // [2]
+  uint64_t* res_full = tmem_empty + 2;           // [1]
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(res_full + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int total_tiles = p.tiles_m * p.tiles_n;
+
+  if (warp == 0 && ptx::elect_one()) {
+    ptx::prefetch_tmap(&tmA);
+    ptx::prefetch_tmap(&tmB);
+    ptx::prefetch_tmap(&tmC);
+    if (p.has_res) ptx::prefetch_tmap(&tmR);
+  }
+  if (warp == 1) {
+    if (ptx::elect_one()) {
+      for (int s = 0; s < p.stages; ++s) {
+        ptx::mbar_init(&full_bar[s], 1);
+        ptx::mbar_init(&empty_bar[s], 1);
+      }
+      for (int a = 0; a < 2; ++a) {
+        ptx::mbar_init(&tmem_full[a], 1);
+        ptx::mbar_init(&tmem_empty[a], 4);  // one arrive per epilogue warp
+      }
+      ptx::mbar_init(res_full, 1);
+      ptx::fence_mbar_init();
+    }
+    __syncwarp();
+    ptx::tmem_alloc(tmem_ptr, C::TMEM_COLS);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    if (ptx::elect_one()) {
+      uint32_t stage = 0, phase = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+        const int tm = tile / p.tiles_n, tn = tile - tm * p.tiles_n;
+        const int m0 = tm * kBM, n0 = tn * BN;
+        int cw = 0, ch = 0, cn = 0;
+        if (p.im2col) {
+          const int q0 = m0 % p.Wo;
+          const int t = m0 / p.Wo;
+          cw = q0 * p.stride - p.pad;
+          ch = (t % p.Ho) * p.stride - p.pad;
+          cn = t / p.Ho;
+        }
+        int tap = 0, cb = 0;
+        for (int kb = 0; kb < p.num_kb; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1, p.debug, 0x100u + stage);
+          uint8_t* sa = stage_base + stage * C::STAGE_BYTES;
+          uint8_t* sb = sa + C::A_BYTES;
+          ptx::mbar_arrive_expect_tx(&full_bar[stage], C::STAGE_BYTES);
+          if (p.im2col) {
+            const int r = tap / 3, s = tap - r * 3;
+            ptx::tma_load_im2col_4d(&tmA, &full_bar[stage], sa, cb * BK, cw, ch, cn, (uint16_t)s, (uint16_t)r);
+          } else {
+            ptx::tma_load_2d(&tmA, &full_bar[stage], sa, cb * BK, m0);
+          }
+          ptx::tma_load_2d(&tmB, &full_bar[stage], sb, kb * BK, n0);
+          if (++cb == p.kb_per_tap) { cb = 0; ++tap; }
+          if (++stage == (uint32_t)p.stages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer
+    if (ptx::elect_one()) {
+      constexpr uint32_t idesc = ptx::make_idesc_f16(kBM, BN);
+      uint32_t stage = 0, phase = 0;
+      int it = 0;
+      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+        const int acc = it & 1;
+        const uint32_t acc_phase = (it >> 1) & 1;
+        mbar_wait(&tmem_empty[acc], acc_phase ^ 1, p.debug, 0x200u + acc);
+        ptx::tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        for (int kb = 0; kb < p.num_kb; ++kb) {
+          mbar_wait(&full_bar[stage], phase, p.debug, 0x300u + stage);
+          ptx::tc_fence_after();
+          const uint32_t a_addr = ptx::smem_u32(stage_base + stage * C::STAGE_BYTES);
+          const uint32_t b_addr = a_addr + C::A_BYTES;
+#pragma unroll
+          for (int k = 0; k < BK / 16; ++k) {
+            const uint64_t adesc = ptx::make_kmajor_desc(a_addr + k * 32, BK * 2);
+            const uint64_t bdesc = ptx::make_kmajor_desc(b_addr + k * 32, BK * 2);
+            ptx::umma_f16_ss(d_tmem, adesc, bdesc, idesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          ptx::umma_commit(&empty_bar[stage]);  // frees the smem stage when these MMAs retire
+          if (++stage == (uint32_t)p.stages) { stage = 0; phase ^= 1; }
+        }
+        ptx::umma_commit(&tmem_full[acc]);  // accumulator complete -> epilogue
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ epilogue (warps 2..5)
+    const int q = warp & 3;            // TMEM lane quarter this warp may read
+    const int row = q * 32 + lane;     // tile row == TMEM lane
+    const int etid = threadIdx.x - 64;  // 0..127
+    const bool leader = (threadIdx.x == 64);
+    int it = 0;
+    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+      const int tm = tile / p.tiles_n, tn = tile - tm * p.tiles_n;
+      const int m0 = tm * kBM, n0 = tn * BN;
+      const int acc = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1;
+      if (leader) {
+        ptx::tma_store_wait_read0();  // previous tile's store has drained the staging tile
+        if (p.has_res) {
+          ptx::mbar_arrive_expect_tx(res_full, C::STAGING_BYTES);
+#pragma unroll
+          for (int sub = 0; sub < C::NUM_SUB; ++sub)
+            ptx::tma_load_2d(&tmR, res_full, staging + sub * C::SUB_BYTES, n0 + sub * C::SUB_COLS, m0);
+        }
+      }
+      for (int i = etid; i < BN; i += kEpiThreads) s_bias[i] = p.bias[n0 + i];
+      ptx::named_bar_sync(kEpiBarrierId, kEpiThreads);
+      mbar_wait(&tmem_full[acc], acc_phase, p.debug, 0x400u + acc);
+      ptx::tc_fence_after();
+      if (p.has_res) mbar_wait(res_full, it & 1, p.debug, 0x500u);
+
+      const uint32_t t_row = tmem_base + acc * BN + (static_cast<uint32_t>(q * 32) << 16);
+#pragma unroll 1
+      for (int c = 0; c < BN; c += 32) {
+        uint32_t r[32];
+        ptx::tmem_ld_32x32b_x32(t_row + c, r);
+        ptx::tmem_ld_wait();
+        float v[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = apply_act(__uint_as_float(r[j]) + s_bias[c + j], p.act);
+        if constexpr (OUT_F32) {
+          // 32 fp32 columns = one 128B staging row of sub-tile c/32
+          uint8_t* sub = staging + (c / C::SUB_COLS) * C::SUB_BYTES;
+          const uint32_t rbase = row * C::SUB_ROW_BYTES + (c % C::SUB_COLS) * 4;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            uint32_t off = rbase + j * 16;
+            off ^= ((off >> 7) & ((1u << C::SWZ_BITS) - 1)) << 4;
+            *reinterpret_cast<float4*>(sub + off) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+          }
+        } else {
+          uint8_t* sub = staging + (c / C::SUB_COLS) * C::SUB_BYTES;
+          const uint32_t rbase = row * C::SUB_ROW_BYTES + (c % C::SUB_COLS) * 2;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            uint32_t off = rbase + j * 16;
+            off ^= ((off >> 7) & ((1u << C::SWZ_BITS) - 1)) << 4;
+            uint4* dst = reinterpret_cast<uint4*>(sub + off);
+            float* vv = v + 8 * j;
+            if (p.has_res) {
+              const uint4 rr = *dst;
+              const __half2* rh = reinterpret_cast<const __half2*>(&rr);
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const float2 f = __half22float2(rh[e]);
+                vv[2 * e] += f.x;
+                vv[2 * e + 1] += f.y;
+              }
+            }
+            uint4 o;
+            __half2* oh = reinterpret_cast<__half2*>(&o);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) oh[e] = __floats2half2_rn(vv[2 * e], vv[2 * e + 1]);
+            *dst = o;
+          }
+        }
+      }
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(&tmem_empty[acc]);  // accumulator may be overwritten
+      ptx::fence_proxy_async_smem();                       // staging writes -> visible to TMA
+      ptx::named_bar_sync(kEpiBarrierId, kEpiThreads);
+      if (leader) {
+#pragma unroll
+        for (int sub = 0; sub < C::NUM_SUB; ++sub)
+          ptx::tma_store_2d(&tmC, staging + sub * C::SUB_BYTES, n0 + sub * C::SUB_COLS, m0);
+        ptx::tma_store_commit();
+      }
+    }
+    if (leader) ptx::tma_store_wait_all0();
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  if (warp == 1) ptx::tmem_dealloc(tmem_base, C::TMEM_COLS);
+}
+
+unsigned long long* g_debug_host = nullptr;
+unsigned long long* g_debug_dev = nullptr;
+
+int ensure_debug_word() {
+  if (g_debug_host) return ME_OK;
+  ME_CUDA(cudaHostAlloc(reinterpret_cast<void**>(&g_debug_host), sizeof(unsigned long long), cudaHostAllocMapped));
+  *g_debug_host = 0;
+  ME_CUDA(cudaHostGetDevicePointer(reinterpret_cast<void**>(&g_debug_dev), g_debug_host, 0));
+  return ME_OK;
+}
+
+template <int BN, int BK, bool OUT_F32>
+int launch(const me_conv_desc* d, const void* x, const void* w, const float* bias, const void* residual, void* y,
+           cudaStream_t stream) {
+  using C = Cfg<BN, BK, OUT_F32>;
+  const int pad = (d->ksize - 1) / 2;
+  const int Ho = (d->h + 2 * pad - d->ksize) / d->stride + 1;
+  const int Wo = (d->w + 2 * pad - d->ksize) / d->stride + 1;
+  const long long M64 = 1LL * d->n * Ho * Wo;
+  ME_REQUIRE(M64 > 0 && M64 < (1LL << 31), "conv: pixel count out of range");
+  const int M = static_cast<int>(M64);
+  const int taps = d->ksize * d->ksize;
+  const int cin_pad = round_up(d->cin, BK);
+  const int ktot = taps * cin_pad;
+
+  ConvParams p{};
+  p.M = M;
+  p.Ho = Ho;
+  p.Wo = Wo;
+  p.stride = d->stride;
+  p.pad = pad;
+  p.kb_per_tap = cin_pad / BK;
+  p.num_kb = taps * p.kb_per_tap;
+  p.tiles_m = ceil_div(M, kBM);
+  p.tiles_n = ceil_div(d->cout, BN);
+  p.act = d->act;
+  p.has_res = (d->res_pitch > 0 && residual != nullptr) ? 1 : 0;
+  p.im2col = (d->ksize == 3) ? 1 : 0;
+  p.bias = bias;
+  int rc = ensure_debug_word();
+  if (rc != ME_OK) return rc;
+  p.debug = g_debug_dev;
+
+  int stages = (227 * 1024 - 1024 - C::STAGING_BYTES - C::TAIL_BYTES) / C::STAGE_BYTES;
+  if (stages > kMaxStages) stages = kMaxStages;
+  ME_REQUIRE(stages >= 2, "conv: not enough shared memory for a 2-stage pipeline");
+  p.stages = stages;
+  const int smem = C::smem_bytes(stages);
+
+  CUtensorMap tmA, tmB, tmC, tmR;
+  const CUtensorMapSwizzle swz_k = swizzle_for_row_bytes(BK * 2);
+  if (p.im2col) {
+    rc = encode_im2col_nhwc(&tmA, x, d->n, d->h, d->w, d->cin, d->in_pitch, d->ksize, pad, d->stride, BK, kBM, swz_k);
+  } else {
+    rc = encode_tiled_2d(&tmA, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, x, d->cin, M, d->in_pitch, BK, kBM, swz_k);
+  }
+  if (rc != ME_OK) return rc;
+  // weights: [cout rows][ktot cols]; rows past cout are zero-filled by TMA.
+  rc = encode_tiled_2d(&tmB, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, w, ktot, d->cout, ktot, BK, BN, swz_k);
+  if (rc != ME_OK) return rc;
+  const CUtensorMapSwizzle swz_o = swizzle_for_row_bytes(C::SUB_ROW_BYTES);
+  rc = encode_tiled_2d(&tmC, OUT_F32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, C::ESIZE, y,
+                       d->cout, M, d->out_pitch, C::SUB_COLS, kBM, swz_o);
+  if (rc != ME_OK) return rc;
+  if (p.has_res) {
+    ME_REQUIRE(!OUT_F32, "conv: residual add only with fp16 output");
+    rc = encode_tiled_2d(&tmR, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, residual, d->cout, M, d->res_pitch, C::SUB_COLS, kBM,
+                         swz_o);
+    if (rc != ME_OK) return rc;
+  } else {
+    tmR = tmC;
+  }
+
+  auto kern = conv_gemm_kernel<BN, BK, OUT_F32>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    ME_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    attr_set = true;
+  }
+  const int total = p.tiles_m * p.tiles_n;
+  int grid = sm_count();
+  if (grid <= 0) grid = 148;
+  if (grid > total) grid = total;
+  kern<<<grid, kThreads, smem, stream>>>(tmA, tmB, tmC, tmR, p);
+  ME_LAUNCH_CHECK();
+  return ME_OK;
+}
+
+}  // namespace
+}  // namespace me
+
+extern "C" {
+
+int me_conv_k_block(int cin) { return cin > 32 ? 64 : (cin > 16 ? 32 : 16); }
+int me_conv_cin_pad(int cin) { return me::round_up(cin, me_conv_k_block(cin)); }
+
+int me_debug_status(unsigned long long* host_word) {
+  if (host_word) *host_word = me::g_debug_host ? *me::g_debug_host : 0ull;
+  return ME_OK;
+}
+
+int me_conv_gemm(const me_conv_desc* d, const void* x, const void* w_packed, const float* bias, const void* residual,
+                 void* y, me_stream_t stream_) {
+  using namespace me;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  ME_REQUIRE(d && x && w_packed && bias && y, "conv: null argument");
+  ME_REQUIRE(d->ksize == 1 || d->ksize == 3, "conv: ksize %d unsupported (1 or 3)", d->ksize);
+  ME_REQUIRE(d->stride == 1 || (d->stride == 2 && d->ksize == 3), "conv: stride %d with ksize %d unsupported", d->stride,
+             d->ksize);
+  ME_REQUIRE(d->cout > 0 && d->cout % 32 == 0, "conv: cout %d must be a positive multiple of 32", d->cout);
+  ME_REQUIRE(d->cin > 0 && d->in_pitch >= d->cin && d->in_pitch % 8 == 0, "conv: bad cin/in_pitch %d/%d", d->cin,
+             d->in_pitch);
+  ME_REQUIRE(d->out_pitch >= d->cout && (d->out_pitch * (d->out_f32 ? 4 : 2)) % 16 == 0, "conv: bad out_pitch %d",
+             d->out_pitch);
+  ME_REQUIRE(d->n > 0 && d->h > 0 && d->w > 0, "conv: empty input");
+  const int bk = me_conv_k_block(d->cin);
+  const bool f32 = d->out_f32 != 0;
+  const int cout = d->cout;
+#define ME_GO(BN, BK, F32) return launch<BN, BK, F32>(d, x, w_packed, bias, residual, y, stream)
+  if (bk == 64) {
+    if (f32) {
+      if (cout >= 128) ME_GO(128, 64, true);
+      if (cout >= 64) ME_GO(64, 64, true);
+      ME_GO(32, 64, true);
+    }
+    if (cout >= 128) ME_GO(128, 64, false);
+    if (cout >= 64) ME_GO(64, 64, false);
+    ME_GO(32, 64, false);
+  } else if (bk == 32) {
+    ME_REQUIRE(!f32, "conv: fp32 output needs cin > 32");
+    if (cout >= 64) ME_GO(64, 32, false);
+    ME_GO(32, 32, false);
+  } else {
+    ME_REQUIRE(!f32, "conv: fp32 output needs cin > 32");
+    if (cout >= 64) ME_GO(64, 16, false);
+    ME_GO(32, 16, false);
+  }
+#undef ME_GO
+  return ME_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,330 @@
+// Confidence filter + class arg-max + batched NMS on the device, bit-compatible with
+// non_max_suppression_cpp (utils/utils.py:337-378) and the torchvision CPU ops it calls
+// (torchvision 0.26 ops/boxes.py:51-120 batched_nms; csrc/ops/cpu/nms_kernel.cpp greedy loop):
+//   * rows with conf >= conf_thresh, in row order, are the candidates;
+//   * class_conf / class_pred = first arg-max over the class scores (torch.max tie rule);
+//   * candidates are ordered by objectness, descending, stable (ties keep row order);
+//   * <= 1000 candidates: "coordinate trick" - boxes are offset by class * (max_coord + 1) in
+//     fp32 and one class-agnostic NMS runs on the offset boxes (the offsets perturb IoUs, so
+//     the same fp32 operations are replayed here);  > 1000: per-class NMS on the raw boxes;
+//   * IoU = inter / (area_i + area_j - inter), strict '>' against the threshold (as double);
+//   * the first max_det survivors in score order are returned.
+// All fp32 arithmetic uses the _rn intrinsics so no FMA contraction changes a rounding.
+#include "common.cuh"
+
+namespace me {
+namespace {
+
+constexpr int kSelThreads = 1024;
+constexpr int kMaxSmemKeys = 16384;
+
+struct Layout {
+  // per-image slices of the workspace (all sized by `rows`, keys by pow2(rows))
+  float* box;        // [rows][4] xyxy
+  float* conf;       // [rows]
+  float* cls_conf;   // [rows]
+  int* cls_idx;      // [rows]
+  float* sbox;       // [rows][4] boxes in sorted order (offset boxes on the coordinate-trick path)
+  float* sarea;      // [rows]
+  int* scls;         // [rows]
+  unsigned long long* keys;  // [pow2]
+};
+
+__host__ __device__ inline int next_pow2(int v) {
+  int p = 1;
+  while (p < v) p <<= 1;
+  return p;
+}
+
+__host__ __device__ inline size_t per_image_bytes(int rows) {
+  const size_t r = static_cast<size_t>(rows);
+  size_t b = r * 4 * 4 + r * 4 + r * 4 + r * 4 + r * 4 * 4 + r * 4 + r * 4;
+  b = (b + 15) & ~size_t(15);
+  b += static_cast<size_t>(next_pow2(rows)) * 8;
+  return (b + 255) & ~size_t(255);
+}
+
+__device__ inline Layout layout_for(void* ws, int rows, int img) {
+  uint8_t* p = static_cast<uint8_t*>(ws) + per_image_bytes(rows) * img;
+  Layout L;
+  const size_t r = static_cast<size_t>(rows);
+  L.box = reinterpret_cast<float*>(p);       p += r * 16;
+  L.conf = reinterpret_cast<float*>(p);      p += r * 4;
+  L.cls_conf = reinterpret_cast<float*>(p);  p += r * 4;
+  L.cls_idx = reinterpret_cast<int*>(p);     p += r * 4;
+  L.sbox = reinterpret_cast<float*>(p);      p += r * 16;
+  L.sarea = reinterpret_cast<float*>(p);     p += r * 4;
+  L.scls = reinterpret_cast<int*>(p);        p += r * 4;
+  p = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(p) + 15) & ~uintptr_t(15));
+  L.keys = reinterpret_cast<unsigned long long*>(p);
+  return L;
+}
+
+// One warp per prediction row: cxcywh -> xyxy, objectness filter, class max / first arg-max.
+__global__ void nms_prepare_kernel(float* __restrict__ pred, int n, int rows, int nc, float conf_thresh, int inplace,
+                                   void* ws) {
+  const int lane = threadIdx.x & 31;
+  const long long warp_id = (blockIdx.x * 1LL * blockDim.x + threadIdx.x) >> 5;
+  const long long nwarps = (1LL * gridDim.x * blockDim.x) >> 5;
+  const int attrs = 5 + nc;
+  for (long long rr = warp_id; rr < 1LL * n * rows; rr += nwarps) {
+    const int img = static_cast<int>(rr / rows);
+    const int row = static_cast<int>(rr - 1LL * img * rows);
+    float* src = pred + rr * attrs;
+    Layout L = layout_for(ws, rows, img);
+    float conf = 0.f;
+    if (lane == 0) {
+      const float cx = src[0], cy = src[1], w = src[2], h = src[3];
+      conf = src[4];
+      // xywh2xyxy, utils.py:68-74: x - w / 2, x + w / 2 (the halving is exact)
+      const float hw = __fdiv_rn(w, 2.f), hh = __fdiv_rn(h, 2.f);
+      const float x1 = __fsub_rn(cx, hw), y1 = __fsub_rn(cy, hh);
+      const float x2 = __fadd_rn(cx, hw), y2 = __fadd_rn(cy, hh);
+      L.box[row * 4 + 0] = x1;
+      L.box[row * 4 + 1] = y1;
+      L.box[row * 4 + 2] = x2;
+      L.box[row * 4 + 3] = y2;
+      L.conf[row] = conf;
+      if (inplace) {
+        src[0] = x1;
+        src[1] = y1;
+        src[2] = x2;
+        src[3] = y2;
+      }
+    }
+    conf = __shfl_sync(0xffffffffu, conf, 0);
+    if (!(conf >= conf_thresh)) continue;  // warp-uniform
+    float best = -INFINITY;
+    int best_i = 0x7fffffff;
+    for (int c = lane; c < nc; c += 32) {
+      const float v = src[5 + c];
+      if (v > best) {  // strict: the first maximum inside this lane's stride wins
+        best = v;
+        best_i = c;
+      }
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+      const float ov = __shfl_xor_sync(0xffffffffu, best, off);
+      const int oi = __shfl_xor_sync(0xffffffffu, best_i, off);
+      if (ov > best || (ov == best && oi < best_i)) {
+        best = ov;
+        best_i = oi;
+      }
+    }
+    if (lane == 0) {
+      L.cls_conf[row] = best;
+      L.cls_idx[row] = best_i == 0x7fffffff ? 0 : best_i;
+    }
+  }
+}
+
+__device__ __forceinline__ unsigned int score_desc_bits(float s) {
+  // monotone map float -> uint (ascending), then invert so that ascending keys = descending scores
+  unsigned int u = __float_as_uint(s);
+  u = (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+  return ~u;
+}
+
+// One block per image: compaction (row order) -> bitonic sort of (score desc, row asc) keys ->
+// greedy suppression, stopping once max_det boxes are kept.
+__global__ void __launch_bounds__(kSelThreads, 1)
+nms_select_kernel(const float* __restrict__ pred, int rows, int nc, float conf_thresh, double nms_thresh, int max_det,
+                  float* __restrict__ det, int* __restrict__ det_count, int* __restrict__ det_index, void* ws) {
+  extern __shared__ unsigned long long s_dyn[];
+  __shared__ int s_scan[kSelThreads / 32];
+  __shared__ int s_k;
+  __shared__ float s_red[kSelThreads / 32];
+  __shared__ float s_maxc;
+  __shared__ int s_keep[256];
+
+  const int img = blockIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+  Layout L = layout_for(ws, rows, img);
+  const int attrs = 5 + nc;
+  const int det_cols = 7 + nc;
+  const int pow2 = next_pow2(rows);
+  unsigned long long* keys = (pow2 <= kMaxSmemKeys) ? s_dyn : L.keys;
+  unsigned char* supp = reinterpret_cast<unsigned char*>(s_dyn + (pow2 <= kMaxSmemKeys ? pow2 : 0));
+
+  // ---- 1. order-preserving compaction of candidate rows into keys[0..k)
+  if (tid == 0) s_k = 0;
+  __syncthreads();
+  for (int base = 0; base < rows; base += kSelThreads) {
+    const int row = base + tid;
+    const bool pass = row < rows && (L.conf[row] >= conf_thresh);
+    const unsigned int ballot = __ballot_sync(0xffffffffu, pass);
+    if (lane == 0) s_scan[wid] = __popc(ballot);
+    __syncthreads();
+    if (wid == 0) {
+      int v = s_scan[lane];
+      int incl = v;
+#pragma unroll
+      for (int off = 1; off < 32; off <<= 1) {
+        const int t = __shfl_up_sync(0xffffffffu, incl, off);
+        if (lane >= off) incl += t;
+      }
+      s_scan[lane] = incl - v;  // exclusive prefix of the warp totals
+      if (lane == 31) s_red[0] = __int_as_float(incl);
+    }
+    __syncthreads();
+    const int k0 = s_k;
+    if (pass) {
+      const int pos = k0 + s_scan[wid] + __popc(ballot & ((1u << lane) - 1));
+      keys[pos] = (static_cast<unsigned long long>(score_desc_bits(L.conf[row])) << 32) | static_cast<unsigned int>(row);
+    }
+    __syncthreads();
+    if (tid == 0) s_k = k0 + __float_as_int(s_red[0]);
+    __syncthreads();
+  }
+  const int k = s_k;
+  if (k == 0) {
+    if (tid == 0) det_count[img] = 0;
+    return;
+  }
+
+  // ---- 2. bitonic sort of the k keys (padded with +inf keys to a power of two)
+  const int kp = next_pow2(k);
+  for (int i = k + tid; i < kp; i += kSelThreads) keys[i] = ~0ull;
+  __syncthreads();
+  for (int size = 2; size <= kp; size <<= 1) {
+    for (int stride = size >> 1; stride > 0; stride >>= 1) {
+      for (int t = tid; t < (kp >> 1); t += kSelThreads) {
+        const int lo = 2 * t - (t & (stride - 1));  // index with bit `stride` clear
+        const int hi = lo + stride;
+        const bool asc = (lo & size) == 0;
+        const unsigned long long a = keys[lo], b = keys[hi];
+        if ((a > b) == asc) {
+          keys[lo] = b;
+          keys[hi] = a;
+        }
+      }
+      __syncthreads();
+    }
+  }
+
+  // ---- 3. boxes in sorted order; coordinate trick when boxes.numel() <= 4000
+  const bool trick = (k * 4) <= 4000;
+  float maxc = -INFINITY;
+  if (trick) {
+    for (int i = tid; i < k; i += kSelThreads) {
+      const int row = static_cast<int>(keys[i] & 0xffffffffu);
+      const float4 b = *reinterpret_cast<const float4*>(L.box + row * 4);
+      maxc = fmaxf(fmaxf(maxc, fmaxf(b.x, b.y)), fmaxf(b.z, b.w));
+    }
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) maxc = fmaxf(maxc, __shfl_xor_sync(0xffffffffu, maxc, off));
+    if (lane == 0) s_red[wid] = maxc;
+    __syncthreads();
+    if (wid == 0) {
+      float v = s_red[lane];
+#pragma unroll
+      for (int off = 16; off > 0; off >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, off));
+      if (lane == 0) s_maxc = v;
+    }
+    __syncthreads();
+  }
+  const float span = trick ? __fadd_rn(s_maxc, 1.f) : 0.f;  // max_coordinate + 1
+  for (int i = tid; i < k; i += kSelThreads) {
+    const int row = static_cast<int>(keys[i] & 0xffffffffu);
+    float4 b = *reinterpret_cast<const float4*>(L.box + row * 4);
+    const int cls = L.cls_idx[row];
+    if (trick) {
+      const float off = __fmul_rn(static_cast<float>(cls), span);  // idxs.to(boxes) * (max + 1)
+      b.x = __fadd_rn(b.x, off);
+      b.y = __fadd_rn(b.y, off);
+      b.z = __fadd_rn(b.z, off);
+      b.w = __fadd_rn(b.w, off);
+    }
+    *reinterpret_cast<float4*>(L.sbox + i * 4) = b;
+    L.sarea[i] = __fmul_rn(__fsub_rn(b.z, b.x), __fsub_rn(b.w, b.y));
+    L.scls[i] = cls;
+    supp[i] = 0;
+  }
+  __syncthreads();
+
+  // ---- 4. greedy suppression in score order
+  int kept = 0;
+  for (int i = 0; i < k; ++i) {
+    if (supp[i]) continue;  // block-uniform
+    if (tid == 0) s_keep[kept] = i;
+    ++kept;
+    if (kept == max_det) break;
+    const float4 bi = *reinterpret_cast<const float4*>(L.sbox + i * 4);
+    const float ai = L.sarea[i];
+    const int ci = L.scls[i];
+    for (int j = i + 1 + tid; j < k; j += kSelThreads) {
+      if (supp[j]) continue;
+      if (!trick && L.scls[j] != ci) continue;
+      const float4 bj = *reinterpret_cast<const float4*>(L.sbox + j * 4);
+      const float xx1 = fmaxf(bi.x, bj.x), yy1 = fmaxf(bi.y, bj.y);
+      const float xx2 = fminf(bi.z, bj.z), yy2 = fminf(bi.w, bj.w);
+      const float w = fmaxf(0.f, __fsub_rn(xx2, xx1)), h = fmaxf(0.f, __fsub_rn(yy2, yy1));
+      const float inter = __fmul_rn(w, h);
+      const float ovr = __fdiv_rn(inter, __fsub_rn(__fadd_rn(ai, L.sarea[j]), inter));
+      if (static_cast<double>(ovr) > nms_thresh) supp[j] = 1;
+    }
+    __syncthreads();
+  }
+  __syncthreads();
+
+  // ---- 5. gather survivors: [x1,y1,x2,y2,conf,class_conf,class_pred,cls...]
+  if (tid == 0) det_count[img] = kept;
+  float* out = det + 1LL * img * max_det * det_cols;
+  for (int e = tid; e < kept * det_cols; e += kSelThreads) {
+    const int d = e / det_cols, c = e - d * det_cols;
+    const int row = static_cast<int>(keys[s_keep[d]] & 0xffffffffu);
+    float v;
+    if (c < 4) v = L.box[row * 4 + c];
+    else if (c == 4) v = L.conf[row];
+    else if (c == 5) v = L.cls_conf[row];
+    else if (c == 6) v = static_cast<float>(L.cls_idx[row]);
+    else v = pred[(1LL * img * rows + row) * attrs + 5 + (c - 7)];
+    out[e] = v;
+  }
+  for (int d = tid; d < kept; d += kSelThreads)
+    det_index[1LL * img * max_det + d] = static_cast<int>(keys[s_keep[d]] & 0xffffffffu);
+}
+
+}  // namespace
+}  // namespace me
+
+extern "C" {
+
+size_t me_filter_nms_workspace(int n, int rows, int num_classes) {
+  (void)num_classes;
+  if (n <= 0 || rows <= 0) return 0;
+  return me::per_image_bytes(rows) * static_cast<size_t>(n);
+}
+
+int me_filter_nms(float* pred, int n, int rows, int num_classes, float conf_thresh, double nms_thresh, int max_det,
+                  int xyxy_inplace, float* det, int* det_count, int* det_index, void* workspace,
+                  size_t workspace_bytes, me_stream_t stream_) {
+  using namespace me;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  ME_REQUIRE(pred && det && det_count && det_index && workspace, "filter_nms: null argument");
+  ME_REQUIRE(n > 0 && rows > 0 && num_classes >= 1, "filter_nms: empty input");
+  ME_REQUIRE(max_det >= 1 && max_det <= 256, "filter_nms: max_det %d out of range (1..256)", max_det);
+  ME_REQUIRE(rows <= (1 << 20), "filter_nms: too many rows");
+  ME_REQUIRE(workspace_bytes >= me_filter_nms_workspace(n, rows, num_classes), "filter_nms: workspace too small");
+  const long long warps = 1LL * n * rows;
+  long long blocks = (warps * 32 + 255) / 256;
+  if (blocks > 148 * 32) blocks = 148 * 32;
+  nms_prepare_kernel<<<static_cast<int>(blocks), 256, 0, stream>>>(pred, n, rows, num_classes, conf_thresh,
+                                                                   xyxy_inplace, workspace);
+  ME_LAUNCH_CHECK();
+  const int pow2 = next_pow2(rows);
+  const size_t smem = (pow2 <= kMaxSmemKeys ? static_cast<size_t>(pow2) * 8 : 0) + static_cast<size_t>(rows) + 16;
+  static bool attr_set = false;
+  if (!attr_set) {
+    ME_CUDA(cudaFuncSetAttribute(nms_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    attr_set = true;
+  }
+  ME_REQUIRE(smem <= 200 * 1024, "filter_nms: %d rows need %zu B of shared memory", rows, smem);
+  nms_select_kernel<<<n, kSelThreads, smem, stream>>>(pred, rows, num_classes, conf_thresh, nms_thresh, max_det, det,
+                                                      det_count, det_index, workspace);
+  ME_LAUNCH_CHECK();
+  return ME_OK;
+}
+
+}  // extern "C"

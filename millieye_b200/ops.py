@@ -1,0 +1,238 @@
+"""torch-tensor front ends of the C-ABI entry points (include/millieye_b200.h).
+
+These are plumbing only: they check devices/dtypes, pass raw device pointers and the current
+CUDA stream to the library and raise on any error code.  No arithmetic happens here.
+"""
+import ctypes
+from ctypes import byref, c_float
+
+import torch
+
+from . import _lib
+from ._lib import ME_ACT_LEAKY, ME_ACT_LINEAR, ME_ACT_SIGMOID, ConvDesc, HeadWeights, check, ptr, stream_ptr
+
+__all__ = [
+    "ME_ACT_LINEAR", "ME_ACT_LEAKY", "ME_ACT_SIGMOID", "round_up", "PackedConv", "pack_conv", "conv_gemm",
+    "FirstConv", "pack_first_conv", "conv_first", "maxpool2", "upsample2", "copy_channels", "nhwc_to_nchw_f32",
+    "nchw_f32_to_nhwc", "yolo_decode", "filter_nms", "psroi_align", "roi_align", "build_proposals", "fusion_heads",
+    "finalize_output",
+]
+
+
+def round_up(a, b):
+    return (a + b - 1) // b * b
+
+
+def _need_cuda(*tensors):
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise _lib.MeError("millieye_b200 runs on CUDA tensors only (no CPU fallback exists)")
+
+
+def _f32(t):
+    return None if t is None else t.detach().to(dtype=torch.float32).contiguous()
+
+
+class PackedConv:
+    """Device-resident, BN-folded fp16 weights of one conv in the GEMM kernel's layout."""
+
+    def __init__(self, w, bias, cin, cout, cout_pad, ksize):
+        self.w, self.bias, self.cin, self.cout, self.cout_pad, self.ksize = w, bias, cin, cout, cout_pad, ksize
+
+
+def pack_conv(weight, conv_bias=None, bn=None, cout_pad=None):
+    """weight: OIHW fp32 (cuda). bn: None or (gamma, beta, running_mean, running_var, eps)."""
+    L = _lib.lib()
+    weight = _f32(weight)
+    _need_cuda(weight)
+    cout, cin, kh, kw = weight.shape
+    assert kh == kw
+    cout_pad = cout_pad or round_up(cout, 32)
+    cin_pad = L.me_conv_cin_pad(cin)
+    wp = torch.empty((cout_pad, kh * kw * cin_pad), dtype=torch.float16, device=weight.device)
+    bias = torch.empty((round_up(cout_pad, 256),), dtype=torch.float32, device=weight.device)
+    cb = _f32(conv_bias)
+    g = b = m = v = None
+    eps = 0.0
+    if bn is not None:
+        g, b, m, v = (_f32(t) for t in bn[:4])
+        eps = float(bn[4])
+    check(L.me_pack_conv_weights(ptr(weight), ptr(cb), ptr(g), ptr(b), ptr(m), ptr(v), eps, cout, cin, kh, cout_pad,
+                                 ptr(wp), ptr(bias), stream_ptr()), "me_pack_conv_weights")
+    return PackedConv(wp, bias, cin, cout, cout_pad, kh)
+
+
+def conv_gemm(x, packed, n, h, w, in_pitch, out, out_pitch, stride=1, act=ME_ACT_LEAKY, residual=None, res_pitch=0,
+              cin=None, cout=None, out_f32=False):
+    """x / out / residual are NHWC fp16 buffers (any tensor whose data_ptr is the first pixel of the view)."""
+    _need_cuda(x, out, residual)
+    d = ConvDesc(n=n, h=h, w=w, cin=cin or packed.cin, in_pitch=in_pitch, cout=cout or packed.cout_pad,
+                 out_pitch=out_pitch, ksize=packed.ksize, stride=stride, act=act, out_f32=1 if out_f32 else 0,
+                 res_pitch=res_pitch if residual is not None else 0)
+    check(_lib.lib().me_conv_gemm(byref(d), ptr(x), ptr(packed.w), ptr(packed.bias), ptr(residual), ptr(out),
+                                  stream_ptr()), "me_conv_gemm")
+    return out
+
+
+class FirstConv:
+    def __init__(self, w, bias, cin, cout):
+        self.w, self.bias, self.cin, self.cout = w, bias, cin, cout
+
+
+def pack_first_conv(weight, conv_bias=None, bn=None):
+    L = _lib.lib()
+    weight = _f32(weight)
+    _need_cuda(weight)
+    cout, cin, kh, kw = weight.shape
+    assert kh == 3 and kw == 3
+    wf = torch.empty_like(weight)
+    bias = torch.empty((cout,), dtype=torch.float32, device=weight.device)
+    cb = _f32(conv_bias)
+    g = b = m = v = None
+    eps = 0.0
+    if bn is not None:
+        g, b, m, v = (_f32(t) for t in bn[:4])
+        eps = float(bn[4])
+    check(L.me_fold_first_weights(ptr(weight), ptr(cb), ptr(g), ptr(b), ptr(m), ptr(v), eps, cout, cin, ptr(wf),
+                                  ptr(bias), stream_ptr()), "me_fold_first_weights")
+    return FirstConv(wf, bias, cin, cout)
+
+
+def conv_first(x_nchw, first, out, out_pitch, act=ME_ACT_LEAKY):
+    _need_cuda(x_nchw, out)
+    assert x_nchw.dtype == torch.float32 and x_nchw.is_contiguous()
+    n, c, h, w = x_nchw.shape
+    assert c == first.cin
+    check(_lib.lib().me_conv_first(ptr(x_nchw), ptr(first.w), ptr(first.bias), ptr(out), n, h, w, c, first.cout,
+                                   out_pitch, act, stream_ptr()), "me_conv_first")
+    return out
+
+
+def maxpool2(x, out, n, h, w, c, in_pitch, out_pitch, stride):
+    _need_cuda(x, out)
+    check(_lib.lib().me_maxpool2(ptr(x), ptr(out), n, h, w, c, in_pitch, out_pitch, stride, stream_ptr()),
+          "me_maxpool2")
+    return out
+
+
+def upsample2(x, out, n, h, w, c, in_pitch, out_pitch):
+    _need_cuda(x, out)
+    check(_lib.lib().me_upsample2(ptr(x), ptr(out), n, h, w, c, in_pitch, out_pitch, stream_ptr()), "me_upsample2")
+    return out
+
+
+def copy_channels(x, out, pixels, c, in_pitch, out_pitch):
+    _need_cuda(x, out)
+    check(_lib.lib().me_copy_channels(ptr(x), ptr(out), pixels, c, in_pitch, out_pitch, stream_ptr()),
+          "me_copy_channels")
+    return out
+
+
+def nhwc_to_nchw_f32(x, n, h, w, c, in_pitch, out=None):
+    _need_cuda(x)
+    if out is None:
+        out = torch.empty((n, c, h, w), dtype=torch.float32, device=x.device)
+    check(_lib.lib().me_nhwc_to_nchw_f32(ptr(x), ptr(out), n, h, w, c, in_pitch, stream_ptr()), "me_nhwc_to_nchw_f32")
+    return out
+
+
+def nchw_f32_to_nhwc(x, out_pitch=None, out=None):
+    _need_cuda(x)
+    assert x.dtype == torch.float32 and x.is_contiguous()
+    n, c, h, w = x.shape
+    out_pitch = out_pitch or round_up(c, 8)
+    if out is None:
+        out = torch.empty((n, h, w, out_pitch), dtype=torch.float16, device=x.device)
+    check(_lib.lib().me_nchw_f32_to_nhwc(ptr(x), ptr(out), n, h, w, c, out_pitch, stream_ptr()), "me_nchw_f32_to_nhwc")
+    return out
+
+
+def yolo_decode(logits, pitch, out, n, g, anchors, num_classes, stride, rows_total, row_offset):
+    _need_cuda(logits, out)
+    assert logits.dtype == torch.float32 and out.dtype == torch.float32
+    flat = [float(v) for wh in anchors for v in wh]
+    arr = (c_float * len(flat))(*flat)
+    check(_lib.lib().me_yolo_decode(ptr(logits), pitch, ptr(out), n, g, len(anchors), num_classes, arr, float(stride),
+                                    rows_total, row_offset, stream_ptr()), "me_yolo_decode")
+    return out
+
+
+class NmsBuffers:
+    """Reusable outputs + workspace of filter_nms for one (n, rows, classes) shape."""
+
+    def __init__(self, n, rows, num_classes, max_det, device):
+        L = _lib.lib()
+        self.n, self.rows, self.nc, self.max_det = n, rows, num_classes, max_det
+        self.det = torch.zeros((n, max_det, 7 + num_classes), dtype=torch.float32, device=device)
+        self.count = torch.zeros((n,), dtype=torch.int32, device=device)
+        self.index = torch.zeros((n, max_det), dtype=torch.int32, device=device)
+        self.ws_bytes = L.me_filter_nms_workspace(n, rows, num_classes)
+        self.ws = torch.empty((self.ws_bytes,), dtype=torch.uint8, device=device)
+
+
+def filter_nms(pred, conf_thresh, nms_thresh=0.5, max_det=200, xyxy_inplace=True, buffers=None):
+    """pred: (n, rows, 5+C) fp32 cuda, contiguous. Returns the NmsBuffers holding det/count/index."""
+    _need_cuda(pred)
+    assert pred.dtype == torch.float32 and pred.is_contiguous() and pred.dim() == 3
+    n, rows, attrs = pred.shape
+    nc = attrs - 5
+    if buffers is None:
+        buffers = NmsBuffers(n, rows, nc, max_det, pred.device)
+    check(_lib.lib().me_filter_nms(ptr(pred), n, rows, nc, float(conf_thresh), float(nms_thresh), max_det,
+                                   1 if xyxy_inplace else 0, ptr(buffers.det), ptr(buffers.count), ptr(buffers.index),
+                                   ptr(buffers.ws), buffers.ws_bytes, stream_ptr()), "me_filter_nms")
+    return buffers
+
+
+def _count_ptr(counts, index):
+    return ctypes.c_void_p(counts.data_ptr() + 4 * index)
+
+
+def psroi_align(feat, n, h, w, pitch, out_channels, pooled, scale, rois, counts, cap, out, out_pitch):
+    _need_cuda(feat, rois, counts, out)
+    check(_lib.lib().me_psroi_align(ptr(feat), n, h, w, pitch, out_channels, pooled, float(scale), ptr(rois),
+                                    _count_ptr(counts, 1), cap, ptr(out), out_pitch, stream_ptr()), "me_psroi_align")
+    return out
+
+
+def roi_align(feat, n, h, w, pitch, channels, pooled, scale, rois, counts, cap, out, out_pitch):
+    _need_cuda(feat, rois, counts, out)
+    check(_lib.lib().me_roi_align(ptr(feat), n, h, w, pitch, channels, pooled, float(scale), ptr(rois),
+                                  _count_ptr(counts, 1), cap, ptr(out), out_pitch, stream_ptr()), "me_roi_align")
+    return out
+
+
+def build_proposals(det, det_count, class_idx, radar_boxes, img_size, img_boxes, rois, counts, cap):
+    _need_cuda(det, det_count, img_boxes, rois, counts)
+    n, max_det, det_cols = det.shape
+    nr = 0 if radar_boxes is None else int(radar_boxes.shape[0])
+    check(_lib.lib().me_build_proposals(ptr(det), ptr(det_count), n, max_det, det_cols, class_idx,
+                                        ptr(radar_boxes) if nr else None, nr, float(img_size), ptr(img_boxes),
+                                        ptr(rois), ptr(counts), cap, stream_ptr()), "me_build_proposals")
+
+
+def fusion_heads(hidden, hidden_pitch, crop, crop_pitch, head_weights, img_boxes, counts, cap, regress, refine, mask):
+    _need_cuda(hidden, crop, img_boxes, counts, regress, refine, mask)
+    check(_lib.lib().me_fusion_heads(ptr(hidden), hidden_pitch, ptr(crop), crop_pitch, byref(head_weights),
+                                     ptr(img_boxes), ptr(counts), cap, ptr(regress), ptr(refine), ptr(mask),
+                                     stream_ptr()), "me_fusion_heads")
+
+
+def finalize_output(img_boxes, rois, refine, regress, mask, counts, cap, thr_img, thr_radar, regress_boxes, out,
+                    out_count, ws):
+    _need_cuda(img_boxes, rois, refine, regress, mask, counts, out, out_count, ws)
+    check(_lib.lib().me_finalize_output(ptr(img_boxes), ptr(rois), ptr(refine), ptr(regress), ptr(mask), ptr(counts),
+                                        cap, float(thr_img), float(thr_radar), 1 if regress_boxes else 0, ptr(out),
+                                        ptr(out_count), ptr(ws), ws.numel() * ws.element_size(), stream_ptr()),
+          "me_finalize_output")
+
+
+def make_head_weights(tensors):
+    """tensors: dict name -> fp32 cuda tensor for every field of me_head_weights."""
+    hw = HeadWeights()
+    for name, _ in HeadWeights._fields_:
+        t = tensors[name]
+        _need_cuda(t)
+        assert t.dtype == torch.float32 and t.is_contiguous()
+        setattr(hw, name, t.data_ptr())
+    return hw
