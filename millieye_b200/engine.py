@@ -1,0 +1,258 @@
+"""Execution plan of the Darknet forward on the B200 kernels.
+
+A plan is built once per (batch, image size): BN is folded and weights are packed into the GEMM
+kernel's layout, every block gets an NHWC fp16 view (buffer, channel offset, pitch) - route/concat
+and shortcut are resolved at plan time into channel slices and a fused residual add, so the only
+kernels left are conv GEMMs, the 3-channel first conv, max-pool, upsample and the YOLO decode -
+and the launch sequence is captured in a CUDA graph that later forwards replay.
+"""
+import torch
+
+from . import ops
+from ._lib import ME_ACT_LEAKY, ME_ACT_LINEAR, MeError
+
+
+class View:
+    """NHWC fp16/fp32 activation view: `c` channels starting at channel `off` of `buf` (pitch = buf.shape[-1])."""
+
+    def __init__(self, buf, off, c, h, w, real_c=None):
+        self.buf, self.off, self.c, self.h, self.w = buf, off, c, h, w
+        self.real_c = real_c if real_c is not None else c
+        self.pitch = buf.shape[-1]
+
+    @property
+    def t(self):
+        """Tensor whose data_ptr is the first element of the view."""
+        return self.buf.view(-1)[self.off:]
+
+
+def describe_blocks(module_defs):
+    """Static per-block description (same rules as create_modules, reference yolov3/models.py:12-79)."""
+    hyper = module_defs[0]
+    chans = [int(hyper["channels"])]
+    blocks = []
+    for i, d in enumerate(module_defs[1:]):
+        kind = d["type"]
+        b = {"type": kind}
+        if kind == "convolutional":
+            b.update(bn=int(d["batch_normalize"]), filters=int(d["filters"]), size=int(d["size"]),
+                     stride=int(d["stride"]), leaky=(d["activation"] == "leaky"), cin=chans[-1])
+            out_c = b["filters"]
+        elif kind == "maxpool":
+            b.update(size=int(d["size"]), stride=int(d["stride"]))
+            out_c = chans[-1]
+        elif kind == "upsample":
+            b.update(stride=int(d["stride"]))
+            out_c = chans[-1]
+        elif kind == "route":
+            b.update(layers=[int(v) if int(v) >= 0 else i + int(v) for v in d["layers"].split(",")])
+            out_c = sum(chans[1:][j] for j in b["layers"])
+        elif kind == "shortcut":
+            b.update(src=i + int(d["from"]))
+            out_c = chans[1:][b["src"]]
+        elif kind == "yolo":
+            mask = [int(v) for v in d["mask"].split(",")]
+            flat = [int(v) for v in d["anchors"].split(",")]
+            pairs = list(zip(flat[0::2], flat[1::2]))
+            b.update(anchors=[pairs[j] for j in mask], classes=int(d["classes"]))
+            out_c = chans[-1]
+        else:
+            raise MeError(f"cfg block type '{kind}' is not part of the supported Darknet subset")
+        b["out_c"] = out_c
+        blocks.append(b)
+        chans.append(out_c)
+    return hyper, blocks
+
+
+class DarknetPlan:
+    """Buffers, packed weights and the op list for one (n, size) shape on one device."""
+
+    def __init__(self, blocks, tensors, n, size, device, feature_tap, in_channels=3):
+        self.blocks, self.n, self.size, self.device = blocks, n, size, device
+        self.feature_tap = feature_tap
+        self.ops = []          # list of zero-arg callables enqueueing one kernel each
+        self.graph = None
+        self.launches = 0
+        self._tensors = tensors
+        self.x_in = torch.zeros((n, in_channels, size, size), dtype=torch.float32, device=device)
+        self._build()
+
+    # ------------------------------------------------------------------ plan construction
+    def _new(self, h, w, c, dtype=torch.float16):
+        return torch.zeros((self.n, h, w, c), dtype=dtype, device=self.device)
+
+    def _build(self):
+        blocks, n = self.blocks, self.n
+        nb = len(blocks)
+        # who reads each block's output (besides the next block)
+        readers = {i: [] for i in range(nb)}
+        for i, b in enumerate(blocks):
+            if b["type"] == "route":
+                for j in b["layers"]:
+                    readers[j].append(i)
+            elif b["type"] == "shortcut":
+                readers[b["src"]].append(i)
+                readers[i - 1].append(i)
+        # spatial size of every block output
+        hw = []
+        s = self.size
+        for i, b in enumerate(blocks):
+            t = b["type"]
+            if t == "convolutional":
+                pad = (b["size"] - 1) // 2
+                s = (s + 2 * pad - b["size"]) // b["stride"] + 1
+            elif t == "maxpool":
+                s = s // 2 if b["stride"] == 2 else s
+            elif t == "upsample":
+                s = s * b["stride"]
+            elif t == "route":
+                s = hw[b["layers"][0]]
+            elif t == "shortcut":
+                s = hw[i - 1]
+            hw.append(s)
+        self.hw = hw
+
+        # two-input routes become channel slices of one concat buffer their producers write into
+        target = {}     # block index -> (concat buffer, channel offset)
+        for i, b in enumerate(blocks):
+            if b["type"] == "route" and len(b["layers"]) > 1:
+                total = sum(blocks[j]["out_c"] for j in b["layers"])
+                buf = self._new(hw[i], hw[i], total)
+                off = 0
+                for j in b["layers"]:
+                    if j in target:
+                        raise MeError("a block feeds two concats; unsupported cfg")
+                    if blocks[j]["out_c"] % 32 != 0:
+                        raise MeError("concat inputs must have a multiple of 32 channels")
+                    target[j] = (buf, off)
+                    off += blocks[j]["out_c"]
+                b["_concat"] = buf
+
+        # yolo output rows
+        self.attrs = None
+        rows_total = 0
+        for i, b in enumerate(blocks):
+            if b["type"] == "yolo":
+                rows_total += len(b["anchors"]) * hw[i] * hw[i]
+                self.attrs = 5 + b["classes"]
+        self.rows_total = rows_total
+        self.yolo_out = torch.zeros((n, rows_total, self.attrs), dtype=torch.float32, device=self.device)
+
+        views = [None] * nb
+        row_off = 0
+        self.feature_view = None
+        for i, b in enumerate(blocks):
+            t = b["type"]
+            src = views[i - 1] if i > 0 else None
+            s_out = hw[i]
+            if t == "convolutional":
+                fuse_res = None
+                nxt = blocks[i + 1] if i + 1 < nb else None
+                if nxt is not None and nxt["type"] == "shortcut":
+                    if readers[i] != [i + 1]:
+                        raise MeError("conv feeding a shortcut is also read elsewhere; unsupported cfg")
+                    fuse_res = nxt["src"]
+                is_head = nxt is not None and nxt["type"] == "yolo"
+                out_idx = i + 1 if fuse_res is not None else i
+                cout = b["filters"]
+                if out_idx in target:
+                    buf, off = target[out_idx]
+                    ov = View(buf, off, cout, s_out, s_out)
+                else:
+                    # the SIMT first conv writes exactly cout channels; the GEMM writes whole 32-wide groups
+                    cpad = ops.round_up(cout, 8 if i == 0 else 32)
+                    ov = View(self._new(s_out, s_out, cpad, torch.float32 if is_head else torch.float16), 0, cpad,
+                              s_out, s_out, real_c=cout)
+                self._add_conv(i, b, src, ov, fuse_res, views, is_head)
+                views[i] = ov
+                if fuse_res is not None:
+                    b["_fused_into_next"] = True
+            elif t == "shortcut":
+                if not blocks[i - 1].get("_fused_into_next"):
+                    raise MeError("shortcut without a preceding conv; unsupported cfg")
+                views[i] = views[i - 1]
+            elif t == "maxpool":
+                if b["size"] != 2:
+                    raise MeError("only 2x2 max-pool is supported")
+                ov = View(self._new(s_out, s_out, ops.round_up(src.c, 8)), 0, src.c, s_out, s_out, real_c=src.real_c)
+                self._add(lambda sv=src, o=ov, st=b["stride"]: ops.maxpool2(sv.t, o.t, n, sv.h, sv.w, ops.round_up(sv.c, 8),
+                                                                            sv.pitch, o.pitch, st))
+                views[i] = ov
+            elif t == "upsample":
+                if b["stride"] != 2:
+                    raise MeError("only x2 upsample is supported")
+                if i in target:
+                    buf, off = target[i]
+                    ov = View(buf, off, src.c, s_out, s_out)
+                else:
+                    ov = View(self._new(s_out, s_out, ops.round_up(src.c, 8)), 0, src.c, s_out, s_out)
+                self._add(lambda sv=src, o=ov: ops.upsample2(sv.t, o.t, n, sv.h, sv.w, sv.c, sv.pitch, o.pitch))
+                views[i] = ov
+            elif t == "route":
+                if len(b["layers"]) == 1:
+                    views[i] = views[b["layers"][0]]
+                else:
+                    buf = b["_concat"]
+                    views[i] = View(buf, 0, buf.shape[-1], s_out, s_out)
+            elif t == "yolo":
+                g = s_out
+                stride = self.size / g
+                self._add(lambda sv=src, bb=b, g=g, st=stride, ro=row_off: ops.yolo_decode(
+                    sv.t, sv.pitch, self.yolo_out, n, g, bb["anchors"], bb["classes"], st, self.rows_total, ro))
+                row_off += len(b["anchors"]) * g * g
+                views[i] = src
+            if i == self.feature_tap:
+                self.feature_view = views[i]
+        self.views = views
+        if self.feature_tap is not None and self.feature_view is not None and self.feature_view.buf.dtype != torch.float16:
+            raise MeError("feature tap must be an fp16 activation")
+
+    def _bn_of(self, i):
+        p = f"module_list.{i}.batch_norm_{i}."
+        t = self._tensors
+        return (t[p + "weight"], t[p + "bias"], t[p + "running_mean"], t[p + "running_var"], 1e-5)
+
+    def _add(self, fn):
+        self.ops.append(fn)
+
+    def _add_conv(self, i, b, src, ov, fuse_res, views, is_head):
+        n = self.n
+        t = self._tensors
+        w = t[f"module_list.{i}.conv_{i}.weight"]
+        bias = t.get(f"module_list.{i}.conv_{i}.bias")
+        bn = self._bn_of(i) if b["bn"] else None
+        act = ME_ACT_LEAKY if b["leaky"] else ME_ACT_LINEAR
+        if i == 0:
+            if b["size"] != 3 or b["stride"] != 1 or b["cin"] > 4:
+                raise MeError("first layer must be a 3x3/stride-1 conv over <= 4 input channels")
+            first = ops.pack_first_conv(w, bias, bn)
+            self._keep = getattr(self, "_keep", []) + [first]
+            self._add(lambda f=first, o=ov, a=act: ops.conv_first(self.x_in, f, o.t, o.pitch, a))
+            return
+        packed = ops.pack_conv(w, bias, bn, cout_pad=ops.round_up(b["filters"], 32))
+        res_v = views[fuse_res] if fuse_res is not None else None
+        self._keep = getattr(self, "_keep", []) + [packed]
+        self._add(lambda sv=src, p=packed, o=ov, st=b["stride"], a=act, rv=res_v, f32=is_head: ops.conv_gemm(
+            sv.t, p, n, sv.h, sv.w, sv.pitch, o.t, o.pitch, stride=st, act=a,
+            residual=None if rv is None else rv.t, res_pitch=0 if rv is None else rv.pitch,
+            cin=sv.real_c if sv.real_c != sv.c else sv.c, cout=p.cout_pad, out_f32=f32))
+
+    # ------------------------------------------------------------------ execution
+    def enqueue(self):
+        for fn in self.ops:
+            fn()
+        self.launches = len(self.ops)
+
+    def run(self, use_graph=True):
+        """Inputs must already be in self.x_in. Enqueues (or replays) the whole forward."""
+        if not use_graph:
+            self.enqueue()
+            return
+        if self.graph is None:
+            self.enqueue()  # warm-up: lazy one-time initialisation inside the library
+            torch.cuda.synchronize(self.device)
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self.enqueue()
+            self.graph = g
+        self.graph.replay()

@@ -1,0 +1,195 @@
+"""Drop-in for the reference's yolov3/models.py: `Darknet(config_path)` with the same constructor,
+forward signature, return structure and state_dict key names
+(module_list.{i}.conv_{i}.weight, module_list.{i}.batch_norm_{i}.*), executed by the sm_100a kernels
+of libmillieye_b200 instead of nn.Module calls.
+
+The nn.Conv2d / nn.BatchNorm2d objects below only own parameters (checkpoint compatibility,
+`load_state_dict`, `load_darknet_weights`); their forward is never used.  There is no CPU or
+eager-PyTorch fallback: a forward on a non-CUDA tensor, or without the built library, raises.
+"""
+import numpy as np
+import torch
+import torch.nn as nn
+
+from . import ops
+from ._lib import MeError
+from .engine import DarknetPlan, describe_blocks
+from .parse_config import parse_model_config
+
+
+class _Holder(nn.Module):
+    """Parameter-free placeholder keeping the reference's module names (route_, shortcut_, yolo_ ...)."""
+
+    def __init__(self, **attrs):
+        super().__init__()
+        for k, v in attrs.items():
+            setattr(self, k, v)
+
+
+class YOLOLayer(_Holder):
+    """Detection layer placeholder; the decode runs in me_yolo_decode (reference models.py:102-179)."""
+
+    def __init__(self, anchors, num_classes, img_dim=416):
+        super().__init__(anchors=anchors, num_anchors=len(anchors), num_classes=num_classes, img_dim=img_dim,
+                         metrics={}, ignore_thres=0.5, obj_scale=1, noobj_scale=100, grid_size=0)
+
+
+def create_modules(module_defs):
+    """Parameter containers named exactly like the reference's create_modules (models.py:12-79).
+    Consumes module_defs[0] ([net]) like the reference does (pop)."""
+    hyperparams = module_defs.pop(0)
+    _, blocks = describe_blocks([hyperparams] + module_defs)
+    module_list = nn.ModuleList()
+    for i, b in enumerate(blocks):
+        seq = nn.Sequential()
+        kind = b["type"]
+        if kind == "convolutional":
+            seq.add_module(f"conv_{i}", nn.Conv2d(b["cin"], b["filters"], b["size"], b["stride"], (b["size"] - 1) // 2,
+                                                  bias=not b["bn"]))
+            if b["bn"]:
+                seq.add_module(f"batch_norm_{i}", nn.BatchNorm2d(b["filters"], momentum=0.9, eps=1e-5))
+            if b["leaky"]:
+                seq.add_module(f"leaky_{i}", nn.LeakyReLU(0.1))
+        elif kind == "yolo":
+            seq.add_module(f"yolo_{i}", YOLOLayer(b["anchors"], b["classes"], int(hyperparams["height"])))
+        else:
+            seq.add_module(f"{kind}_{i}", _Holder())
+        module_list.append(seq)
+    return hyperparams, module_list
+
+
+class Darknet(nn.Module):
+    """YOLOv3 / YOLOv3-tiny detector. forward(x) -> (featuremap, yolo_outputs) like reference models.py:247-267.
+
+    featuremap: (N, C, S/16, S/16) fp32 - output of the block named conv_8 (reference :254-255).  On
+      cfgs where block 8 is not a conv (yolov3.cfg: the reference itself raises there)
+      set `feature_tap` to a block index, or leave None to get an empty tensor.
+    yolo_outputs: (N, sum A*G*G, 5+C) fp32, rows [cx, cy, w, h, conf, cls...] in pixels.
+    """
+
+    def __init__(self, config_path, img_size=416):
+        super().__init__()
+        self.module_defs = parse_model_config(config_path)
+        self.hyperparams, self.module_list = create_modules(self.module_defs)
+        _, self._blocks = describe_blocks([self.hyperparams] + self.module_defs)
+        self.yolo_layers = [seq[0] for seq in self.module_list if isinstance(seq[0], YOLOLayer)]
+        self.img_size = img_size
+        self.seen = 0
+        self.header_info = np.array([0, 0, 0, self.seen, 0], dtype=np.int32)
+        self.feature_tap = 8 if len(self._blocks) > 8 and self._blocks[8]["type"] == "convolutional" else None
+        self.use_cuda_graph = True
+        self._plans = {}
+        self._weights_version = 0
+
+    # ------------------------------------------------------------------ engine plumbing
+    def _invalidate(self, *_):
+        self._plans = {}
+
+    def load_state_dict(self, *args, **kwargs):
+        self._invalidate()
+        return super().load_state_dict(*args, **kwargs)
+
+    def _apply(self, fn, *args, **kwargs):
+        self._invalidate()
+        return super()._apply(fn, *args, **kwargs)
+
+    def refresh_weights(self):
+        """Call after mutating parameters in place (the packed fp16 copies are rebuilt lazily)."""
+        self._invalidate()
+
+    def plan_for(self, n, size, device):
+        key = (n, size, device.index, self.feature_tap)
+        plan = self._plans.get(key)
+        if plan is None:
+            if device.type != "cuda":
+                raise MeError("Darknet.forward needs CUDA tensors: the sm_100a library is the only implementation")
+            tensors = {k: v.detach().to(device=device, dtype=torch.float32) for k, v in self.state_dict().items()
+                       if v.is_floating_point()}
+            with torch.cuda.device(device):
+                plan = DarknetPlan(self._blocks, tensors, n, size, device, self.feature_tap,
+                                   in_channels=int(self.hyperparams["channels"]))
+            self._plans[key] = plan
+        return plan
+
+    def forward_device(self, x):
+        """Runs the forward and returns the plan (outputs stay in the plan's device buffers)."""
+        if x.dim() != 4 or x.shape[2] != x.shape[3]:
+            raise MeError(f"expected a square (N,C,S,S) batch, got {tuple(x.shape)}")
+        dev = x.device if x.is_cuda else next(self.parameters()).device
+        plan = self.plan_for(x.shape[0], x.shape[2], dev)
+        with torch.cuda.device(dev):
+            plan.x_in.copy_(x, non_blocking=True)   # device->device, or pinned host->device
+            plan.run(self.use_cuda_graph)
+        return plan
+
+    def forward(self, x, targets=None):
+        if targets is not None:
+            raise MeError("the YOLO training loss (models.py:180-232) is outside the accelerated path; "
+                          "no reference script calls it (SURVEY.md F10)")
+        plan = self.forward_device(x)
+        n = plan.n
+        with torch.cuda.device(plan.device):
+            if plan.feature_view is not None:
+                v = plan.feature_view
+                feat = ops.nhwc_to_nchw_f32(v.t, n, v.h, v.w, v.real_c, v.pitch)
+            else:
+                feat = torch.empty(0, device=plan.device)
+            self.featuremap = feat
+            return feat, plan.yolo_out.clone()
+
+    # ------------------------------------------------------------------ darknet binary weights
+    def _conv_bn_pairs(self, cutoff=None):
+        for i, (b, seq) in enumerate(zip(self._blocks, self.module_list)):
+            if cutoff is not None and i == cutoff:
+                return
+            if b["type"] == "convolutional":
+                yield seq[0], (seq[1] if b["bn"] else None)
+
+    def load_darknet_weights(self, weights_path):
+        """Darknet .weights: 5 x int32 header, then per conv [bn bias, bn weight, bn mean, bn var | conv bias],
+        conv weight, all float32 (reference models.py:269-326)."""
+        with open(weights_path, "rb") as fh:
+            header = np.fromfile(fh, dtype=np.int32, count=5)
+            flat = np.fromfile(fh, dtype=np.float32)
+        self.header_info = header
+        self.seen = header[3]
+        cutoff = None
+        if "darknet53.conv.74" in weights_path:
+            cutoff = 75
+        if "yolov3-tiny.conv.15" in weights_path:
+            cutoff = 15
+        pos = 0
+
+        def take(dst):
+            nonlocal pos
+            cnt = dst.numel()
+            dst.data.copy_(torch.from_numpy(flat[pos:pos + cnt]).view_as(dst))
+            pos += cnt
+
+        for conv, bn in self._conv_bn_pairs(cutoff):
+            if bn is not None:
+                for t in (bn.bias, bn.weight, bn.running_mean, bn.running_var):
+                    take(t)
+            else:
+                take(conv.bias)
+            take(conv.weight)
+        self._invalidate()
+
+    def save_darknet_weights(self, path, cutoff=-1):
+        """Inverse of load_darknet_weights (reference models.py:328-352); cutoff=-1 keeps the reference's
+        slice semantics (all blocks but the last)."""
+        blocks = list(zip(self._blocks, self.module_list))[:cutoff]
+        with open(path, "wb") as fh:
+            self.header_info[3] = self.seen
+            self.header_info.tofile(fh)
+            for b, seq in blocks:
+                if b["type"] != "convolutional":
+                    continue
+                conv = seq[0]
+                if b["bn"]:
+                    bn = seq[1]
+                    for t in (bn.bias, bn.weight, bn.running_mean, bn.running_var):
+                        t.data.cpu().numpy().tofile(fh)
+                else:
+                    conv.bias.data.cpu().numpy().tofile(fh)
+                conv.weight.data.cpu().numpy().tofile(fh)

@@ -1,0 +1,284 @@
+"""Drop-in for the reference's module3_our_dataset/my_models.py: `Network(base_detector, conf_thresh)`
+with the same constructor, attributes, forward signature and state_dict keys, running the whole
+detection-and-fusion forward (my_models.py:433-539) on the device through libmillieye_b200:
+
+  Darknet (graph replay) -> me_filter_nms -> me_build_proposals -> conv GEMMs for the image / radar
+  score maps -> me_psroi_align / me_roi_align -> GEMM 490->256 -> me_fusion_heads -> me_finalize_output
+
+The reference's device boundary (D2H of every decoded box for CPU NMS, H2D of the survivors,
+my_models.py:457-470) disappears; the only host synchronisation is the read of the final row count.
+The nn modules below are parameter containers (checkpoint compatibility); their forward is unused.
+"""
+import torch
+from torch import nn
+
+from . import ops
+from ._lib import ME_ACT_LEAKY, ME_ACT_SIGMOID, MeError
+from .models import Darknet
+
+
+def define_yolo(model_def):
+    """reference my_models.py:13-24"""
+    return Darknet(model_def)
+
+
+def init_yolo(model, weights_path):
+    """reference my_models.py:27-44: darknet .weights, ultralytics .pt (positional remap) or a state_dict."""
+    if weights_path.endswith(".weights"):
+        model.load_darknet_weights(weights_path)
+    elif weights_path.endswith(".pt"):
+        param = torch.load(weights_path)["model"]
+        names = list(param)
+        own = model.state_dict()
+        for i, name in enumerate(own):
+            own[name] = param[names[i]]
+        model.load_state_dict(own)
+    else:
+        model.load_state_dict(torch.load(weights_path))
+
+
+class cnn_layers_1(nn.Module):
+    """1x1 conv + BN + LeakyReLU stack on the feature map (reference :47-77). Parameter container."""
+
+    def __init__(self, channels):
+        super().__init__()
+        self.net = nn.Sequential()
+        for i in range(len(channels) - 1):
+            self.net.add_module(f"conv_{i}", nn.Conv2d(channels[i], channels[i + 1], kernel_size=(1, 1), stride=(1, 1)))
+            self.net.add_module(f"batch_norm_{i}", nn.BatchNorm2d(channels[i + 1], momentum=0.1))
+            self.net.add_module(f"leaky_{i}", nn.LeakyReLU(0.1))
+
+
+class cnn_layers_3(nn.Module):
+    """Radar heat-map CNN 3->32->64->128->10 + sigmoid (reference :130-157). Parameter container."""
+
+    def __init__(self):
+        super().__init__()
+
+        def block(cin, cout, *tail):
+            return nn.Sequential(nn.Conv2d(cin, cout, kernel_size=3, stride=1, padding=1),
+                                 nn.BatchNorm2d(cout, momentum=0.1), nn.LeakyReLU(0.1), *tail)
+
+        self.conv1 = block(3, 32)
+        self.conv2 = block(32, 64)
+        self.conv3 = block(64, 128, nn.Conv2d(128, 10, kernel_size=1, stride=1))
+
+
+class ensemble_head(nn.Module):
+    """reference :176-210. Parameter container."""
+
+    def __init__(self, channels, activation_softmax=True):
+        super().__init__()
+        self.activation_softmax = activation_softmax
+        self.fc1 = nn.Sequential(nn.Linear(channels[0], channels[1]), nn.LeakyReLU(0.1))
+        self.fc2 = nn.Sequential(nn.Linear(channels[2], channels[3]))
+        self.softmax = nn.Softmax(dim=1)
+
+
+class refinement_head(nn.Module):
+    """reference :213-284. Parameter container (net3 / fusion_head exist in checkpoints but are unused, F7)."""
+
+    def __init__(self, channels):
+        super().__init__()
+        self.count = 0
+        tmp = 49
+        self.net0 = nn.Sequential(nn.Linear(channels[0], channels[1]), nn.LeakyReLU(0.1))
+        self.net1 = nn.Sequential(nn.Linear(channels[1], 4))
+        self.net2 = nn.Sequential(nn.Linear(channels[1], 13), nn.Sigmoid())
+        self.net3 = nn.Sequential(nn.Linear(channels[1], tmp), nn.Sigmoid())
+        self.radar_net = nn.Sequential(nn.Conv2d(10, 10, kernel_size=7, stride=1, padding=0),
+                                       nn.BatchNorm2d(10, momentum=0.1), nn.LeakyReLU(0.1),
+                                       nn.Conv2d(10, 1, kernel_size=1, stride=1, padding=0), nn.Sigmoid())
+        self.fusion_head = nn.Sequential(nn.Linear(2 * tmp, 1), nn.Sigmoid())
+
+
+class _FusionPlan:
+    """Device buffers + packed weights of the fusion tail for one (n, size) shape."""
+
+    MAX_DET = 200  # detections_per_img of non_max_suppression_cpp (utils.py:337)
+
+    def __init__(self, net, base_plan, n, size, device, radar_cap):
+        self.n, self.size, self.device = n, size, device
+        self.base = base_plan
+        fv = base_plan.feature_view
+        if fv is None:
+            raise MeError("the base detector has no feature tap (set base_detector.feature_tap to a stride-16 "
+                          "block with 256 channels; the reference only defines it for the tiny cfgs, SURVEY.md F1)")
+        if fv.real_c != 256:
+            raise MeError(f"feature map has {fv.real_c} channels, img_cnn_layers expects 256")
+        self.g = fv.h
+        g = self.g
+        sd = {k: v.detach().to(device=device, dtype=torch.float32) for k, v in net.state_dict().items()
+              if v.is_floating_point() and not k.startswith("base_detector.")}
+
+        def bn(prefix):
+            return (sd[prefix + "weight"], sd[prefix + "bias"], sd[prefix + "running_mean"], sd[prefix + "running_var"], 1e-5)
+
+        f16 = dict(dtype=torch.float16, device=device)
+        f32 = dict(dtype=torch.float32, device=device)
+        i32 = dict(dtype=torch.int32, device=device)
+        # score maps
+        self.img_conv = ops.pack_conv(sd["img_cnn_layers.net.conv_0.weight"], sd["img_cnn_layers.net.conv_0.bias"],
+                                      bn("img_cnn_layers.net.batch_norm_0."), cout_pad=512)
+        self.roi_score = torch.zeros((n, g, g, 512), **f16)
+        self.maps_in = torch.zeros((n, 3, g, g), **f32)
+        self.r1 = ops.pack_first_conv(sd["radar_cnn_layers.conv1.0.weight"], sd["radar_cnn_layers.conv1.0.bias"],
+                                      bn("radar_cnn_layers.conv1.1."))
+        self.r2 = ops.pack_conv(sd["radar_cnn_layers.conv2.0.weight"], sd["radar_cnn_layers.conv2.0.bias"],
+                                bn("radar_cnn_layers.conv2.1."))
+        self.r3 = ops.pack_conv(sd["radar_cnn_layers.conv3.0.weight"], sd["radar_cnn_layers.conv3.0.bias"],
+                                bn("radar_cnn_layers.conv3.1."))
+        self.r4 = ops.pack_conv(sd["radar_cnn_layers.conv3.3.weight"], sd["radar_cnn_layers.conv3.3.bias"], None,
+                                cout_pad=32)
+        self.ra = torch.zeros((n, g, g, 32), **f16)
+        self.rb = torch.zeros((n, g, g, 64), **f16)
+        self.rc = torch.zeros((n, g, g, 128), **f16)
+        self.radar_score = torch.zeros((n, g, g, 32), **f16)
+        # proposals
+        self.radar_cap = radar_cap
+        self.cap = n * self.MAX_DET + radar_cap
+        cap = self.cap
+        self.nms = ops.NmsBuffers(n, base_plan.rows_total, base_plan.attrs - 5, self.MAX_DET, device)
+        self.radar_dev = torch.zeros((max(radar_cap, 1), 5), **f32)
+        self.img_boxes = torch.zeros((cap, 9), **f32)
+        self.rois = torch.zeros((cap, 5), **f32)
+        self.counts = torch.zeros((2,), **i32)
+        self.crop_img = torch.zeros((cap, 512), **f16)
+        self.crop_radar = torch.zeros((cap, 496), **f16)
+        self.hidden = torch.zeros((cap, 256), **f16)
+        w0 = sd["refinement_head.net0.0.weight"]
+        self.fc0 = ops.pack_conv(w0.view(w0.shape[0], w0.shape[1], 1, 1), sd["refinement_head.net0.0.bias"], None)
+        # small heads stay fp32
+        rw = sd["refinement_head.radar_net.0.weight"]
+        g_, b_, m_, v_, eps = bn("refinement_head.radar_net.1.")
+        scale = g_ / torch.sqrt(v_ + eps)
+        self._hw_tensors = {
+            "net1_w": sd["refinement_head.net1.0.weight"].contiguous(), "net1_b": sd["refinement_head.net1.0.bias"].contiguous(),
+            "net2_w": sd["refinement_head.net2.0.weight"].contiguous(), "net2_b": sd["refinement_head.net2.0.bias"].contiguous(),
+            "radar_w": (rw.reshape(rw.shape[0], -1) * scale[:, None]).contiguous(),
+            "radar_b": ((sd["refinement_head.radar_net.0.bias"] - m_) * scale + b_).contiguous(),
+            "radar2_w": sd["refinement_head.radar_net.3.weight"].reshape(-1).contiguous(),
+            "radar2_b": sd["refinement_head.radar_net.3.bias"].contiguous(),
+            "fc1_w": sd["ensemble_head.fc1.0.weight"].contiguous(), "fc1_b": sd["ensemble_head.fc1.0.bias"].contiguous(),
+            "fc2_w": sd["ensemble_head.fc2.0.weight"].contiguous(), "fc2_b": sd["ensemble_head.fc2.0.bias"].contiguous(),
+        }
+        self.head_weights = ops.make_head_weights(self._hw_tensors)
+        self.regress = torch.zeros((cap, 4), **f32)
+        self.refine = torch.zeros((cap, 2), **f32)
+        self.mask = torch.zeros((cap,), **f32)
+        self.out = torch.zeros((cap, 8), **f32)
+        self.out_count = torch.zeros((1,), **i32)
+        ws_bytes = 1
+        while ws_bytes < cap:
+            ws_bytes <<= 1
+        self.final_ws = torch.zeros((ws_bytes * 8,), dtype=torch.uint8, device=device)
+        self.launches = 0
+
+    def score_maps(self):
+        """img_cnn_layers + radar_cnn_layers (my_models.py:486-487)."""
+        n, g = self.n, self.g
+        fv = self.base.feature_view
+        ops.conv_gemm(fv.t, self.img_conv, n, g, g, fv.pitch, self.roi_score, 512, act=ME_ACT_LEAKY, cin=256)
+        ops.conv_first(self.maps_in, self.r1, self.ra, 32, act=ME_ACT_LEAKY)
+        ops.conv_gemm(self.ra, self.r2, n, g, g, 32, self.rb, 64, act=ME_ACT_LEAKY)
+        ops.conv_gemm(self.rb, self.r3, n, g, g, 64, self.rc, 128, act=ME_ACT_LEAKY)
+        ops.conv_gemm(self.rc, self.r4, n, g, g, 128, self.radar_score, 32, act=ME_ACT_SIGMOID)
+        self.launches += 5
+
+    def proposals(self, conf_thresh, class_idx, num_radar):
+        ops.filter_nms(self.base.yolo_out, conf_thresh, 0.5, self.MAX_DET, xyxy_inplace=True, buffers=self.nms)
+        ops.build_proposals(self.nms.det, self.nms.count, class_idx, self.radar_dev[:num_radar] if num_radar else None,
+                            1.0, self.img_boxes, self.rois, self.counts, self.cap)
+        self.launches += 3
+
+    def heads(self, thr_img, thr_radar, regress_boxes):
+        n, g, cap = self.n, self.g, self.cap
+        ops.psroi_align(self.roi_score, n, g, g, 512, 10, 7, 1.0 / 16, self.rois, self.counts, cap, self.crop_img, 512)
+        ops.roi_align(self.radar_score, n, g, g, 32, 10, 7, 1.0 / 16, self.rois, self.counts, cap, self.crop_radar, 496)
+        ops.conv_gemm(self.crop_img, self.fc0, cap, 1, 1, 512, self.hidden, 256, act=ME_ACT_LEAKY, cin=490)
+        ops.fusion_heads(self.hidden, 256, self.crop_radar, 496, self.head_weights, self.img_boxes, self.counts, cap,
+                         self.regress, self.refine, self.mask)
+        ops.finalize_output(self.img_boxes, self.rois, self.refine, self.regress, self.mask, self.counts, cap,
+                            thr_img, thr_radar, regress_boxes, self.out, self.out_count, self.final_ws)
+        self.launches += 5
+
+
+class Network(nn.Module):
+    """milliEye fusion model (reference my_models.py:411-640), inference branch on the B200 kernels."""
+
+    def __init__(self, base_detector, conf_thresh):
+        super().__init__()
+        self.device = torch.device("cuda" if torch.cuda.is_available() else "cpu")
+        self.conf_thresh = conf_thresh
+        self.seen = 0
+        self.iou_thresh = (0.3, 0.7)
+        self.alpha = 0.75
+        self.balance_factor = 5
+        self.loss_lambda = (6, 1)
+        self.refine_threshold_img, self.refine_threshold_radar = 0, 0
+        self.class_num = 1
+        self.class_idx = 0
+
+        self.base_detector = base_detector.eval()
+        self.img_cnn_layers = cnn_layers_1((256, 490))
+        self.radar_cnn_layers = cnn_layers_3()
+        self.refinement_head = refinement_head((490, 256, 128, self.class_num + 1))
+        self.ensemble_head = ensemble_head((2, 32, 32 * (1 + self.class_num), 2))
+        self._plans = {}
+
+    def _invalidate(self):
+        self._plans = {}
+
+    def load_state_dict(self, *args, **kwargs):
+        self._invalidate()
+        return super().load_state_dict(*args, **kwargs)
+
+    def _apply(self, fn, *args, **kwargs):
+        self._invalidate()
+        return super()._apply(fn, *args, **kwargs)
+
+    def refresh_weights(self):
+        self._invalidate()
+        self.base_detector.refresh_weights()
+
+    def _plan(self, base_plan, num_radar):
+        key = (base_plan.n, base_plan.size, base_plan.device.index, id(base_plan))
+        plan = self._plans.get(key)
+        need = max(num_radar, 1)
+        if plan is None or plan.radar_cap < need:
+            cap = max(16 * base_plan.n, 1 << (need - 1).bit_length())
+            with torch.cuda.device(base_plan.device):
+                plan = _FusionPlan(self, base_plan, base_plan.n, base_plan.size, base_plan.device, cap)
+            self._plans[key] = plan
+        return plan
+
+    def forward(self, images, maps, radar_boxes_location, model_mode=0, targets=None):
+        """Same contract as reference my_models.py:433-452.  images (N,3,S,S) fp32 0..1; maps (N,3,S/16,S/16);
+        radar_boxes_location (n,5) [frame, x1,y1,x2,y2] in 0..1 - scaled by S IN PLACE like the reference (:491);
+        model_mode 0 fusion / 1 YOLO only / 2 radar only.  Returns output (K,8) on the device."""
+        if targets is not None:
+            raise MeError("the stage-3 training branch (my_models.py:545-640) is not part of this round's "
+                          "accelerated path; run inference (targets=None)")
+        base = self.base_detector
+        plan_b = base.forward_device(images)
+        dev = plan_b.device
+        n_radar = int(radar_boxes_location.shape[0]) if radar_boxes_location is not None else 0
+        plan = self._plan(plan_b, n_radar)
+        with torch.cuda.device(dev):
+            plan.launches = 0
+            if model_mode == 1:
+                plan.proposals(self.conf_thresh, self.class_idx, 0)
+                n_img = int(plan.counts[0].item())
+                return plan.img_boxes[:n_img, :8].clone()
+            if model_mode == 2:
+                self.refine_threshold_img = 1   # persistent, like the reference (:480)
+            if n_radar > 0:
+                radar_boxes_location[:, 1:] *= images.shape[-1]          # reference side effect (:491)
+                plan.radar_dev[:n_radar].copy_(radar_boxes_location, non_blocking=True)
+            plan.maps_in.copy_(maps, non_blocking=True)
+            plan.score_maps()
+            plan.proposals(self.conf_thresh, self.class_idx, n_radar)
+            plan.heads(float(self.refine_threshold_img), float(self.refine_threshold_radar), model_mode != 2)
+            self.refinement_head.count += 1
+            k = int(plan.out_count.item())                               # the forward's only host sync
+            return plan.out[:k].clone()

@@ -1,0 +1,135 @@
+"""Oracle restatement of milliEye's fusion forward (reference my_models.py), inference branch.
+
+Test infrastructure only (see oracle/__init__.py).  fp32 on CPU.  The conv / linear / batch-norm
+arithmetic goes through the torch CPU operators the reference's modules call; the wiring, the
+proposal assembly, the masks, thresholds, box regression and ordering are restated.
+"""
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+from . import boxes as obox
+from . import roi as oroi
+from .darknet import darknet_forward
+
+
+def _bn(x, sd, p, momentum=0.1):
+    return F.batch_norm(x, sd[p + "running_mean"], sd[p + "running_var"], sd[p + "weight"], sd[p + "bias"],
+                        training=False, momentum=momentum, eps=1e-5)
+
+
+def img_cnn_layers(feat, sd, prefix="img_cnn_layers."):
+    """cnn_layers_1((256, 490)) - my_models.py:47-77: 1x1 conv (bias) + BN + LeakyReLU(0.1)."""
+    x = F.conv2d(feat, sd[prefix + "net.conv_0.weight"], sd[prefix + "net.conv_0.bias"])
+    return F.leaky_relu(_bn(x, sd, prefix + "net.batch_norm_0."), 0.1)
+
+
+def radar_cnn_layers(maps, sd, prefix="radar_cnn_layers."):
+    """cnn_layers_3 - my_models.py:130-157."""
+    x = maps
+    for name in ("conv1", "conv2", "conv3"):
+        x = F.conv2d(x, sd[f"{prefix}{name}.0.weight"], sd[f"{prefix}{name}.0.bias"], padding=1)
+        x = F.leaky_relu(_bn(x, sd, f"{prefix}{name}.1."), 0.1)
+    x = F.conv2d(x, sd[prefix + "conv3.3.weight"], sd[prefix + "conv3.3.bias"])
+    return torch.sigmoid(x)
+
+
+def refinement_head(radar_maps, img_maps, sd, prefix="refinement_head."):
+    """refinement_head.forward - my_models.py:260-284 (net3 / fusion_head are unused there)."""
+    flat = img_maps.flatten(start_dim=1)
+    t = F.leaky_relu(F.linear(flat, sd[prefix + "net0.0.weight"], sd[prefix + "net0.0.bias"]), 0.1)
+    reg = F.linear(t, sd[prefix + "net1.0.weight"], sd[prefix + "net1.0.bias"])
+    cls = torch.sigmoid(F.linear(t, sd[prefix + "net2.0.weight"], sd[prefix + "net2.0.bias"]))
+    r = F.conv2d(radar_maps, sd[prefix + "radar_net.0.weight"], sd[prefix + "radar_net.0.bias"])
+    r = F.leaky_relu(_bn(r, sd, prefix + "radar_net.1."), 0.1)
+    r = torch.sigmoid(F.conv2d(r, sd[prefix + "radar_net.3.weight"], sd[prefix + "radar_net.3.bias"]))
+    radar_conf = r.squeeze(-1).squeeze(-1)
+    conf = torch.sigmoid(radar_conf + cls[:, :1])
+    return reg, torch.cat((conf, cls[:, 1:2]), -1)
+
+
+def ensemble_head(ref_vec, yolo_vec, sd, prefix="ensemble_head."):
+    """ensemble_head.forward - my_models.py:202-210."""
+    x = torch.stack((ref_vec, yolo_vec), -1)
+    x = F.leaky_relu(F.linear(x, sd[prefix + "fc1.0.weight"], sd[prefix + "fc1.0.bias"]), 0.1)
+    x = x.flatten(start_dim=1)
+    x = F.linear(x, sd[prefix + "fc2.0.weight"], sd[prefix + "fc2.0.bias"])
+    return torch.softmax(x, dim=1)
+
+
+def box_regress(reg, roi_xyxy):
+    """my_models.py:378-391."""
+    xywh = torch.from_numpy(obox.xyxy2xywh(roi_xyxy.numpy()))
+    x, y, w, h = xywh.t()
+    out = torch.stack((reg[:, 0] * w + x, reg[:, 1] * h + y, torch.exp(reg[:, 2]) * w, torch.exp(reg[:, 3]) * h), 1)
+    return torch.from_numpy(obox.xywh2xyxy(out.numpy()))
+
+
+def network_forward(module_defs, sd, images, maps, radar_boxes, conf_thresh, model_mode=0, refine_threshold_img=0.0,
+                    refine_threshold_radar=0.0, class_idx=0, class_num=1, use_torchvision=False, feature_tap=None,
+                    return_intermediates=False):
+    """Network.forward with targets=None (my_models.py:433-539).
+
+    radar_boxes (n,5) is taken in the caller's 0..1 scale and, like the reference (:491), scaled by the
+    image size - on a copy; the in-place side effect on the caller's tensor is the wrapper's concern.
+    Returns output (K,8) = [image_i, x1, y1, x2, y2, new_conf, class_score, class_pred].
+    """
+    feat, yolo_out = darknet_forward(module_defs, sd, images, prefix="base_detector.", feature_tap=feature_tap)
+    pred = yolo_out.clone().numpy()
+    dets, _ = obox.non_max_suppression_cpp(pred, conf_thresh, use_torchvision=use_torchvision)
+    rows = []
+    for i, d in enumerate(dets):
+        if d is None:
+            continue
+        d = d[d[:, 6] == class_idx]
+        if len(d) > 0:
+            b = np.zeros((len(d), 8 + class_num), dtype=np.float32)
+            b[:, 0] = i
+            b[:, 1:] = d[:, :7 + class_num]
+            rows.append(b)
+    img_boxes = torch.from_numpy(np.concatenate(rows, 0)) if rows else torch.empty((0, 8 + class_num))
+    n_img = len(img_boxes)
+    if model_mode == 1:
+        return img_boxes[:, :8]
+    if model_mode == 2:
+        refine_threshold_img = 1
+
+    roi_score_map = img_cnn_layers(feat, sd)
+    radar_score_map = radar_cnn_layers(maps, sd)
+    radar_boxes = radar_boxes.clone().float()
+    if len(radar_boxes) > 0:
+        radar_boxes[:, 1:] *= images.shape[-1]
+    box_locations = torch.cat((img_boxes[:, :5], radar_boxes), 0)
+    if use_torchvision:
+        from torchvision.ops import ps_roi_align, roi_align
+        crop_img = ps_roi_align(roi_score_map, box_locations, (7, 7), spatial_scale=1. / 16)
+        crop_radar = roi_align(radar_score_map, box_locations, (7, 7), spatial_scale=1. / 16)
+    else:
+        crop_img = torch.from_numpy(oroi.ps_roi_align(roi_score_map.numpy(), box_locations.numpy(), 7, 1. / 16))
+        crop_radar = torch.from_numpy(oroi.roi_align(radar_score_map.numpy(), box_locations.numpy(), 7, 1. / 16))
+    if len(box_locations) == 0:
+        crop_img = crop_img.reshape(0, 10, 7, 7)
+        crop_radar = crop_radar.reshape(0, 10, 7, 7)
+    reg, ref_vec = refinement_head(crop_radar, crop_img, sd)
+
+    radar_rows = torch.cat((radar_boxes, ref_vec[n_img:], torch.zeros((len(radar_boxes), 1)), ref_vec[n_img:, 1:]), -1)
+    all_boxes = torch.cat((img_boxes, radar_rows), 0)
+    yolo_vec = torch.cat((img_boxes[:, 5:6], img_boxes[:, 8:]), 1)
+    masks_img = ensemble_head(ref_vec[:n_img], yolo_vec, sd)
+    m = torch.cat((masks_img[:, :1], ref_vec[n_img:, :1]), 0)
+    masks = torch.cat((1 - m, m), -1)
+    positive = torch.cat((masks[:n_img, 1] > refine_threshold_img, masks[n_img:, 1] > refine_threshold_radar), 0)
+    if model_mode != 2:
+        new_xyxy = box_regress(reg[positive], all_boxes[positive, 1:5])
+    else:
+        new_xyxy = all_boxes[positive, 1:5]
+    output = torch.cat((all_boxes[positive, :1], new_xyxy, masks[positive, 1:], all_boxes[positive, 6:8]), -1)
+    pri = masks.clone()
+    pri[n_img:, 1] /= 5
+    order = torch.sort(pri[positive, 1], descending=True, stable=True).indices
+    output = output[order]
+    if return_intermediates:
+        return output, dict(feat=feat, yolo_out=yolo_out, img_boxes=img_boxes, box_locations=box_locations,
+                            roi_score_map=roi_score_map, radar_score_map=radar_score_map, crop_img=crop_img,
+                            crop_radar=crop_radar, reg=reg, ref_vec=ref_vec, masks=masks, positive=positive)
+    return output
