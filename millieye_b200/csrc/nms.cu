@@ -37,7 +37,7 @@ __host__ __device__ inline int next_pow2(int v) {
 }
 
 __host__ __device__ inline size_t per_image_bytes(int rows) {
-  const size_t r = static_cast<size_t>(rows);
+  const size_t r = (static_cast<size_t>(rows) + 3) & ~size_t(3);  // keeps every array 16B aligned
   size_t b = r * 4 * 4 + r * 4 + r * 4 + r * 4 + r * 4 * 4 + r * 4 + r * 4;
   b = (b + 15) & ~size_t(15);
   b += static_cast<size_t>(next_pow2(rows)) * 8;
@@ -47,7 +47,7 @@ __host__ __device__ inline size_t per_image_bytes(int rows) {
 __device__ inline Layout layout_for(void* ws, int rows, int img) {
   uint8_t* p = static_cast<uint8_t*>(ws) + per_image_bytes(rows) * img;
   Layout L;
-  const size_t r = static_cast<size_t>(rows);
+  const size_t r = (static_cast<size_t>(rows) + 3) & ~size_t(3);
   L.box = reinterpret_cast<float*>(p);       p += r * 16;
   L.conf = reinterpret_cast<float*>(p);      p += r * 4;
   L.cls_conf = reinterpret_cast<float*>(p);  p += r * 4;

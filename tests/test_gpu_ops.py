@@ -1,0 +1,289 @@
+"""Per-kernel parity tests through the C-ABI on a B200 (`-m gpu`): every kernel against the oracle
+(oracle/) or the torch fp32 operator on the same seeded inputs, plus the committed golden fixtures."""
+import os
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+from millieye_b200 import ops
+from oracle import boxes as obox
+from oracle import darknet as odark
+from oracle import roi as oroi
+from oracle import synth
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+# ------------------------------------------------------------------------------- conv GEMM
+def _conv_case(n, h, w, cin, cout, k, s, act, bn=True, res=False, f32=False, seed=0):
+    torch.manual_seed(seed)
+    x = torch.randn(n, cin, h, w)
+    wt = torch.randn(cout, cin, k, k) / (cin * k * k) ** 0.5
+    bias = None if bn else torch.randn(cout) * 0.1
+    bnp = (torch.rand(cout) + 0.5, torch.randn(cout) * 0.1, torch.randn(cout) * 0.1, torch.rand(cout) + 0.5, 1e-5) if bn else None
+    in_pitch, cout_pad = ops.round_up(cin, 8), ops.round_up(cout, 32)
+    xh = torch.zeros(n, h, w, in_pitch, dtype=torch.float16)
+    xh[..., :cin] = x.permute(0, 2, 3, 1).half()
+    x_used = xh[..., :cin].float().permute(0, 3, 1, 2).contiguous()
+    pad = (k - 1) // 2
+    ho, wo = (h + 2 * pad - k) // s + 1, (w + 2 * pad - k) // s + 1
+    resid = torch.randn(n, ho, wo, cout_pad).half() if res else None
+    packed = ops.pack_conv(wt.to(DEV), None if bias is None else bias.to(DEV),
+                           None if bnp is None else tuple(t.to(DEV) if torch.is_tensor(t) else t for t in bnp), cout_pad=cout_pad)
+    cin_pad = packed.w.shape[1] // (k * k)
+    wq = packed.w.float().cpu().view(cout_pad, k * k, cin_pad)[:cout, :, :cin].permute(0, 2, 1).reshape(cout, cin, k, k)
+    ref = F.conv2d(x_used, wq, packed.bias.cpu()[:cout], stride=s, padding=pad)
+    ref = F.leaky_relu(ref, 0.1) if act == 1 else (torch.sigmoid(ref) if act == 2 else ref)
+    if res:
+        ref = ref + resid[..., :cout].float().permute(0, 3, 1, 2)
+    out = torch.full((n, ho, wo, cout_pad), float("nan"), dtype=torch.float32 if f32 else torch.float16, device=DEV)
+    ops.conv_gemm(xh.to(DEV), packed, n, h, w, in_pitch, out, cout_pad, stride=s, act=act,
+                  residual=None if resid is None else resid.to(DEV), res_pitch=cout_pad, out_f32=f32)
+    torch.cuda.synchronize()
+    got = out.float().cpu()[..., :cout].permute(0, 3, 1, 2)
+    assert not torch.isnan(got).any()
+    # fp32 accumulate over exactly representable fp16 products: only the output rounding differs
+    tol = (2e-5 if f32 else 1.5e-3) * max(1.0, float(ref.abs().max()))
+    assert float((got - ref).abs().max()) <= tol
+    if cout_pad > cout and act != 2:  # padded channels carry zeros
+        assert float(out.float().cpu()[..., cout:].abs().max()) == 0.0
+
+
+CONV_CASES = {
+    "1x1_64_64_linear_bias": dict(n=1, h=16, w=16, cin=64, cout=64, k=1, s=1, act=0, bn=False),
+    "1x1_128_128": dict(n=2, h=32, w=32, cin=128, cout=128, k=1, s=1, act=1),
+    "1x1_256_512": dict(n=2, h=13, w=13, cin=256, cout=512, k=1, s=1, act=1),
+    "1x1_ragged_m": dict(n=1, h=13, w=13, cin=64, cout=32, k=1, s=1, act=1),
+    "3x3_64_64_13": dict(n=2, h=13, w=13, cin=64, cout=64, k=3, s=1, act=1),
+    "3x3_128_256_26": dict(n=3, h=26, w=26, cin=128, cout=256, k=3, s=1, act=1),
+    "3x3_s2_64_128": dict(n=2, h=16, w=16, cin=64, cout=128, k=3, s=2, act=1),
+    "3x3_s2_32_64": dict(n=2, h=32, w=32, cin=32, cout=64, k=3, s=2, act=1),
+    "3x3_bk32": dict(n=2, h=26, w=26, cin=32, cout=64, k=3, s=1, act=1),
+    "3x3_bk16": dict(n=2, h=26, w=26, cin=16, cout=32, k=3, s=1, act=1),
+    "3x3_residual": dict(n=2, h=13, w=13, cin=64, cout=128, k=3, s=1, act=1, res=True),
+    "1x1_head_f32_255": dict(n=2, h=13, w=13, cin=1024, cout=255, k=1, s=1, act=0, bn=False, f32=True),
+    "1x1_head_f32_51": dict(n=2, h=26, w=26, cin=256, cout=51, k=1, s=1, act=0, bn=False, f32=True),
+    "1x1_490": dict(n=2, h=26, w=26, cin=256, cout=490, k=1, s=1, act=1),
+    "3x3_cin384": dict(n=2, h=26, w=26, cin=384, cout=256, k=3, s=1, act=1),
+    "1x1_sigmoid_10": dict(n=2, h=26, w=26, cin=128, cout=10, k=1, s=1, act=2, bn=False),
+    "fc_490_256": dict(n=300, h=1, w=1, cin=490, cout=256, k=1, s=1, act=1, bn=False),
+    "3x3_single_pixel_rows": dict(n=5, h=1, w=7, cin=64, cout=32, k=3, s=1, act=1),
+    "3x3_many_tiles": dict(n=4, h=52, w=52, cin=64, cout=128, k=3, s=1, act=1),
+}
+
+
+@pytest.mark.parametrize("name", sorted(CONV_CASES))
+def test_conv_gemm(name):
+    _conv_case(**CONV_CASES[name])
+
+
+def test_conv_gemm_concat_slice():
+    """Output written into a channel slice of a wider buffer, input read from another slice (route fusion)."""
+    torch.manual_seed(3)
+    n, h, w, cin, cout = 2, 13, 13, 64, 64
+    wide_in = torch.randn(n, h, w, 192).half()
+    wt = torch.randn(cout, cin, 1, 1) / 8
+    packed = ops.pack_conv(wt.to(DEV))
+    wide_out = torch.zeros(n, h, w, 160, dtype=torch.float16, device=DEV)
+    xin = wide_in.to(DEV)
+    ops.conv_gemm(xin.view(-1)[64:], packed, n, h, w, 192, wide_out.view(-1)[96:], 160, act=0, cin=64, cout=64)
+    torch.cuda.synchronize()
+    ref = F.conv2d(wide_in[..., 64:128].float().permute(0, 3, 1, 2), packed.w.float().cpu().view(cout, cin, 1, 1))
+    got = wide_out.cpu().float()
+    assert float((got[..., 96:160].permute(0, 3, 1, 2) - ref).abs().max()) < 5e-3
+    assert float(got[..., :96].abs().max()) == 0.0  # neighbours untouched
+
+
+def test_conv_rejects_bad_arguments():
+    from millieye_b200._lib import MeError
+    packed = ops.pack_conv(torch.randn(32, 64, 1, 1, device=DEV))
+    x = torch.zeros(1, 4, 4, 64, dtype=torch.float16, device=DEV)
+    y = torch.zeros(1, 4, 4, 32, dtype=torch.float16, device=DEV)
+    with pytest.raises(MeError):
+        ops.conv_gemm(x, packed, 1, 4, 4, 64, y, 32, cout=24)       # cout not a multiple of 32
+    with pytest.raises(MeError):
+        ops.conv_gemm(x, packed, 1, 4, 4, 60, y, 32)                # pitch < cin
+    with pytest.raises(MeError):
+        ops.conv_gemm(x.cpu(), packed, 1, 4, 4, 64, y, 32)          # CPU tensor: no fallback
+
+
+# ------------------------------------------------------------------------------- SIMT glue
+@pytest.mark.parametrize("cout,act", [(16, 1), (32, 1), (32, 2)])
+def test_conv_first(cout, act):
+    torch.manual_seed(1)
+    n, h, w = 2, 20, 28
+    x = torch.rand(n, 3, h, w)
+    wt = torch.randn(cout, 3, 3, 3) * 0.3
+    bn = (torch.rand(cout) + 0.5, torch.randn(cout) * 0.1, torch.randn(cout) * 0.1, torch.rand(cout) + 0.5, 1e-5)
+    first = ops.pack_first_conv(wt.to(DEV), None, tuple(t.to(DEV) if torch.is_tensor(t) else t for t in bn))
+    out = torch.zeros(n, h, w, cout, dtype=torch.float16, device=DEV)
+    ops.conv_first(x.to(DEV), first, out, cout, act=act)
+    ref = F.batch_norm(F.conv2d(x, wt, padding=1), bn[2], bn[3], bn[0], bn[1], False, 0.9, 1e-5)
+    ref = F.leaky_relu(ref, 0.1) if act == 1 else torch.sigmoid(ref)
+    got = out.float().cpu().permute(0, 3, 1, 2)
+    assert float((got - ref).abs().max()) <= 2e-3 * max(1.0, float(ref.abs().max()))
+
+
+@pytest.mark.parametrize("stride", [1, 2])
+def test_maxpool(stride):
+    torch.manual_seed(2)
+    n, h, w, c = 2, 13 if stride == 1 else 26, 13 if stride == 1 else 26, 64
+    x = torch.randn(n, h, w, c).half()
+    ho = h if stride == 1 else h // 2
+    out = torch.zeros(n, ho, ho, c, dtype=torch.float16, device=DEV)
+    ops.maxpool2(x.to(DEV), out, n, h, w, c, c, c, stride)
+    xr = x.float().permute(0, 3, 1, 2)
+    if stride == 1:
+        xr = F.pad(xr, (0, 1, 0, 1))   # reference models.py:46-49
+    ref = F.max_pool2d(xr, 2, stride)
+    assert torch.equal(out.float().cpu().permute(0, 3, 1, 2), ref)
+
+
+def test_upsample_into_slice_and_layout_converts():
+    torch.manual_seed(4)
+    n, h, w, c = 2, 13, 13, 128
+    x = torch.randn(n, h, w, c).half()
+    wide = torch.zeros(n, 2 * h, 2 * w, 384, dtype=torch.float16, device=DEV)
+    ops.upsample2(x.to(DEV), wide, n, h, w, c, c, 384)
+    ref = F.interpolate(x.float().permute(0, 3, 1, 2), scale_factor=2, mode="nearest")
+    got = wide.float().cpu()
+    assert torch.equal(got[..., :c].permute(0, 3, 1, 2), ref)
+    assert float(got[..., c:].abs().max()) == 0.0
+    nchw = ops.nhwc_to_nchw_f32(wide.view(-1)[0:], n, 2 * h, 2 * w, c, 384)
+    assert torch.equal(nchw.cpu(), ref)
+    back = ops.nchw_f32_to_nhwc(nchw.contiguous(), out_pitch=c)
+    assert torch.equal(back.float().cpu().permute(0, 3, 1, 2), ref)
+
+
+# ------------------------------------------------------------------------------- decode
+@pytest.mark.parametrize("g,anchors,classes,size", [
+    (13, [(81, 82), (135, 169), (344, 319)], 12, 416),
+    (26, [(23, 27), (37, 58), (81, 82)], 12, 416),
+    (52, [(10, 13), (16, 30), (33, 23)], 80, 416),
+    (10, [(116, 90), (156, 198), (373, 326)], 80, 320),
+])
+def test_yolo_decode(g, anchors, classes, size):
+    torch.manual_seed(5)
+    n, attrs = 2, 5 + classes
+    ch = 3 * attrs
+    pitch = ops.round_up(ch, 32)
+    logits = torch.randn(n, ch, g, g) * 2
+    nhwc = torch.zeros(n, g, g, pitch)
+    nhwc[..., :ch] = logits.permute(0, 2, 3, 1)
+    rows = 3 * g * g
+    out = torch.zeros(n, rows + 7, attrs, device=DEV)
+    ops.yolo_decode(nhwc.to(DEV), pitch, out, n, g, anchors, classes, size / g, rows + 7, 7)
+    ref = odark.yolo_decode(logits, anchors, classes, size)
+    got = out.cpu()
+    assert float(got[:, :7].abs().max()) == 0.0
+    # same formula in fp32; only exp/sigmoid implementations differ (<= 2 ulp)
+    np.testing.assert_allclose(got[:, 7:].numpy(), ref.numpy(), rtol=3e-6, atol=1e-6)
+
+
+# ------------------------------------------------------------------------------- NMS
+def _check_nms(pred, thr, golden=None):
+    ref_dets, ref_rows = obox.non_max_suppression_cpp(pred.numpy().copy(), thr)
+    dev_pred = pred.clone().to(DEV)
+    buf = ops.filter_nms(dev_pred, thr, 0.5, 200, xyxy_inplace=True)
+    torch.cuda.synchronize()
+    counts = buf.count.cpu().numpy()
+    for i in range(pred.shape[0]):
+        k = int(counts[i])
+        if ref_dets[i] is None:
+            assert k == 0
+            continue
+        assert k == len(ref_dets[i])
+        # survivor rows and order are bit-exact: indices, then every float of the row
+        np.testing.assert_array_equal(buf.index[i, :k].cpu().numpy(), ref_rows[i])
+        np.testing.assert_array_equal(buf.det[i, :k].cpu().numpy(), ref_dets[i])
+        if golden is not None:
+            np.testing.assert_array_equal(buf.det[i, :k].cpu().numpy(), golden[i])
+    # in-place xywh -> xyxy of the whole tensor, like utils.py:354
+    np.testing.assert_array_equal(dev_pred[..., :4].cpu().numpy(), obox.xywh2xyxy(pred[..., :4].numpy()))
+
+
+@pytest.mark.parametrize("tag,mu,thr", [("trick", -6.0, 0.01), ("vanilla", -1.0, 0.2)])
+def test_filter_nms_golden(golden_dir, tag, mu, thr):
+    g = np.load(os.path.join(golden_dir, "nms_cpp.npz"))
+    pred = synth.synth_predictions(2, 2535, 12, seed=7, conf_mu=mu)
+    _check_nms(pred, thr, golden=[g[f"{tag}_0"], g[f"{tag}_1"]])
+
+
+@pytest.mark.parametrize("rows,classes,mu,thr", [
+    (2535, 12, -6.0, 0.01), (2535, 12, -2.0, 0.25), (10647, 80, -5.0, 0.01), (10647, 80, -2.5, 0.2),
+    (375, 12, 3.0, 0.01), (135, 1, -1.0, 0.5), (10647, 80, 4.0, 0.01),
+])
+def test_filter_nms_vs_oracle(rows, classes, mu, thr):
+    _check_nms(synth.synth_predictions(3, rows, classes, seed=rows + classes, conf_mu=mu), thr)
+
+
+def test_filter_nms_edges():
+    # nothing above threshold; exactly-at-threshold rows are kept (>=); duplicate boxes / equal scores
+    pred = synth.synth_predictions(2, 300, 12, seed=1, conf_mu=-9.0)
+    pred[0, :, 4] = 0.001
+    pred[1, 5, 4] = 0.25
+    pred[1, 9, :] = pred[1, 5, :]
+    pred[1, 200, :4] = pred[1, 5, :4]
+    pred[1, 200, 4] = 0.25
+    _check_nms(pred, 0.25)
+
+
+# ------------------------------------------------------------------------------- RoI gathers
+def _roi_inputs(seed, n=2, g=26):
+    rng = np.random.RandomState(seed)
+    feat = rng.randn(n, 490, g, g).astype(np.float32)
+    rfeat = rng.rand(n, 10, g, g).astype(np.float32)
+    return feat, rfeat
+
+
+def _run_roi(feat, rfeat, rois, cap):
+    n, _, g, _ = feat.shape
+    f = torch.zeros(n, g, g, 512, dtype=torch.float16)
+    f[..., :490] = torch.from_numpy(feat).permute(0, 2, 3, 1).half()
+    r = torch.zeros(n, g, g, 32, dtype=torch.float16)
+    r[..., :10] = torch.from_numpy(rfeat).permute(0, 2, 3, 1).half()
+    rois_d = torch.zeros(cap, 5)
+    rois_d[:len(rois)] = torch.from_numpy(rois)
+    counts = torch.tensor([0, len(rois)], dtype=torch.int32)
+    out_ps = torch.full((cap, 512), 7.0, dtype=torch.float16, device=DEV)
+    out_ra = torch.full((cap, 496), 7.0, dtype=torch.float16, device=DEV)
+    ops.psroi_align(f.to(DEV), n, g, g, 512, 10, 7, 1 / 16., rois_d.to(DEV), counts.to(DEV), cap, out_ps, 512)
+    ops.roi_align(r.to(DEV), n, g, g, 32, 10, 7, 1 / 16., rois_d.to(DEV), counts.to(DEV), cap, out_ra, 496)
+    torch.cuda.synchronize()
+    # oracle on the same fp16-rounded maps
+    ref_ps = oroi.ps_roi_align(f[..., :490].float().permute(0, 3, 1, 2).numpy(), rois)
+    ref_ra = oroi.roi_align(r[..., :10].float().permute(0, 3, 1, 2).numpy(), rois)
+    return out_ps.float().cpu().numpy(), out_ra.float().cpu().numpy(), ref_ps, ref_ra
+
+
+def test_roi_gathers(golden_dir):
+    g = np.load(os.path.join(golden_dir, "roi_ops.npz"))
+    rng = np.random.RandomState(11)
+    feat = rng.randn(2, 490, 26, 26).astype(np.float32)
+    rfeat = rng.rand(2, 10, 26, 26).astype(np.float32)
+    rois = g["rois"]
+    cap = 64
+    ps, ra, ref_ps, ref_ra = _run_roi(feat, rfeat, rois, cap)
+    k = len(rois)
+    tol = 2e-3  # fp16 storage of maps and outputs
+    np.testing.assert_allclose(ps[:k, :490], ref_ps.reshape(k, -1), atol=tol * np.abs(ref_ps).max())
+    np.testing.assert_allclose(ra[:k, :490], ref_ra.reshape(k, -1), atol=tol)
+    # and against torchvision's own output on the fp32 maps (fp16 rounding of the inputs included)
+    np.testing.assert_allclose(ps[:k, :490], g["ps"].reshape(k, -1), atol=4e-3 * np.abs(g["ps"]).max())
+    np.testing.assert_allclose(ra[:k, :490], g["ra"].reshape(k, -1), atol=4e-3)
+    assert np.all(ps[:k, 490:] == 0) and np.all(ps[k:] == 0) and np.all(ra[k:] == 0)  # padding / dead rows zeroed
+
+
+def test_roi_gathers_empty_and_degenerate():
+    feat, rfeat = _roi_inputs(3)
+    rois = np.array([[0, 50, 50, 50, 50], [1, 400, 400, 500, 500], [0, -40, -40, -20, -20], [1, 0, 0, 416, 416]],
+                    dtype=np.float32)
+    ps, ra, ref_ps, ref_ra = _run_roi(feat, rfeat, rois, 8)
+    good = ~np.isnan(ref_ps.reshape(4, -1))
+    np.testing.assert_allclose(ps[:4, :490][good], ref_ps.reshape(4, -1)[good], atol=1e-2)
+    np.testing.assert_allclose(ra[:4, :490], ref_ra.reshape(4, -1), atol=2e-3)
+    ps, ra, _, _ = _run_roi(feat, rfeat, np.zeros((0, 5), np.float32), 8)
+    assert np.all(ps == 0) and np.all(ra == 0)

@@ -1,0 +1,132 @@
+"""Pins the oracle (oracle/) against outputs of the reference itself (tests/golden/*.npz, produced by
+tests/golden/make_golden.py from the unmodified reference) and against the installed torchvision for
+the third-party box ops.  CPU only."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from millieye_b200 import configs
+from oracle import boxes as obox
+from oracle import darknet as odark
+from oracle import fusion as ofus
+from oracle import roi as oroi
+from oracle import synth
+from oracle.parse_config import parse_model_config
+
+
+def _tiny_sd(seed, **kw):
+    from millieye_b200.models import Darknet
+    net = Darknet(configs.cfg_path("yolov3-tiny-12"))
+    return synth.fill_state_dict(net.state_dict(), seed=seed, **kw)
+
+
+def test_darknet_tiny_matches_reference(golden_dir):
+    g = np.load(os.path.join(golden_dir, "darknet_tiny12_96.npz"))
+    md = parse_model_config(configs.cfg_path("yolov3-tiny-12"))
+    sd = _tiny_sd(1)
+    assert list(sd.keys()) == list(g["keys"])
+    with torch.no_grad():
+        feat, yolo = odark.darknet_forward(md, sd, synth.synth_images(2, 96, seed=1))
+    np.testing.assert_allclose(feat.numpy(), g["featuremap"], rtol=1e-5, atol=1e-5)
+    np.testing.assert_allclose(yolo.numpy(), g["yolo"], rtol=1e-5, atol=1e-5)
+
+
+def test_darknet53_matches_reference(golden_dir):
+    from millieye_b200.models import Darknet
+    g = np.load(os.path.join(golden_dir, "darknet53_64.npz"))
+    md = parse_model_config(configs.cfg_path("yolov3"))
+    sd = synth.fill_state_dict(Darknet(configs.cfg_path("yolov3")).state_dict(), seed=2, conv_gain=0.6)
+    with torch.no_grad():
+        feat, yolo = odark.darknet_forward(md, sd, synth.synth_images(1, 64, seed=2))
+    assert feat is None  # block 8 of yolov3.cfg is a shortcut: no reference featuremap
+    np.testing.assert_allclose(yolo.numpy(), g["yolo"], rtol=2e-5, atol=2e-5)
+
+
+def test_yolo_row_order_is_anchor_major():
+    """Rows are anchor-major, then gy, then gx (reference models.py:142-177)."""
+    x = torch.zeros(1, 3 * 17, 2, 2)
+    x[0, 17 * 1 + 0, 1, 0] = 10.0  # anchor 1, tx at gy=1, gx=0
+    out = odark.yolo_decode(x, [(10, 14), (23, 27), (37, 58)], 12, 64)
+    row = 1 * 4 + 1 * 2 + 0
+    assert out[0, row, 0] == pytest.approx((1 / (1 + np.exp(-10.0)) + 0) * 32, rel=1e-6)
+    assert out[0, row, 1] == pytest.approx((0.5 + 1) * 32)
+
+
+@pytest.mark.parametrize("mode", [0, 1, 2])
+def test_fusion_matches_reference(golden_dir, mode):
+    from millieye_b200.my_models import Network, define_yolo
+    g = np.load(os.path.join(golden_dir, "fusion_tiny12_160.npz"))
+    model = Network(define_yolo(configs.cfg_path("yolov3-tiny-12")), conf_thresh=0.05)
+    sd = synth.fill_state_dict(model.state_dict(), seed=3, obj_bias=-0.5)
+    assert list(sd.keys()) == list(g["keys"])
+    md = parse_model_config(configs.cfg_path("yolov3-tiny-12"))
+    with torch.no_grad():
+        out = ofus.network_forward(md, sd, synth.synth_images(3, 160, seed=3), synth.synth_maps(3, 160, seed=3),
+                                   synth.synth_radar_boxes(3, seed=5), conf_thresh=0.05, model_mode=mode)
+    ref = g[f"mode{mode}"]
+    assert tuple(out.shape) == ref.shape
+    np.testing.assert_allclose(out.numpy(), ref, rtol=1e-4, atol=1e-4)
+
+
+@pytest.mark.parametrize("tag,mu,thr", [("trick", -6.0, 0.01), ("vanilla", -1.0, 0.2)])
+def test_nms_cpp_matches_reference(golden_dir, tag, mu, thr):
+    g = np.load(os.path.join(golden_dir, "nms_cpp.npz"))
+    pred = synth.synth_predictions(2, 2535, 12, seed=7, conf_mu=mu).numpy()
+    ncand = [(pred[i, :, 4] >= np.float32(thr)).sum() for i in range(2)]
+    assert list(g[f"{tag}_ncand"]) == ncand
+    assert (ncand[0] > 1000) == (tag == "vanilla")  # the two batched_nms code paths
+    dets, _ = obox.non_max_suppression_cpp(pred.copy(), thr)
+    for i in range(2):
+        np.testing.assert_array_equal(dets[i], g[f"{tag}_{i}"])  # bit-exact rows, same order
+
+
+@pytest.mark.parametrize("n", [0, 1, 17, 300, 1001, 1500])
+def test_batched_nms_matches_torchvision(n):
+    from torchvision.ops import batched_nms
+    rng = np.random.RandomState(n)
+    xy = rng.uniform(0, 400, (n, 2))
+    wh = rng.uniform(4, 150, (n, 2))
+    b = np.concatenate([xy, xy + wh], 1).astype(np.float32)
+    s = rng.rand(n).astype(np.float32)
+    lab = rng.randint(0, 12, n).astype(np.float32)
+    mine = obox.batched_nms(b, s, lab, 0.5)
+    theirs = batched_nms(torch.from_numpy(b), torch.from_numpy(s), torch.from_numpy(lab), 0.5).numpy()
+    np.testing.assert_array_equal(mine, theirs)
+
+
+def test_nms_ties_and_threshold_edges():
+    from torchvision.ops import nms
+    # equal scores: stable order keeps the lower index first; IoU exactly 0.5 is NOT suppressed (strict >)
+    b = np.array([[0, 0, 10, 10], [0, 0, 10, 10], [0, 0, 10, 5], [20, 20, 30, 30]], dtype=np.float32)
+    s = np.array([0.5, 0.5, 0.5, 0.9], dtype=np.float32)
+    mine = obox.nms(b, s, 0.5)
+    theirs = nms(torch.from_numpy(b), torch.from_numpy(s), 0.5).numpy()
+    np.testing.assert_array_equal(mine, theirs)
+    assert list(mine) == [3, 0, 2]
+
+
+def test_roi_ops_match_torchvision(golden_dir):
+    g = np.load(os.path.join(golden_dir, "roi_ops.npz"))
+    rng = np.random.RandomState(11)
+    feat = rng.randn(2, 490, 26, 26).astype(np.float32)
+    rfeat = rng.rand(2, 10, 26, 26).astype(np.float32)
+    np.testing.assert_allclose(oroi.ps_roi_align(feat, g["rois"]), g["ps"], rtol=0, atol=2e-6)
+    np.testing.assert_allclose(oroi.roi_align(rfeat, g["rois"]), g["ra"], rtol=0, atol=2e-6)
+
+
+def test_roi_empty_and_degenerate():
+    from torchvision.ops import roi_align
+    feat = np.random.RandomState(0).rand(1, 10, 26, 26).astype(np.float32)
+    assert oroi.roi_align(feat, np.zeros((0, 5), np.float32)).shape == (0, 10, 7, 7)
+    rois = np.array([[0, 50, 50, 50, 50], [0, 400, 400, 500, 500], [0, -40, -40, -20, -20]], dtype=np.float32)
+    ref = roi_align(torch.from_numpy(feat), torch.from_numpy(rois), (7, 7), 1 / 16.).numpy()
+    np.testing.assert_allclose(oroi.roi_align(feat, rois), ref, atol=2e-6)
+
+
+def test_conv_flops_match_survey():
+    md = parse_model_config(configs.cfg_path("yolov3"))
+    assert odark.conv_flops(md, 416) / 1e9 == pytest.approx(65.864, abs=0.01)
+    md = parse_model_config(configs.cfg_path("yolov3-tiny-12"))
+    assert odark.conv_flops(md, 416) / 1e9 == pytest.approx(5.459, abs=0.01)
