@@ -1,0 +1,139 @@
+"""CPU-only checks of the host side: cfg handling, state_dict compatibility, the C-ABI surface (the
+library loads and exports every symbol include/millieye_b200.h declares - no compute calls), loud
+failure without CUDA / without the library, plan description, weights-file format, sharding maths."""
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+from millieye_b200 import _lib, configs
+from millieye_b200.dist import shard_bounds, shard_rows_by_frame
+from millieye_b200.engine import describe_blocks
+from millieye_b200.models import Darknet
+from millieye_b200.my_models import Network, define_yolo
+from millieye_b200.parse_config import parse_data_config, parse_model_config
+from oracle import synth
+from oracle.parse_config import parse_model_config as oracle_parse
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF_CFG = "/root/reference/module3_our_dataset/config"
+
+
+@pytest.mark.parametrize("name", ["yolov3-tiny-12", "yolov3-tiny-coco", "yolov3"])
+def test_cfg_parsers_agree(name):
+    path = configs.cfg_path(name)
+    assert parse_model_config(path) == oracle_parse(path)
+    if os.path.isdir(REF_CFG):  # build container only: generated cfg == reference cfg, block by block
+        ref = oracle_parse(os.path.join(REF_CFG, name + ".cfg"))
+        mine = parse_model_config(path)
+        assert parse_model_config(os.path.join(REF_CFG, name + ".cfg")) == ref
+        assert len(ref) == len(mine)
+        keys = ("type", "batch_normalize", "filters", "size", "stride", "activation", "layers", "from", "mask",
+                "anchors", "classes")
+        for a, b in zip(mine[1:], ref[1:]):
+            for k in keys:
+                assert str(a.get(k)).replace(" ", "") == str(b.get(k)).replace(" ", "")
+
+
+def test_cfg_parser_rules(tmp_path):
+    p = tmp_path / "x.cfg"
+    p.write_text("[net]\nchannels=3\n# comment\n\n[convolutional]\nfilters = 8 \nsize=3\nstride=1\nactivation=leaky\n")
+    blocks = parse_model_config(str(p))
+    assert blocks[1]["batch_normalize"] == 0 and blocks[1]["filters"] == "8" and blocks[0]["channels"] == "3"
+    d = tmp_path / "x.data"
+    d.write_text("classes= 12\ntrain=a b\n# c\n\nnames=n.txt\n")
+    opts = parse_data_config(str(d))
+    assert opts["gpus"] == "0,1,2,3" and opts["train"] == ["a", "b"] and opts["names"] == "n.txt"
+
+
+def test_plan_description_matches_reference_shapes():
+    _, tiny = describe_blocks(parse_model_config(configs.cfg_path("yolov3-tiny-12")))
+    assert [b["type"] for b in tiny].count("convolutional") == 13 and len(tiny) == 24
+    assert tiny[20]["out_c"] == 384 and tiny[20]["layers"] == [19, 8] and tiny[17]["layers"] == [13]
+    assert tiny[15]["filters"] == 51 and not tiny[15]["bn"] and not tiny[15]["leaky"]
+    _, full = describe_blocks(parse_model_config(configs.cfg_path("yolov3")))
+    kinds = [b["type"] for b in full]
+    assert (len(full), kinds.count("convolutional"), kinds.count("shortcut"), kinds.count("route")) == (107, 75, 23, 4)
+    assert full[86]["out_c"] == 768 and full[98]["out_c"] == 384 and full[4]["src"] == 1
+    assert full[82]["anchors"] == [(116, 90), (156, 198), (373, 326)]
+
+
+def test_state_dict_keys_match_reference(golden_dir):
+    g = np.load(os.path.join(golden_dir, "fusion_tiny12_160.npz"))
+    model = Network(define_yolo(configs.cfg_path("yolov3-tiny-12")), conf_thresh=0.2)
+    assert list(model.state_dict().keys()) == list(g["keys"])
+    assert len(g["keys"]) == 123 and sum(k.startswith("base_detector.") for k in g["keys"]) == 70
+    for attr in ("base_detector", "refinement_head", "refine_threshold_radar", "seen", "conf_thresh", "class_idx"):
+        assert hasattr(model, attr)
+
+
+def test_header_symbols_exported(built_lib):
+    text = open(os.path.join(ROOT, "include", "millieye_b200.h")).read()
+    declared = set(re.findall(r"^(?:int|size_t)\s+(me_\w+)\s*\(", text, flags=re.M))
+    assert len(declared) >= 20
+    assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
+    handle = _lib.lib()
+    for name in declared:
+        assert hasattr(handle, name), f"{name} missing from {built_lib}"
+    assert handle.me_version() >= 100
+    assert [handle.me_conv_k_block(c) for c in (3, 16, 17, 32, 33, 64, 490)] == [16, 16, 32, 32, 64, 64, 64]
+    assert handle.me_conv_cin_pad(490) == 512 and handle.me_conv_cin_pad(16) == 16
+
+
+def test_no_cpu_fallback():
+    net = Darknet(configs.cfg_path("yolov3-tiny-12")).eval()
+    with pytest.raises(_lib.MeError):
+        net(torch.rand(1, 3, 96, 96))
+    from millieye_b200 import ops, utils
+    with pytest.raises(_lib.MeError):
+        utils.non_max_suppression_cpp(torch.rand(1, 10, 17), 0.1)
+    with pytest.raises(_lib.MeError):
+        ops.maxpool2(torch.zeros(1, 2, 2, 8, dtype=torch.float16), torch.zeros(1, 1, 1, 8, dtype=torch.float16), 1, 2, 2, 8, 8, 8, 2)
+
+
+def test_missing_library_fails_loudly(monkeypatch):
+    monkeypatch.setattr(_lib, "_LIB", None)
+    monkeypatch.setattr(_lib._build, "LIB", "/nonexistent/libmillieye_b200.so")
+    with pytest.raises(_lib.MeError, match="only implementation"):
+        _lib.lib()
+
+
+def test_product_does_not_import_oracle():
+    pkg = os.path.join(ROOT, "millieye_b200")
+    for fn in os.listdir(pkg):
+        if fn.endswith(".py"):
+            src = open(os.path.join(pkg, fn)).read()
+            assert not re.search(r"^\s*(from|import)\s+oracle", src, flags=re.M), fn
+
+
+def test_darknet_weights_file_roundtrip(tmp_path):
+    a = Darknet(configs.cfg_path("yolov3-tiny-12"))
+    a.load_state_dict(synth.fill_state_dict(a.state_dict(), seed=5))
+    a.seen = 1234
+    path = str(tmp_path / "t.weights")
+    a.save_darknet_weights(path, cutoff=len(a.module_list))
+    raw = np.fromfile(path, dtype=np.int32, count=5)
+    assert raw[3] == 1234
+    b = Darknet(configs.cfg_path("yolov3-tiny-12"))
+    b.load_darknet_weights(path)
+    assert b.seen == 1234
+    for (k, va), (_, vb) in zip(a.state_dict().items(), b.state_dict().items()):
+        if va.is_floating_point():
+            assert torch.equal(va, vb), k
+    n_floats = sum(v.numel() for k, v in a.state_dict().items() if v.is_floating_point())
+    assert os.path.getsize(path) == 20 + 4 * n_floats
+
+
+def test_shard_bounds():
+    for total in (1, 7, 32, 33, 64):
+        for world in (1, 2, 3, 8):
+            spans = [shard_bounds(total, world, r) for r in range(world)]
+            assert spans[0][0] == 0 and spans[-1][1] == total
+            assert all(a[1] == b[0] for a, b in zip(spans, spans[1:]))
+            sizes = [hi - lo for lo, hi in spans]
+            assert max(sizes) - min(sizes) <= 1
+    rows = torch.tensor([[0, 1.0], [3, 2.0], [4, 3.0], [7, 4.0]])
+    got = shard_rows_by_frame(rows, 8, 2, 1)
+    assert got.tolist() == [[0, 3.0], [3, 4.0]]
