@@ -91,6 +91,12 @@ int me_fold_first_weights(const float* w_oihw, const float* conv_bias, const flo
                           int cout, int cin, float* w_folded, float* bias_out, me_stream_t stream);
 int me_conv_first(const float* x_nchw, const float* w_folded, const float* bias, void* y_nhwc, int n, int h,
                   int w, int cin, int cout, int out_pitch, int act, me_stream_t stream);
+/* Same layer on tcgen05: producer warps im2col the fp32 image into a 128x32 fp16 tile in shared memory
+ * (K = 9*cin padded to 32), two tcgen05.mma per tile, fused bias/activation epilogue.  cin <= 3,
+ * cout in {16, 32, 64}; wk_scratch: fp16 [cout][32] device buffer owned by the caller. */
+int me_conv_first_tc(const float* x_nchw, const float* w_folded, const float* bias, void* wk_scratch,
+                     void* y_nhwc, int n, int h, int w, int cin, int cout, int out_pitch, int act,
+                     me_stream_t stream);
 
 /* ---- glue layers (A3) -------------------------------------------------------------- */
 /* MaxPool2d(2, stride) on NHWC fp16; stride 1 uses the right/bottom zero pad of

@@ -1,0 +1,244 @@
+// First conv (3x3 / stride 1 / pad 1, cin <= 3) on tcgen05 with an in-kernel im2col producer.
+//
+// The layer reads the caller's NCHW fp32 image directly: K = 9*cin = 27 (padded to 32) is too thin
+// for a TMA-fed pipeline, so 4 producer warps build the 128 x 32 fp16 A tile in shared memory
+// themselves (one output pixel per thread: 27 coalesced fp32 loads, zero fill at the border), in the
+// no-swizzle K-major canonical layout  addr(row, k8) = k8 * 2048 + row * 16  (8-row core matrices are
+// 128 contiguous bytes, LBO = 2048, SBO = 128), fence it to the async proxy and hand it to the MMA
+// warp through an mbarrier.  Two tcgen05.mma (K = 16 each) per tile accumulate into TMEM; 4 epilogue
+// warps add the folded-BN bias, apply the activation and write NHWC fp16 rows with 16-byte stores
+// (a warp's 32 rows are one contiguous span).  Replaces the Conv2d/BN/LeakyReLU of module 0
+// (yolov3/models.py:22-41, :252) - 0.3 GFLOP/frame of SIMT work that used to cost as much as ten
+// tensor-core layers.
+#include "common.cuh"
+#include "ptx.cuh"
+
+namespace me {
+namespace {
+
+constexpr int kTileM = 128;
+constexpr int kK = 32;                 // 27 real + 5 zero
+constexpr int kStages = 4;             // A tiles in flight = producer groups (one group owns one stage)
+constexpr int kABytes = kTileM * kK * 2;
+constexpr int kProdWarps = 4 * kStages;
+constexpr int kThreadsTC = 32 * (kProdWarps + 1 + 4);  // 16 producer warps, 1 MMA warp, 4 epilogue warps
+
+__device__ __forceinline__ void mbar_wait_spin(uint64_t* bar, uint32_t parity) {
+  while (!ptx::mbar_try_wait(bar, parity)) {
+  }
+}
+
+__device__ __forceinline__ uint64_t make_nosw_desc(uint32_t addr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((addr & 0x3FFFFu) >> 4);
+  d |= static_cast<uint64_t>(lbo_bytes >> 4) << 16;
+  d |= static_cast<uint64_t>(sbo_bytes >> 4) << 32;
+  d |= static_cast<uint64_t>(1u) << 46;  // descriptor version; layout_type 0 = no swizzle
+  return d;
+}
+
+template <int COUT>
+__global__ void __launch_bounds__(kThreadsTC, 1)
+conv_first_tc_kernel(const float* __restrict__ x, const __half* __restrict__ wk, const float* __restrict__ bias,
+                     __half* __restrict__ y, int n, int h, int w, int cin, int out_pitch, int act, int tiles) {
+  __shared__ __align__(1024) uint8_t s_a[kStages][kABytes];
+  __shared__ __align__(128) uint8_t s_b[COUT * kK * 2];
+  __shared__ float s_bias[COUT];
+  __shared__ __align__(8) uint64_t full_bar[kStages], empty_bar[kStages], tmem_full[2], tmem_empty[2];
+  __shared__ uint32_t tmem_ptr;
+  constexpr int TMEM_COLS = (2 * COUT <= 32) ? 32 : (2 * COUT <= 64) ? 64 : 128;
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int total_px = n * h * w;  // < 2^31, checked by the launcher
+
+  // weights: wk is [COUT][32] fp16 (k = c*9 + r*3 + s, zero padded) -> canonical layout, chunk-major
+  for (int i = threadIdx.x; i < COUT * 4; i += blockDim.x) {
+    const int o = i >> 2, k8 = i & 3;
+    *reinterpret_cast<uint4*>(s_b + k8 * (COUT * 16) + o * 16) = *reinterpret_cast<const uint4*>(wk + o * kK + k8 * 8);
+  }
+  for (int i = threadIdx.x; i < COUT; i += blockDim.x) s_bias[i] = bias[i];
+  if (warp == kProdWarps) {
+    if (ptx::elect_one()) {
+      for (int s = 0; s < kStages; ++s) {
+        ptx::mbar_init(&full_bar[s], 128);  // every producer thread arrives
+        ptx::mbar_init(&empty_bar[s], 1);
+      }
+      for (int a = 0; a < 2; ++a) {
+        ptx::mbar_init(&tmem_full[a], 1);
+        ptx::mbar_init(&tmem_empty[a], 4);
+      }
+      ptx::fence_mbar_init();
+    }
+    __syncwarp();
+    ptx::tmem_alloc(&tmem_ptr, TMEM_COLS);
+    ptx::tmem_relinquish();
+  }
+  ptx::fence_proxy_async_smem();  // s_b was written through the generic proxy
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = tmem_ptr;
+
+  if (warp < kProdWarps) {
+    // ------------------------------------------------------------ im2col producers
+    // 4 groups of 128 threads; group g fills stage g with every 4th tile of this CTA, so four tiles'
+    // worth of global loads are in flight per SM (the layer is HBM-bound: 66 MB in, 354 MB out at batch 32).
+    const int row = threadIdx.x & 127;
+    const uint32_t stage = warp >> 2;
+    uint32_t phase = 0;
+    for (int tile = blockIdx.x + stage * gridDim.x; tile < tiles; tile += kStages * gridDim.x) {
+      const int pix = tile * kTileM + row;
+      float v[27];
+#pragma unroll
+      for (int i = 0; i < 27; ++i) v[i] = 0.f;
+      if (pix < total_px) {
+        const int px = pix % w;
+        const int t = pix / w;
+        const int py = t % h;
+        const int img = t / h;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          if (c >= cin) break;
+          const float* plane = x + (1LL * img * cin + c) * h * w;
+#pragma unroll
+          for (int r = 0; r < 3; ++r) {
+            const int yy = py + r - 1;
+            const bool yok = yy >= 0 && yy < h;
+#pragma unroll
+            for (int s = 0; s < 3; ++s) {
+              const int xx = px + s - 1;
+              if (yok && xx >= 0 && xx < w) v[c * 9 + r * 3 + s] = __ldg(plane + 1LL * yy * w + xx);
+            }
+          }
+        }
+      }
+      mbar_wait_spin(&empty_bar[stage], phase ^ 1);
+      uint8_t* dst = s_a[stage] + row * 16;
+#pragma unroll
+      for (int k8 = 0; k8 < 4; ++k8) {
+        uint4 pk;
+        __half2* ph = reinterpret_cast<__half2*>(&pk);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int k = k8 * 8 + 2 * e;
+          ph[e] = __floats2half2_rn(k < 27 ? v[k] : 0.f, k + 1 < 27 ? v[k + 1] : 0.f);
+        }
+        *reinterpret_cast<uint4*>(dst + k8 * (kTileM * 16)) = pk;
+      }
+      ptx::fence_proxy_async_smem();
+      ptx::mbar_arrive(&full_bar[stage]);
+      phase ^= 1;
+    }
+  } else if (warp == kProdWarps) {
+    // ------------------------------------------------------------ MMA issuer
+    if (ptx::elect_one()) {
+      constexpr uint32_t idesc = ptx::make_idesc_f16(kTileM, COUT);
+      const uint32_t b_addr = ptx::smem_u32(s_b);
+      uint32_t stage = 0, phase = 0;
+      int it = 0;
+      for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++it) {
+        const int acc = it & 1;
+        mbar_wait_spin(&tmem_empty[acc], ((it >> 1) & 1) ^ 1);
+        mbar_wait_spin(&full_bar[stage], phase);
+        ptx::tc_fence_after();
+        const uint32_t a_addr = ptx::smem_u32(s_a[stage]);
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+          const uint64_t adesc = make_nosw_desc(a_addr + k * 2 * (kTileM * 16), kTileM * 16, 128);
+          const uint64_t bdesc = make_nosw_desc(b_addr + k * 2 * (COUT * 16), COUT * 16, 128);
+          ptx::umma_f16_ss(tmem_base + acc * COUT, adesc, bdesc, idesc, k);
+        }
+        ptx::umma_commit(&empty_bar[stage]);
+        ptx::umma_commit(&tmem_full[acc]);
+        if (++stage == kStages) { stage = 0; phase ^= 1; }
+      }
+    }
+  } else {
+    // ------------------------------------------------------------ epilogue (last 4 warps)
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++it) {
+      const int acc = it & 1;
+      mbar_wait_spin(&tmem_full[acc], (it >> 1) & 1);
+      ptx::tc_fence_after();
+      const uint32_t taddr = tmem_base + acc * COUT + (static_cast<uint32_t>(q * 32) << 16);
+      const int pix = tile * kTileM + row;
+      __half* dst = y + 1LL * pix * out_pitch;
+#pragma unroll
+      for (int c = 0; c < COUT; c += 16) {
+        uint32_t r[16];
+        ptx::tmem_ld_32x32b_x16(taddr + c, r);
+        ptx::tmem_ld_wait();
+        uint4 o[2];
+        __half2* oh = reinterpret_cast<__half2*>(o);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+          float a = __uint_as_float(r[2 * e]) + s_bias[c + 2 * e];
+          float b = __uint_as_float(r[2 * e + 1]) + s_bias[c + 2 * e + 1];
+          if (act == ME_ACT_LEAKY) {
+            a = a > 0.f ? a : 0.1f * a;
+            b = b > 0.f ? b : 0.1f * b;
+          } else if (act == ME_ACT_SIGMOID) {
+            a = 1.f / (1.f + __expf(-a));
+            b = 1.f / (1.f + __expf(-b));
+          }
+          oh[e] = __floats2half2_rn(a, b);
+        }
+        if (pix < total_px) {
+          *reinterpret_cast<uint4*>(dst + c) = o[0];
+          *reinterpret_cast<uint4*>(dst + c + 8) = o[1];
+        }
+      }
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(&tmem_empty[acc]);
+    }
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  if (warp == kProdWarps) ptx::tmem_dealloc(tmem_base, TMEM_COLS);
+}
+
+__global__ void pack_first_tc_kernel(const float* __restrict__ w_folded, int cout, int per_out, __half* __restrict__ wk) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= cout * kK) return;
+  const int o = i / kK, k = i - o * kK;
+  wk[i] = __float2half_rn(k < per_out ? w_folded[o * per_out + k] : 0.f);
+}
+
+}  // namespace
+}  // namespace me
+
+extern "C" {
+
+// wk: fp16 [cout][32] scratch owned by the caller (filled here from the folded fp32 weights).
+int me_conv_first_tc(const float* x_nchw, const float* w_folded, const float* bias, void* wk_scratch, void* y_nhwc,
+                     int n, int h, int w, int cin, int cout, int out_pitch, int act, me_stream_t stream_) {
+  using namespace me;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  ME_REQUIRE(x_nchw && w_folded && bias && wk_scratch && y_nhwc, "conv_first_tc: null argument");
+  ME_REQUIRE(cin >= 1 && cin <= 3, "conv_first_tc: cin %d must be 1..3", cin);
+  ME_REQUIRE(out_pitch >= cout && out_pitch % 8 == 0, "conv_first_tc: bad out_pitch %d", out_pitch);
+  __half* wk = static_cast<__half*>(wk_scratch);
+  pack_first_tc_kernel<<<ceil_div(cout * kK, 128), 128, 0, stream>>>(w_folded, cout, cin * 9, wk);
+  ME_LAUNCH_CHECK();
+  const long long total = 1LL * n * h * w;
+  ME_REQUIRE(total > 0 && total < (1LL << 31) - kTileM, "conv_first_tc: pixel count out of range");
+  const int tiles = static_cast<int>((total + kTileM - 1) / kTileM);
+  int grid = sm_count();
+  if (grid <= 0) grid = 148;
+  if (grid > tiles) grid = tiles;
+  __half* y = static_cast<__half*>(y_nhwc);
+  switch (cout) {
+    case 16: conv_first_tc_kernel<16><<<grid, kThreadsTC, 0, stream>>>(x_nchw, wk, bias, y, n, h, w, cin, out_pitch, act, tiles); break;
+    case 32: conv_first_tc_kernel<32><<<grid, kThreadsTC, 0, stream>>>(x_nchw, wk, bias, y, n, h, w, cin, out_pitch, act, tiles); break;
+    case 64: conv_first_tc_kernel<64><<<grid, kThreadsTC, 0, stream>>>(x_nchw, wk, bias, y, n, h, w, cin, out_pitch, act, tiles); break;
+    default: return fail(ME_ERR_UNSUPPORTED, "conv_first_tc: cout %d unsupported (16, 32 or 64)", cout);
+  }
+  ME_LAUNCH_CHECK();
+  return ME_OK;
+}
+
+}  // extern "C"

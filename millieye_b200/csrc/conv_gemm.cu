@@ -17,8 +17,13 @@
 // and refinement_head.net0 (:238-241).
 #include "common.cuh"
 #include "ptx.cuh"
+#include <cstdlib>
 
 namespace me {
+
+int conv_gemm_pair(int bn, const me_conv_desc* d, const void* x, const void* w, const float* bias, const void* residual,
+                   void* y, cudaStream_t stream);  // conv_gemm_pair.cu
+
 namespace {
 
 constexpr int kBM = 128;
@@ -380,6 +385,25 @@ int launch(const me_conv_desc* d, const void* x, const void* w, const float* bia
 }
 
 }  // namespace
+
+unsigned long long* conv_debug_word() { return g_debug_dev; }
+int conv_ensure_debug_word() { return ensure_debug_word(); }
+
+// 0 = automatic, 1 = single-CTA tiles only, 2 = CTA pairs with N=128, 3 = CTA pairs with N=256 (where legal)
+static int conv_mode() {
+  static int mode = -1;
+  if (mode < 0) {
+    const char* e = getenv("ME_CONV_MODE");
+    mode = 0;
+    if (e) {
+      if (!strcmp(e, "single")) mode = 1;
+      else if (!strcmp(e, "pair128")) mode = 2;
+      else if (!strcmp(e, "pair256")) mode = 3;
+    }
+  }
+  return mode;
+}
+
 }  // namespace me
 
 extern "C" {
@@ -410,6 +434,18 @@ int me_conv_gemm(const me_conv_desc* d, const void* x, const void* w_packed, con
   const bool f32 = d->out_f32 != 0;
   const int cout = d->cout;
 #define ME_GO(BN, BK, F32) return launch<BN, BK, F32>(d, x, w_packed, bias, residual, y, stream)
+  if (bk == 64 && !f32 && cout >= 128) {
+    // CTA pairs (256 x BN tiles) halve the shared-memory bytes per flop; worth it once the layer has
+    // enough pair tiles to fill the 74 SM pairs.
+    const int pad = (d->ksize - 1) / 2;
+    const long long m = 1LL * d->n * ((d->h + 2 * pad - d->ksize) / d->stride + 1) * ((d->w + 2 * pad - d->ksize) / d->stride + 1);
+    const int mode = conv_mode();
+    int pair_bn = 0;
+    if (mode == 2) pair_bn = 128;
+    else if (mode == 3) pair_bn = cout >= 256 ? 256 : 128;
+    else if (mode == 0 && m >= 256) pair_bn = cout >= 256 ? 256 : 128;
+    if (pair_bn) return conv_gemm_pair(pair_bn, d, x, w_packed, bias, residual, y, stream);
+  }
   if (bk == 64) {
     if (f32) {
       if (cout >= 128) ME_GO(128, 64, true);

@@ -1,0 +1,378 @@
+// CTA-pair (cta_group::2) variant of the fused conv implicit GEMM for the large layers.
+//
+// Why: with one CTA per 128 x 128 tile every tcgen05.mma (K=16) reads 8 KB of operands from shared
+// memory in ~64 clocks while TMA refills the same 8 KB - 256 B/clk against a 128 B/clk shared-memory
+// port, which is what held the 3x3 layers at ~65 % of the tensor peak (profiles/round1).  A CTA pair
+// computes a 256 x BN tile with ONE instruction stream: each CTA stages its own 128 rows of A and only
+// BN/2 rows of the weights, the pair's tensor cores read both halves of B, so operand bytes per flop
+// halve.  BN = 256 gives 64 B/clk of reads + 64 B/clk of fills per CTA.
+//
+// Structure (per CTA, roles as in conv_gemm.cu):
+//   warp 0   TMA producer for this CTA's A rows (im2col or tiled) and its half of the B rows; the byte
+//            count lands on the LEADER CTA's full barrier (cp.async.bulk.tensor ... .cta_group::2).
+//   warp 1   leader only: waits the full barrier, issues tcgen05.mma.cta_group::2 (M=256, N=BN) and
+//            multicast-commits to the empty / tmem_full barriers of both CTAs.
+//   warps 2-5 epilogue over this CTA's 128 accumulator rows (own TMEM), same fused epilogue + TMA store;
+//            both CTAs release the accumulator on the leader's tmem_empty barrier (8 arrivals).
+#include "common.cuh"
+#include "ptx.cuh"
+
+namespace me {
+
+// defined in conv_gemm.cu
+unsigned long long* conv_debug_word();
+int conv_ensure_debug_word();
+
+namespace {
+
+constexpr int kBM = 128;       // rows per CTA (256 per pair)
+constexpr int kThreads = 192;
+constexpr int kEpiThreads = 128;
+constexpr uint32_t kEpiBarrierId = 1;
+constexpr int kMaxStages = 8;
+constexpr int kBK = 64;
+
+struct PairParams {
+  int M;
+  int Ho, Wo;
+  int stride, pad;
+  int kb_per_tap;
+  int num_kb;
+  int tiles_m, tiles_n;   // in pair tiles: 256 x BN
+  int act;
+  int has_res;
+  int im2col;
+  int stages;
+  const float* bias;
+  unsigned long long* debug;
+};
+
+template <int BN>
+struct PCfg {
+  static constexpr int A_BYTES = kBM * kBK * 2;
+  static constexpr int B_BYTES = (BN / 2) * kBK * 2;
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int SUB_COLS = 64;                 // fp16, 128-byte staging rows
+  static constexpr int NUM_SUB = BN / SUB_COLS;
+  static constexpr int SUB_BYTES = kBM * 128;
+  static constexpr int STAGING_BYTES = NUM_SUB * SUB_BYTES;
+  static constexpr int TMEM_COLS = (2 * BN <= 256) ? 256 : 512;
+  static constexpr int TAIL_BYTES = BN * 4 + 64 * 8 + 16;
+  static constexpr int smem_bytes(int stages) { return 1024 + stages * STAGE_BYTES + STAGING_BYTES + TAIL_BYTES; }
+  static_assert(BN == 128 || BN == 256, "pair tile N");
+};
+
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, unsigned long long* dbg, uint32_t tag) {
+  if (ptx::mbar_try_wait(bar, parity)) return;
+  const long long t0 = clock64();
+  uint32_t spins = 0;
+  while (!ptx::mbar_try_wait(bar, parity)) {
+    if ((++spins & 1023u) == 0 && clock64() - t0 > 4000000000LL) {
+      if (dbg) {
+        *reinterpret_cast<volatile unsigned long long*>(dbg) =
+            (static_cast<unsigned long long>(tag | 0x8000u) << 32) | (static_cast<unsigned long long>(blockIdx.x) << 8) | parity | 0x80u;
+        __threadfence_system();
+      }
+      __trap();
+    }
+  }
+}
+
+__device__ __forceinline__ float apply_act(float v, int act) {
+  if (act == ME_ACT_LEAKY) return v > 0.f ? v : 0.1f * v;
+  if (act == ME_ACT_SIGMOID) return 1.f / (1.f + __expf(-v));
+  return v;
+}
+
+template <int BN>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
+conv_gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                      const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmR,
+                      const PairParams p) {
+  using C = PCfg<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* stage_base = smem;
+  uint8_t* staging = smem + p.stages * C::STAGE_BYTES;
+  float* s_bias = reinterpret_cast<float*>(staging + C::STAGING_BYTES);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_bias + BN);
+  uint64_t* full_bar = bars;                    // used in the leader CTA only
+  uint64_t* empty_bar = bars + kMaxStages;      // per CTA, multicast-arrived by the leader's commits
+  uint64_t* tmem_full = bars + 2 * kMaxStages;  // per CTA
+  uint64_t* tmem_empty = tmem_full + 2;         // leader CTA only, 8 arrivals
+  uint64_t* res_full = tmem_empty + 2;          // per CTA
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(res_full + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = ptx::cluster_ctarank();
+  const bool leader = rank == 0;
+  const int pair = static_cast<int>(ptx::cluster_id_x());
+  const int npairs = static_cast<int>(ptx::num_clusters_x());
+  const int total_tiles = p.tiles_m * p.tiles_n;
+
+  if (warp == 0 && ptx::elect_one()) {
+    ptx::prefetch_tmap(&tmA);
+    ptx::prefetch_tmap(&tmB);
+    ptx::prefetch_tmap(&tmC);
+    if (p.has_res) ptx::prefetch_tmap(&tmR);
+  }
+  if (warp == 1) {
+    if (ptx::elect_one()) {
+      for (int s = 0; s < p.stages; ++s) {
+        ptx::mbar_init(&full_bar[s], 1);
+        ptx::mbar_init(&empty_bar[s], 1);
+      }
+      for (int a = 0; a < 2; ++a) {
+        ptx::mbar_init(&tmem_full[a], 1);
+        ptx::mbar_init(&tmem_empty[a], 8);  // 4 epilogue warps x 2 CTAs
+      }
+      ptx::mbar_init(res_full, 1);
+      ptx::fence_mbar_init();
+    }
+    __syncwarp();
+  }
+  ptx::cluster_sync();  // both CTAs' barriers exist before any remote arrive / multicast commit
+  if (warp == 1) {
+    ptx::tmem_alloc_pair(tmem_ptr, C::TMEM_COLS);
+    ptx::tmem_relinquish_pair();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer (both CTAs)
+    if (ptx::elect_one()) {
+      uint32_t stage = 0, phase = 0;
+      for (int tile = pair; tile < total_tiles; tile += npairs) {
+        const int tm = tile / p.tiles_n, tn = tile - tm * p.tiles_n;
+        int m0 = tm * 2 * kBM + static_cast<int>(rank) * kBM;         // this CTA's 128 rows
+        if (m0 >= p.M) m0 = 0;  // ragged last pair: rows are discarded by the epilogue, load something valid
+        const int nb = tn * BN + static_cast<int>(rank) * (BN / 2);   // this CTA's half of the weight rows
+        int cw = 0, ch = 0, cn = 0;
+        if (p.im2col) {
+          const int q0 = m0 % p.Wo;
+          const int t = m0 / p.Wo;
+          cw = q0 * p.stride - p.pad;
+          ch = (t % p.Ho) * p.stride - p.pad;
+          cn = t / p.Ho;
+        }
+        int tap = 0, cb = 0;
+        for (int kb = 0; kb < p.num_kb; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1, p.debug, 0x100u + stage);
+          uint8_t* sa = stage_base + stage * C::STAGE_BYTES;
+          uint8_t* sb = sa + C::A_BYTES;
+          const uint32_t full_leader = ptx::mapa(ptx::smem_u32(&full_bar[stage]), 0);
+          if (leader) ptx::mbar_arrive_expect_tx(&full_bar[stage], 2 * C::STAGE_BYTES);  // both CTAs' bytes
+          if (p.im2col) {
+            const int r = tap / 3, s = tap - r * 3;
+            ptx::tma_load_im2col_4d_pair(&tmA, full_leader, sa, cb * kBK, cw, ch, cn, (uint16_t)s, (uint16_t)r);
+          } else {
+            ptx::tma_load_2d_pair(&tmA, full_leader, sa, cb * kBK, m0);
+          }
+          ptx::tma_load_2d_pair(&tmB, full_leader, sb, kb * kBK, nb);
+          if (++cb == p.kb_per_tap) { cb = 0; ++tap; }
+          if (++stage == (uint32_t)p.stages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer (leader CTA only)
+    if (leader && ptx::elect_one()) {
+      constexpr uint32_t idesc = ptx::make_idesc_f16(2 * kBM, BN);
+      uint32_t stage = 0, phase = 0;
+      int it = 0;
+      for (int tile = pair; tile < total_tiles; tile += npairs, ++it) {
+        const int acc = it & 1;
+        const uint32_t acc_phase = (it >> 1) & 1;
+        mbar_wait(&tmem_empty[acc], acc_phase ^ 1, p.debug, 0x200u + acc);
+        ptx::tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BN;
+        for (int kb = 0; kb < p.num_kb; ++kb) {
+          mbar_wait(&full_bar[stage], phase, p.debug, 0x300u + stage);
+          ptx::tc_fence_after();
+          const uint32_t a_addr = ptx::smem_u32(stage_base + stage * C::STAGE_BYTES);
+          const uint32_t b_addr = a_addr + C::A_BYTES;
+#pragma unroll
+          for (int k = 0; k < kBK / 16; ++k) {
+            const uint64_t adesc = ptx::make_kmajor_desc(a_addr + k * 32, kBK * 2);
+            const uint64_t bdesc = ptx::make_kmajor_desc(b_addr + k * 32, kBK * 2);
+            ptx::umma_f16_ss_pair(d_tmem, adesc, bdesc, idesc, (kb | k) != 0 ? 1u : 0u);
+          }
+          ptx::umma_commit_pair(&empty_bar[stage], 0b11);   // frees the stage in both CTAs
+          if (++stage == (uint32_t)p.stages) { stage = 0; phase ^= 1; }
+        }
+        ptx::umma_commit_pair(&tmem_full[acc], 0b11);       // accumulator ready in both CTAs
+      }
+    }
+    __syncwarp();
+  } else {
+    // ------------------------------------------------------------------ epilogue (warps 2..5, both CTAs)
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    const int etid = threadIdx.x - 64;
+    const bool eleader = (threadIdx.x == 64);
+    int it = 0;
+    for (int tile = pair; tile < total_tiles; tile += npairs, ++it) {
+      const int tm = tile / p.tiles_n, tn = tile - tm * p.tiles_n;
+      const int m0 = tm * 2 * kBM + static_cast<int>(rank) * kBM, n0 = tn * BN;
+      const int acc = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1;
+      if (eleader) {
+        ptx::tma_store_wait_read0();
+        if (p.has_res) {
+          ptx::mbar_arrive_expect_tx(res_full, C::STAGING_BYTES);
+#pragma unroll
+          for (int sub = 0; sub < C::NUM_SUB; ++sub)
+            ptx::tma_load_2d(&tmR, res_full, staging + sub * C::SUB_BYTES, n0 + sub * C::SUB_COLS, m0 < p.M ? m0 : 0);
+        }
+      }
+      for (int i = etid; i < BN; i += kEpiThreads) s_bias[i] = p.bias[n0 + i];
+      ptx::named_bar_sync(kEpiBarrierId, kEpiThreads);
+      mbar_wait(&tmem_full[acc], acc_phase, p.debug, 0x400u + acc);
+      ptx::tc_fence_after();
+      if (p.has_res) mbar_wait(res_full, it & 1, p.debug, 0x500u);
+
+      const uint32_t t_row = tmem_base + acc * BN + (static_cast<uint32_t>(q * 32) << 16);
+#pragma unroll 1
+      for (int c = 0; c < BN; c += 32) {
+        uint32_t r[32];
+        ptx::tmem_ld_32x32b_x32(t_row + c, r);
+        ptx::tmem_ld_wait();
+        float v[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = apply_act(__uint_as_float(r[j]) + s_bias[c + j], p.act);
+        uint8_t* sub = staging + (c / C::SUB_COLS) * C::SUB_BYTES;
+        const uint32_t rbase = row * 128 + (c % C::SUB_COLS) * 2;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          uint32_t off = rbase + j * 16;
+          off ^= ((off >> 7) & 7u) << 4;
+          uint4* dst = reinterpret_cast<uint4*>(sub + off);
+          float* vv = v + 8 * j;
+          if (p.has_res) {
+            const uint4 rr = *dst;
+            const __half2* rh = reinterpret_cast<const __half2*>(&rr);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const float2 f = __half22float2(rh[e]);
+              vv[2 * e] += f.x;
+              vv[2 * e + 1] += f.y;
+            }
+          }
+          uint4 o;
+          __half2* oh = reinterpret_cast<__half2*>(&o);
+#pragma unroll
+          for (int e = 0; e < 4; ++e) oh[e] = __floats2half2_rn(vv[2 * e], vv[2 * e + 1]);
+          *dst = o;
+        }
+      }
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive_cluster(ptx::mapa(ptx::smem_u32(&tmem_empty[acc]), 0));
+      ptx::fence_proxy_async_smem();
+      ptx::named_bar_sync(kEpiBarrierId, kEpiThreads);
+      if (eleader && m0 < p.M) {
+#pragma unroll
+        for (int sub = 0; sub < C::NUM_SUB; ++sub)
+          ptx::tma_store_2d(&tmC, staging + sub * C::SUB_BYTES, n0 + sub * C::SUB_COLS, m0);
+        ptx::tma_store_commit();
+      }
+    }
+    if (eleader) ptx::tma_store_wait_all0();
+  }
+
+  ptx::tc_fence_before();
+  ptx::cluster_sync();  // the peer may still be reading our barriers / issuing MMAs on our TMEM
+  ptx::tc_fence_after();
+  if (warp == 1) ptx::tmem_dealloc_pair(tmem_base, C::TMEM_COLS);
+}
+
+template <int BN>
+int launch_pair(const me_conv_desc* d, const void* x, const void* w, const float* bias, const void* residual, void* y,
+                cudaStream_t stream) {
+  using C = PCfg<BN>;
+  const int pad = (d->ksize - 1) / 2;
+  const int Ho = (d->h + 2 * pad - d->ksize) / d->stride + 1;
+  const int Wo = (d->w + 2 * pad - d->ksize) / d->stride + 1;
+  const int M = d->n * Ho * Wo;
+  const int taps = d->ksize * d->ksize;
+  const int cin_pad = round_up(d->cin, kBK);
+  const int ktot = taps * cin_pad;
+
+  PairParams p{};
+  p.M = M;
+  p.Ho = Ho;
+  p.Wo = Wo;
+  p.stride = d->stride;
+  p.pad = pad;
+  p.kb_per_tap = cin_pad / kBK;
+  p.num_kb = taps * p.kb_per_tap;
+  p.tiles_m = ceil_div(M, 2 * kBM);
+  p.tiles_n = ceil_div(d->cout, BN);
+  p.act = d->act;
+  p.has_res = (d->res_pitch > 0 && residual != nullptr) ? 1 : 0;
+  p.im2col = (d->ksize == 3) ? 1 : 0;
+  p.bias = bias;
+  int rc = conv_ensure_debug_word();
+  if (rc != ME_OK) return rc;
+  p.debug = conv_debug_word();
+
+  int stages = (227 * 1024 - 1024 - C::STAGING_BYTES - C::TAIL_BYTES) / C::STAGE_BYTES;
+  if (stages > kMaxStages) stages = kMaxStages;
+  ME_REQUIRE(stages >= 2, "conv(pair): not enough shared memory");
+  p.stages = stages;
+  const int smem = C::smem_bytes(stages);
+
+  CUtensorMap tmA, tmB, tmC, tmR;
+  if (p.im2col) {
+    rc = encode_im2col_nhwc(&tmA, x, d->n, d->h, d->w, d->cin, d->in_pitch, d->ksize, pad, d->stride, kBK, kBM,
+                            CU_TENSOR_MAP_SWIZZLE_128B);
+  } else {
+    rc = encode_tiled_2d(&tmA, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, x, d->cin, M, d->in_pitch, kBK, kBM,
+                         CU_TENSOR_MAP_SWIZZLE_128B);
+  }
+  if (rc != ME_OK) return rc;
+  rc = encode_tiled_2d(&tmB, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, w, ktot, d->cout, ktot, kBK, BN / 2,
+                       CU_TENSOR_MAP_SWIZZLE_128B);
+  if (rc != ME_OK) return rc;
+  rc = encode_tiled_2d(&tmC, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, y, d->cout, M, d->out_pitch, C::SUB_COLS, kBM,
+                       CU_TENSOR_MAP_SWIZZLE_128B);
+  if (rc != ME_OK) return rc;
+  if (p.has_res) {
+    rc = encode_tiled_2d(&tmR, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, residual, d->cout, M, d->res_pitch, C::SUB_COLS, kBM,
+                         CU_TENSOR_MAP_SWIZZLE_128B);
+    if (rc != ME_OK) return rc;
+  } else {
+    tmR = tmC;
+  }
+
+  auto kern = conv_gemm_pair_kernel<BN>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    ME_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    attr_set = true;
+  }
+  const int total = p.tiles_m * p.tiles_n;
+  int sms = sm_count();
+  if (sms <= 0) sms = 148;
+  int pairs = sms / 2;
+  if (pairs > total) pairs = total;
+  kern<<<2 * pairs, kThreads, smem, stream>>>(tmA, tmB, tmC, tmR, p);
+  ME_LAUNCH_CHECK();
+  return ME_OK;
+}
+
+}  // namespace
+
+// Entry used by me_conv_gemm's dispatcher. bn is 128 or 256.
+int conv_gemm_pair(int bn, const me_conv_desc* d, const void* x, const void* w, const float* bias, const void* residual,
+                   void* y, cudaStream_t stream) {
+  if (bn == 256) return launch_pair<256>(d, x, w, bias, residual, y, stream);
+  return launch_pair<128>(d, x, w, bias, residual, y, stream);
+}
+
+}  // namespace me

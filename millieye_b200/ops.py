@@ -77,6 +77,7 @@ def conv_gemm(x, packed, n, h, w, in_pitch, out, out_pitch, stride=1, act=ME_ACT
 class FirstConv:
     def __init__(self, w, bias, cin, cout):
         self.w, self.bias, self.cin, self.cout = w, bias, cin, cout
+        self.wk = torch.zeros((cout, 32), dtype=torch.float16, device=w.device)  # tensor-core weight tile
 
 
 def pack_first_conv(weight, conv_bias=None, bn=None):
@@ -98,11 +99,15 @@ def pack_first_conv(weight, conv_bias=None, bn=None):
     return FirstConv(wf, bias, cin, cout)
 
 
-def conv_first(x_nchw, first, out, out_pitch, act=ME_ACT_LEAKY):
+def conv_first(x_nchw, first, out, out_pitch, act=ME_ACT_LEAKY, tensor_cores=True):
     _need_cuda(x_nchw, out)
     assert x_nchw.dtype == torch.float32 and x_nchw.is_contiguous()
     n, c, h, w = x_nchw.shape
     assert c == first.cin
+    if tensor_cores and c <= 3 and first.cout in (16, 32, 64):
+        check(_lib.lib().me_conv_first_tc(ptr(x_nchw), ptr(first.w), ptr(first.bias), ptr(first.wk), ptr(out), n, h, w,
+                                          c, first.cout, out_pitch, act, stream_ptr()), "me_conv_first_tc")
+        return out
     check(_lib.lib().me_conv_first(ptr(x_nchw), ptr(first.w), ptr(first.bias), ptr(out), n, h, w, c, first.cout,
                                    out_pitch, act, stream_ptr()), "me_conv_first")
     return out

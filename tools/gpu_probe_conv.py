@@ -31,6 +31,15 @@ CASES = {
     "big_3x3_256_512": dict(n=8, h=26, w=26, cin=256, cout=512, k=3, s=1, act=1, bn=True, time=True),
     "big_1x1_64_32_208": dict(n=8, h=208, w=208, cin=64, cout=32, k=1, s=1, act=1, bn=True, time=True),
     "big_3x3_32_64_208": dict(n=8, h=208, w=208, cin=32, cout=64, k=3, s=1, act=1, bn=True, time=True),
+    # Darknet-53 layer shapes at batch 32 (timing, GPU reference would be too slow on CPU -> spot check only)
+    "d53_104_3x3_64_128_res": dict(n=32, h=104, w=104, cin=64, cout=128, k=3, s=1, act=1, bn=True, res=True, time=True, spot=True),
+    "d53_52_1x1_256_128": dict(n=32, h=52, w=52, cin=256, cout=128, k=1, s=1, act=1, bn=True, time=True, spot=True),
+    "d53_52_3x3_128_256_res": dict(n=32, h=52, w=52, cin=128, cout=256, k=3, s=1, act=1, bn=True, res=True, time=True, spot=True),
+    "d53_26_1x1_512_256": dict(n=32, h=26, w=26, cin=512, cout=256, k=1, s=1, act=1, bn=True, time=True, spot=True),
+    "d53_26_3x3_256_512_res": dict(n=32, h=26, w=26, cin=256, cout=512, k=3, s=1, act=1, bn=True, res=True, time=True, spot=True),
+    "d53_13_1x1_1024_512": dict(n=32, h=13, w=13, cin=1024, cout=512, k=1, s=1, act=1, bn=True, time=True, spot=True),
+    "d53_13_3x3_512_1024_res": dict(n=32, h=13, w=13, cin=512, cout=1024, k=3, s=1, act=1, bn=True, res=True, time=True, spot=True),
+    "d53_26_3x3_s2_256_512": dict(n=32, h=52, w=52, cin=256, cout=512, k=3, s=2, act=1, bn=True, time=True, spot=True),
 }
 
 
@@ -119,7 +128,10 @@ def main():
     if len(sys.argv) > 1:
         run_case(sys.argv[1])
         return
+    flt = os.environ.get("PROBE_FILTER", "")
     for name in CASES:
+        if flt and not any(name.startswith(f) for f in flt.split(",")):
+            continue
         t0 = time.time()
         try:
             r = subprocess.run([sys.executable, os.path.abspath(__file__), name], capture_output=True, text=True,
