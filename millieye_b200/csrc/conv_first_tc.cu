@@ -1,15 +1,20 @@
 // First conv (3x3 / stride 1 / pad 1, cin <= 3) on tcgen05 with an in-kernel im2col producer.
 //
 // The layer reads the caller's NCHW fp32 image directly: K = 9*cin = 27 (padded to 32) is too thin
-// for a TMA-fed pipeline, so 4 producer warps build the 128 x 32 fp16 A tile in shared memory
-// themselves (one output pixel per thread: 27 coalesced fp32 loads, zero fill at the border), in the
-// no-swizzle K-major canonical layout  addr(row, k8) = k8 * 2048 + row * 16  (8-row core matrices are
-// 128 contiguous bytes, LBO = 2048, SBO = 128), fence it to the async proxy and hand it to the MMA
-// warp through an mbarrier.  Two tcgen05.mma (K = 16 each) per tile accumulate into TMEM; 4 epilogue
-// warps add the folded-BN bias, apply the activation and write NHWC fp16 rows with 16-byte stores
-// (a warp's 32 rows are one contiguous span).  Replaces the Conv2d/BN/LeakyReLU of module 0
+// for a TMA-fed pipeline, so producer warps build the 128 x 32 fp16 A tile in shared memory themselves,
+// in the no-swizzle K-major canonical layout  addr(row, k8) = k8 * 2048 + row * 16  (8-row core
+// matrices are 128 contiguous bytes, LBO = 2048, SBO = 128), fence it to the async proxy and hand it to
+// the MMA warp through an mbarrier.  Two tcgen05.mma (K = 16 each) per tile accumulate into TMEM; 4
+// epilogue warps add the folded-BN bias, apply the activation and write NHWC fp16 rows with 16-byte
+// stores (a warp's 32 rows are one contiguous span).  Replaces the Conv2d/BN/LeakyReLU of module 0
 // (yolov3/models.py:22-41, :252) - 0.3 GFLOP/frame of SIMT work that used to cost as much as ten
 // tensor-core layers.
+//
+// Two producer flavours (the layer is HBM-bound: 12 B in, 2*COUT B out per pixel, so what matters is
+// bytes in flight and instructions per pixel):
+//   VEC  (image width % 4 == 0): one warp builds a whole tile, each lane 4 consecutive pixels from one
+//        128-bit load + two edge scalars per (channel, row) - 6.75 loads per pixel; 8 warps / 8 stages.
+//   !VEC (any width): one pixel per thread, 27 scalar loads; 4 groups of 4 warps / 4 stages.
 #include "common.cuh"
 #include "ptx.cuh"
 
@@ -18,10 +23,16 @@ namespace {
 
 constexpr int kTileM = 128;
 constexpr int kK = 32;                 // 27 real + 5 zero
-constexpr int kStages = 4;             // A tiles in flight = producer groups (one group owns one stage)
 constexpr int kABytes = kTileM * kK * 2;
-constexpr int kProdWarps = 4 * kStages;
-constexpr int kThreadsTC = 32 * (kProdWarps + 1 + 4);  // 16 producer warps, 1 MMA warp, 4 epilogue warps
+
+template <bool VEC>
+struct FCfg {
+  static constexpr int STAGES = VEC ? 8 : 4;
+  static constexpr int PROD_WARPS = VEC ? 8 : 16;
+  static constexpr int ARRIVALS = VEC ? 32 : 128;  // producer threads per tile
+  static constexpr int THREADS = 32 * (PROD_WARPS + 1 + 4);
+  static constexpr int SMEM = STAGES * kABytes + 1024;
+};
 
 __device__ __forceinline__ void mbar_wait_spin(uint64_t* bar, uint32_t parity) {
   while (!ptx::mbar_try_wait(bar, parity)) {
@@ -37,30 +48,50 @@ __device__ __forceinline__ uint64_t make_nosw_desc(uint32_t addr, uint32_t lbo_b
   return d;
 }
 
-template <int COUT>
-__global__ void __launch_bounds__(kThreadsTC, 1)
+// 27 taps of one pixel (k = c*9 + r*3 + s) -> one 64-byte K-major row, written as four 16-byte chunks
+__device__ __forceinline__ void store_row(uint8_t* tile, int row, const float (&v)[27]) {
+  uint8_t* dst = tile + row * 16;
+#pragma unroll
+  for (int k8 = 0; k8 < 4; ++k8) {
+    uint4 pk;
+    __half2* ph = reinterpret_cast<__half2*>(&pk);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int k = k8 * 8 + 2 * e;
+      ph[e] = __floats2half2_rn(k < 27 ? v[k] : 0.f, k + 1 < 27 ? v[k + 1] : 0.f);
+    }
+    *reinterpret_cast<uint4*>(dst + k8 * (kTileM * 16)) = pk;
+  }
+}
+
+template <int COUT, bool VEC>
+__global__ void __launch_bounds__(FCfg<VEC>::THREADS, 1)
 conv_first_tc_kernel(const float* __restrict__ x, const __half* __restrict__ wk, const float* __restrict__ bias,
                      __half* __restrict__ y, int n, int h, int w, int cin, int out_pitch, int act, int tiles) {
-  __shared__ __align__(1024) uint8_t s_a[kStages][kABytes];
+  using F = FCfg<VEC>;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* s_a = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   __shared__ __align__(128) uint8_t s_b[COUT * kK * 2];
   __shared__ float s_bias[COUT];
-  __shared__ __align__(8) uint64_t full_bar[kStages], empty_bar[kStages], tmem_full[2], tmem_empty[2];
+  __shared__ __align__(8) uint64_t full_bar[F::STAGES], empty_bar[F::STAGES], tmem_full[2], tmem_empty[2];
   __shared__ uint32_t tmem_ptr;
   constexpr int TMEM_COLS = (2 * COUT <= 32) ? 32 : (2 * COUT <= 64) ? 64 : 128;
+  constexpr int MMA_WARP = F::PROD_WARPS;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int total_px = n * h * w;  // < 2^31, checked by the launcher
 
+  ptx::pdl_launch_dependents();
   // weights: wk is [COUT][32] fp16 (k = c*9 + r*3 + s, zero padded) -> canonical layout, chunk-major
   for (int i = threadIdx.x; i < COUT * 4; i += blockDim.x) {
     const int o = i >> 2, k8 = i & 3;
     *reinterpret_cast<uint4*>(s_b + k8 * (COUT * 16) + o * 16) = *reinterpret_cast<const uint4*>(wk + o * kK + k8 * 8);
   }
   for (int i = threadIdx.x; i < COUT; i += blockDim.x) s_bias[i] = bias[i];
-  if (warp == kProdWarps) {
+  if (warp == MMA_WARP) {
     if (ptx::elect_one()) {
-      for (int s = 0; s < kStages; ++s) {
-        ptx::mbar_init(&full_bar[s], 128);  // every producer thread arrives
+      for (int s = 0; s < F::STAGES; ++s) {
+        ptx::mbar_init(&full_bar[s], F::ARRIVALS);
         ptx::mbar_init(&empty_bar[s], 1);
       }
       for (int a = 0; a < 2; ++a) {
@@ -78,58 +109,85 @@ conv_first_tc_kernel(const float* __restrict__ x, const __half* __restrict__ wk,
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = tmem_ptr;
+  ptx::pdl_wait();
 
-  if (warp < kProdWarps) {
+  if (warp < F::PROD_WARPS) {
     // ------------------------------------------------------------ im2col producers
-    // 4 groups of 128 threads; group g fills stage g with every 4th tile of this CTA, so four tiles'
-    // worth of global loads are in flight per SM (the layer is HBM-bound: 66 MB in, 354 MB out at batch 32).
-    const int row = threadIdx.x & 127;
-    const uint32_t stage = warp >> 2;
+    // producer unit u (a warp when VEC, a 4-warp group otherwise) owns stage u and every STAGES-th tile
+    const uint32_t stage = VEC ? warp : (warp >> 2);
     uint32_t phase = 0;
-    for (int tile = blockIdx.x + stage * gridDim.x; tile < tiles; tile += kStages * gridDim.x) {
-      const int pix = tile * kTileM + row;
-      float v[27];
+    for (int tile = blockIdx.x + stage * gridDim.x; tile < tiles; tile += F::STAGES * gridDim.x) {
+      uint8_t* a_tile = s_a + stage * kABytes;
+      if constexpr (VEC) {
+        const int pix = tile * kTileM + lane * 4;  // 4 pixels of one image row (w % 4 == 0)
+        float v[4][27];
 #pragma unroll
-      for (int i = 0; i < 27; ++i) v[i] = 0.f;
-      if (pix < total_px) {
-        const int px = pix % w;
-        const int t = pix / w;
-        const int py = t % h;
-        const int img = t / h;
+        for (int j = 0; j < 4; ++j)
 #pragma unroll
-        for (int c = 0; c < 3; ++c) {
-          if (c >= cin) break;
-          const float* plane = x + (1LL * img * cin + c) * h * w;
+          for (int i = 0; i < 27; ++i) v[j][i] = 0.f;
+        if (pix < total_px) {
+          const int px = pix % w;
+          const int t = pix / w;
+          const int py = t % h;
+          const int img = t / h;
 #pragma unroll
-          for (int r = 0; r < 3; ++r) {
-            const int yy = py + r - 1;
-            const bool yok = yy >= 0 && yy < h;
+          for (int c = 0; c < 3; ++c) {
+            if (c >= cin) break;
+            const float* plane = x + (1LL * img * cin + c) * h * w;
 #pragma unroll
-            for (int s = 0; s < 3; ++s) {
-              const int xx = px + s - 1;
-              if (yok && xx >= 0 && xx < w) v[c * 9 + r * 3 + s] = __ldg(plane + 1LL * yy * w + xx);
+            for (int r = 0; r < 3; ++r) {
+              const int yy = py + r - 1;
+              if (yy < 0 || yy >= h) continue;
+              const float* rowp = plane + 1LL * yy * w + px;
+              const float4 m = __ldg(reinterpret_cast<const float4*>(rowp));
+              const float left = px > 0 ? __ldg(rowp - 1) : 0.f;
+              const float right = px + 4 < w ? __ldg(rowp + 4) : 0.f;
+              const float win[6] = {left, m.x, m.y, m.z, m.w, right};
+#pragma unroll
+              for (int j = 0; j < 4; ++j)
+#pragma unroll
+                for (int s = 0; s < 3; ++s) v[j][c * 9 + r * 3 + s] = win[j + s];
             }
           }
         }
-      }
-      mbar_wait_spin(&empty_bar[stage], phase ^ 1);
-      uint8_t* dst = s_a[stage] + row * 16;
+        mbar_wait_spin(&empty_bar[stage], phase ^ 1);
 #pragma unroll
-      for (int k8 = 0; k8 < 4; ++k8) {
-        uint4 pk;
-        __half2* ph = reinterpret_cast<__half2*>(&pk);
+        for (int j = 0; j < 4; ++j) store_row(a_tile, lane * 4 + j, v[j]);
+      } else {
+        const int row = threadIdx.x & 127;
+        const int pix = tile * kTileM + row;
+        float v[27];
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const int k = k8 * 8 + 2 * e;
-          ph[e] = __floats2half2_rn(k < 27 ? v[k] : 0.f, k + 1 < 27 ? v[k + 1] : 0.f);
+        for (int i = 0; i < 27; ++i) v[i] = 0.f;
+        if (pix < total_px) {
+          const int px = pix % w;
+          const int t = pix / w;
+          const int py = t % h;
+          const int img = t / h;
+#pragma unroll
+          for (int c = 0; c < 3; ++c) {
+            if (c >= cin) break;
+            const float* plane = x + (1LL * img * cin + c) * h * w;
+#pragma unroll
+            for (int r = 0; r < 3; ++r) {
+              const int yy = py + r - 1;
+              const bool yok = yy >= 0 && yy < h;
+#pragma unroll
+              for (int s = 0; s < 3; ++s) {
+                const int xx = px + s - 1;
+                if (yok && xx >= 0 && xx < w) v[c * 9 + r * 3 + s] = __ldg(plane + 1LL * yy * w + xx);
+              }
+            }
+          }
         }
-        *reinterpret_cast<uint4*>(dst + k8 * (kTileM * 16)) = pk;
+        mbar_wait_spin(&empty_bar[stage], phase ^ 1);
+        store_row(a_tile, row, v);
       }
       ptx::fence_proxy_async_smem();
       ptx::mbar_arrive(&full_bar[stage]);
       phase ^= 1;
     }
-  } else if (warp == kProdWarps) {
+  } else if (warp == MMA_WARP) {
     // ------------------------------------------------------------ MMA issuer
     if (ptx::elect_one()) {
       constexpr uint32_t idesc = ptx::make_idesc_f16(kTileM, COUT);
@@ -141,7 +199,7 @@ conv_first_tc_kernel(const float* __restrict__ x, const __half* __restrict__ wk,
         mbar_wait_spin(&tmem_empty[acc], ((it >> 1) & 1) ^ 1);
         mbar_wait_spin(&full_bar[stage], phase);
         ptx::tc_fence_after();
-        const uint32_t a_addr = ptx::smem_u32(s_a[stage]);
+        const uint32_t a_addr = ptx::smem_u32(s_a + stage * kABytes);
 #pragma unroll
         for (int k = 0; k < 2; ++k) {
           const uint64_t adesc = make_nosw_desc(a_addr + k * 2 * (kTileM * 16), kTileM * 16, 128);
@@ -150,7 +208,7 @@ conv_first_tc_kernel(const float* __restrict__ x, const __half* __restrict__ wk,
         }
         ptx::umma_commit(&empty_bar[stage]);
         ptx::umma_commit(&tmem_full[acc]);
-        if (++stage == kStages) { stage = 0; phase ^= 1; }
+        if (++stage == F::STAGES) { stage = 0; phase ^= 1; }
       }
     }
   } else {
@@ -198,7 +256,7 @@ conv_first_tc_kernel(const float* __restrict__ x, const __half* __restrict__ wk,
   ptx::tc_fence_before();
   __syncthreads();
   ptx::tc_fence_after();
-  if (warp == kProdWarps) ptx::tmem_dealloc(tmem_base, TMEM_COLS);
+  if (warp == MMA_WARP) ptx::tmem_dealloc(tmem_base, TMEM_COLS);
 }
 
 __global__ void pack_first_tc_kernel(const float* __restrict__ w_folded, int cout, int per_out, __half* __restrict__ wk) {
@@ -206,6 +264,21 @@ __global__ void pack_first_tc_kernel(const float* __restrict__ w_folded, int cou
   if (i >= cout * kK) return;
   const int o = i / kK, k = i - o * kK;
   wk[i] = __float2half_rn(k < per_out ? w_folded[o * per_out + k] : 0.f);
+}
+
+template <int COUT, bool VEC>
+int launch_first(const float* x, const __half* wk, const float* bias, __half* y, int n, int h, int w, int cin,
+                 int out_pitch, int act, int tiles, int grid, cudaStream_t stream) {
+  using F = FCfg<VEC>;
+  auto kern = conv_first_tc_kernel<COUT, VEC>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    ME_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, F::SMEM));
+    attr_set = true;
+  }
+  kern<<<grid, F::THREADS, F::SMEM, stream>>>(x, wk, bias, y, n, h, w, cin, out_pitch, act, tiles);
+  ME_LAUNCH_CHECK();
+  return ME_OK;
 }
 
 }  // namespace
@@ -231,14 +304,17 @@ int me_conv_first_tc(const float* x_nchw, const float* w_folded, const float* bi
   if (grid <= 0) grid = 148;
   if (grid > tiles) grid = tiles;
   __half* y = static_cast<__half*>(y_nhwc);
+  const bool vec = (w % 4 == 0) && ((reinterpret_cast<uintptr_t>(x_nchw) & 15) == 0);
+#define ME_FIRST(C)                                                                                              \
+  return vec ? launch_first<C, true>(x_nchw, wk, bias, y, n, h, w, cin, out_pitch, act, tiles, grid, stream)     \
+             : launch_first<C, false>(x_nchw, wk, bias, y, n, h, w, cin, out_pitch, act, tiles, grid, stream)
   switch (cout) {
-    case 16: conv_first_tc_kernel<16><<<grid, kThreadsTC, 0, stream>>>(x_nchw, wk, bias, y, n, h, w, cin, out_pitch, act, tiles); break;
-    case 32: conv_first_tc_kernel<32><<<grid, kThreadsTC, 0, stream>>>(x_nchw, wk, bias, y, n, h, w, cin, out_pitch, act, tiles); break;
-    case 64: conv_first_tc_kernel<64><<<grid, kThreadsTC, 0, stream>>>(x_nchw, wk, bias, y, n, h, w, cin, out_pitch, act, tiles); break;
+    case 16: ME_FIRST(16);
+    case 32: ME_FIRST(32);
+    case 64: ME_FIRST(64);
     default: return fail(ME_ERR_UNSUPPORTED, "conv_first_tc: cout %d unsupported (16, 32 or 64)", cout);
   }
-  ME_LAUNCH_CHECK();
-  return ME_OK;
+#undef ME_FIRST
 }
 
 }  // extern "C"

@@ -112,6 +112,9 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   const int lane = threadIdx.x & 31;
   const int total_tiles = p.tiles_m * p.tiles_n;
 
+  // PDL: let the next layer's CTAs get scheduled as ours retire; everything up to pdl_wait() below touches
+  // only our own smem / TMEM / kernel parameters, so it overlaps the previous layer's tail.
+  ptx::pdl_launch_dependents();
   if (warp == 0 && ptx::elect_one()) {
     ptx::prefetch_tmap(&tmA);
     ptx::prefetch_tmap(&tmB);
@@ -139,6 +142,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
+  ptx::pdl_wait();  // inputs written by the previous kernel are complete and visible from here on
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
@@ -296,6 +300,17 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   if (warp == 1) ptx::tmem_dealloc(tmem_base, C::TMEM_COLS);
 }
 
+// ME_PDL=0 disables programmatic dependent launch (A/B measurements).
+bool pdl_enabled_impl() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("ME_PDL");
+    v = (e && e[0] == '0') ? 0 : 1;
+  }
+  return v != 0;
+}
+inline bool pdl_enabled() { return pdl_enabled_impl(); }
+
 unsigned long long* g_debug_host = nullptr;
 unsigned long long* g_debug_dev = nullptr;
 
@@ -379,7 +394,17 @@ int launch(const me_conv_desc* d, const void* x, const void* w, const float* bia
   int grid = sm_count();
   if (grid <= 0) grid = 148;
   if (grid > total) grid = total;
-  kern<<<grid, kThreads, smem, stream>>>(tmA, tmB, tmC, tmR, p);
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  ME_CUDA(cudaLaunchKernelEx(&cfg, kern, tmA, tmB, tmC, tmR, p));
   ME_LAUNCH_CHECK();
   return ME_OK;
 }
@@ -387,6 +412,7 @@ int launch(const me_conv_desc* d, const void* x, const void* w, const float* bia
 }  // namespace
 
 unsigned long long* conv_debug_word() { return g_debug_dev; }
+bool conv_pdl_enabled() { return pdl_enabled_impl(); }
 int conv_ensure_debug_word() { return ensure_debug_word(); }
 
 // 0 = automatic, 1 = single-CTA tiles only, 2 = CTA pairs with N=128, 3 = CTA pairs with N=256 (where legal)
@@ -443,7 +469,9 @@ int me_conv_gemm(const me_conv_desc* d, const void* x, const void* w_packed, con
     int pair_bn = 0;
     if (mode == 2) pair_bn = 128;
     else if (mode == 3) pair_bn = cout >= 256 ? 256 : 128;
-    else if (mode == 0 && m >= 256) pair_bn = cout >= 256 ? 256 : 128;
+    // measured on B200 (profiles/round1): pairs win on 3x3 layers with >= 256 output channels and enough rows
+    // to fill 74 pairs more than twice; 1x1 layers and 128-channel layers are faster on single-CTA tiles.
+    else if (mode == 0 && d->ksize == 3 && cout >= 256 && m >= 16384) pair_bn = 256;
     if (pair_bn) return conv_gemm_pair(pair_bn, d, x, w_packed, bias, residual, y, stream);
   }
   if (bk == 64) {

@@ -22,6 +22,7 @@ namespace me {
 // defined in conv_gemm.cu
 unsigned long long* conv_debug_word();
 int conv_ensure_debug_word();
+bool conv_pdl_enabled();
 
 namespace {
 
@@ -111,6 +112,7 @@ conv_gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
   const int npairs = static_cast<int>(ptx::num_clusters_x());
   const int total_tiles = p.tiles_m * p.tiles_n;
 
+  ptx::pdl_launch_dependents();  // see conv_gemm.cu
   if (warp == 0 && ptx::elect_one()) {
     ptx::prefetch_tmap(&tmA);
     ptx::prefetch_tmap(&tmB);
@@ -141,6 +143,7 @@ conv_gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
+  ptx::pdl_wait();
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer (both CTAs)
@@ -361,7 +364,17 @@ int launch_pair(const me_conv_desc* d, const void* x, const void* w, const float
   if (sms <= 0) sms = 148;
   int pairs = sms / 2;
   if (pairs > total) pairs = total;
-  kern<<<2 * pairs, kThreads, smem, stream>>>(tmA, tmB, tmC, tmR, p);
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(2 * pairs);
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = conv_pdl_enabled() ? 1 : 0;
+  ME_CUDA(cudaLaunchKernelEx(&cfg, kern, tmA, tmB, tmC, tmR, p));
   ME_LAUNCH_CHECK();
   return ME_OK;
 }

@@ -25,6 +25,10 @@ class View:
         """Tensor whose data_ptr is the first element of the view."""
         return self.buf.view(-1)[self.off:]
 
+    def at(self, b0):
+        """Same, starting at frame b0 of the batch (sub-batch execution)."""
+        return self.buf[b0:].view(-1)[self.off:]
+
 
 def describe_blocks(module_defs):
     """Static per-block description (same rules as create_modules, reference yolov3/models.py:12-79)."""
@@ -67,10 +71,19 @@ def describe_blocks(module_defs):
 class DarknetPlan:
     """Buffers, packed weights and the op list for one (n, size) shape on one device."""
 
-    def __init__(self, blocks, tensors, n, size, device, feature_tap, in_channels=3):
+    def __init__(self, blocks, tensors, n, size, device, feature_tap, in_channels=3, splits=None):
         self.blocks, self.n, self.size, self.device = blocks, n, size, device
         self.feature_tap = feature_tap
-        self.ops = []          # list of zero-arg callables enqueueing one kernel each
+        self.ops = []          # callables fn(b0, nb) enqueueing one kernel each over frames [b0, b0+nb)
+        # Frames are independent, so the batch is run as `splits` sub-batches on parallel streams inside one
+        # CUDA graph: while one sub-batch's persistent kernel drains its last (partial) wave of tiles, the
+        # other sub-batch's kernel takes over the idle SMs.
+        # (measured on B200, profiles/round1/splits_sweep.log: 1 -> 10.4k, 2 -> 10.3-10.5k, 4 -> 9.3k frames/s at
+        # batch 32: the persistent kernels already keep the SMs busy, so the default stays at one stream.)
+        if splits is None:
+            splits = 1
+        self.splits = splits if n % splits == 0 else 1
+        self._streams = None
         self.graph = None
         self.launches = 0
         self._tensors = tensors
@@ -175,8 +188,8 @@ class DarknetPlan:
                 if b["size"] != 2:
                     raise MeError("only 2x2 max-pool is supported")
                 ov = View(self._new(s_out, s_out, ops.round_up(src.c, 8)), 0, src.c, s_out, s_out, real_c=src.real_c)
-                self._add(lambda sv=src, o=ov, st=b["stride"]: ops.maxpool2(sv.t, o.t, n, sv.h, sv.w, ops.round_up(sv.c, 8),
-                                                                            sv.pitch, o.pitch, st))
+                self._add(lambda b0, nb, sv=src, o=ov, st=b["stride"]: ops.maxpool2(
+                    sv.at(b0), o.at(b0), nb, sv.h, sv.w, ops.round_up(sv.c, 8), sv.pitch, o.pitch, st))
                 views[i] = ov
             elif t == "upsample":
                 if b["stride"] != 2:
@@ -186,7 +199,8 @@ class DarknetPlan:
                     ov = View(buf, off, src.c, s_out, s_out)
                 else:
                     ov = View(self._new(s_out, s_out, ops.round_up(src.c, 8)), 0, src.c, s_out, s_out)
-                self._add(lambda sv=src, o=ov: ops.upsample2(sv.t, o.t, n, sv.h, sv.w, sv.c, sv.pitch, o.pitch))
+                self._add(lambda b0, nb, sv=src, o=ov: ops.upsample2(sv.at(b0), o.at(b0), nb, sv.h, sv.w, sv.c, sv.pitch,
+                                                                     o.pitch))
                 views[i] = ov
             elif t == "route":
                 if len(b["layers"]) == 1:
@@ -197,8 +211,8 @@ class DarknetPlan:
             elif t == "yolo":
                 g = s_out
                 stride = self.size / g
-                self._add(lambda sv=src, bb=b, g=g, st=stride, ro=row_off: ops.yolo_decode(
-                    sv.t, sv.pitch, self.yolo_out, n, g, bb["anchors"], bb["classes"], st, self.rows_total, ro))
+                self._add(lambda b0, nb, sv=src, bb=b, g=g, st=stride, ro=row_off: ops.yolo_decode(
+                    sv.at(b0), sv.pitch, self.yolo_out[b0:], nb, g, bb["anchors"], bb["classes"], st, self.rows_total, ro))
                 row_off += len(b["anchors"]) * g * g
                 views[i] = src
             if i == self.feature_tap:
@@ -227,32 +241,54 @@ class DarknetPlan:
                 raise MeError("first layer must be a 3x3/stride-1 conv over <= 4 input channels")
             first = ops.pack_first_conv(w, bias, bn)
             self._keep = getattr(self, "_keep", []) + [first]
-            self._add(lambda f=first, o=ov, a=act: ops.conv_first(self.x_in, f, o.t, o.pitch, a))
+            self._add(lambda b0, nb, f=first, o=ov, a=act: ops.conv_first(self.x_in[b0:b0 + nb], f, o.at(b0), o.pitch, a))
             return
         packed = ops.pack_conv(w, bias, bn, cout_pad=ops.round_up(b["filters"], 32))
         res_v = views[fuse_res] if fuse_res is not None else None
         self._keep = getattr(self, "_keep", []) + [packed]
-        self._add(lambda sv=src, p=packed, o=ov, st=b["stride"], a=act, rv=res_v, f32=is_head: ops.conv_gemm(
-            sv.t, p, n, sv.h, sv.w, sv.pitch, o.t, o.pitch, stride=st, act=a,
-            residual=None if rv is None else rv.t, res_pitch=0 if rv is None else rv.pitch,
+        self._add(lambda b0, nb, sv=src, p=packed, o=ov, st=b["stride"], a=act, rv=res_v, f32=is_head: ops.conv_gemm(
+            sv.at(b0), p, nb, sv.h, sv.w, sv.pitch, o.at(b0), o.pitch, stride=st, act=a,
+            residual=None if rv is None else rv.at(b0), res_pitch=0 if rv is None else rv.pitch,
             cin=sv.real_c if sv.real_c != sv.c else sv.c, cout=p.cout_pad, out_f32=f32))
 
     # ------------------------------------------------------------------ execution
-    def enqueue(self):
-        for fn in self.ops:
-            fn()
-        self.launches = len(self.ops)
+    def enqueue(self, b0=0, nb=None, only=None):
+        nb = self.n if nb is None else nb
+        for i, fn in enumerate(self.ops):
+            if only is None or i in only:
+                fn(b0, nb)
+
+    def enqueue_split(self, only=None):
+        """All sub-batches, each on its own stream, joined back into the current stream.
+        `only`: optional set of op indices (profiling a subset of the launch list)."""
+        if self.splits == 1:
+            self.enqueue(only=only)
+            self.launches = len(self.ops)
+            return
+        if self._streams is None:
+            self._streams = [torch.cuda.Stream(device=self.device) for _ in range(self.splits - 1)]
+        cur = torch.cuda.current_stream()
+        nb = self.n // self.splits
+        for s in self._streams:
+            s.wait_stream(cur)
+        self.enqueue(0, nb, only)
+        for k, s in enumerate(self._streams):
+            with torch.cuda.stream(s):
+                self.enqueue((k + 1) * nb, nb, only)
+        for s in self._streams:
+            cur.wait_stream(s)
+        self.launches = len(self.ops) * self.splits
 
     def run(self, use_graph=True):
         """Inputs must already be in self.x_in. Enqueues (or replays) the whole forward."""
         if not use_graph:
-            self.enqueue()
+            self.enqueue_split()
             return
         if self.graph is None:
-            self.enqueue()  # warm-up: lazy one-time initialisation inside the library
+            self.enqueue_split()  # warm-up: lazy one-time initialisation inside the library
             torch.cuda.synchronize(self.device)
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g):
-                self.enqueue()
+                self.enqueue_split()
             self.graph = g
         self.graph.replay()

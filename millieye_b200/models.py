@@ -7,6 +7,8 @@ The nn.Conv2d / nn.BatchNorm2d objects below only own parameters (checkpoint com
 `load_state_dict`, `load_darknet_weights`); their forward is never used.  There is no CPU or
 eager-PyTorch fallback: a forward on a non-CUDA tensor, or without the built library, raises.
 """
+import os
+
 import numpy as np
 import torch
 import torch.nn as nn
@@ -98,7 +100,10 @@ class Darknet(nn.Module):
         self._invalidate()
 
     def plan_for(self, n, size, device):
-        key = (n, size, device.index, self.feature_tap)
+        splits = getattr(self, "sub_batches", None)
+        if splits is None and os.environ.get("ME_SPLITS"):
+            splits = int(os.environ["ME_SPLITS"])
+        key = (n, size, device.index, self.feature_tap, splits)
         plan = self._plans.get(key)
         if plan is None:
             if device.type != "cuda":
@@ -107,7 +112,7 @@ class Darknet(nn.Module):
                        if v.is_floating_point()}
             with torch.cuda.device(device):
                 plan = DarknetPlan(self._blocks, tensors, n, size, device, self.feature_tap,
-                                   in_channels=int(self.hyperparams["channels"]))
+                                   in_channels=int(self.hyperparams["channels"]), splits=splits)
             self._plans[key] = plan
         return plan
 

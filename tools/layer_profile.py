@@ -27,6 +27,7 @@ def main():
     net.load_state_dict(synth.fill_state_dict(net.state_dict(), seed=0, conv_gain=0.6 if cfg == "yolov3" else 1.0))
     net.to(dev)
     plan = net.plan_for(n, size, dev)
+    plan.splits = 1
     plan.x_in.copy_(torch.rand(n, 3, size, size, device=dev))
     plan.enqueue()
     torch.cuda.synchronize()
@@ -39,12 +40,12 @@ def main():
     rows = []
     for (i, b), fn in zip(kinds, plan.ops):
         for _ in range(2):
-            fn()
+            fn(0, n)
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         reps = 10
         e0.record()
         for _ in range(reps):
-            fn()
+            fn(0, n)
         e1.record()
         torch.cuda.synchronize()
         ms = e0.elapsed_time(e1) / reps
