@@ -43,8 +43,40 @@ struct ConvParams {
   int has_res;
   int im2col;
   int stages;
+  int bres_bytes;  // weight-stationary mode: bytes of the resident weight slab (num_kb * B_BYTES)
   const float* bias;
   unsigned long long* debug;  // host-mapped word, written before a watchdog trap
+};
+
+// Tile order of one persistent CTA.  Default: tile = blockIdx.x + i * gridDim.x over the (m, n) tile grid,
+// n fastest, so the CTAs that share an A tile run together.  Weight-stationary: the CTA keeps ONE n tile
+// (its weight slab stays in shared memory) and strides over the m tiles.
+template <bool WS>
+struct TileWalk {
+  int tm, tn, step, tiles_m, tiles_n, tile;
+  __device__ TileWalk(int tiles_m_, int tiles_n_) : tiles_m(tiles_m_), tiles_n(tiles_n_) {
+    if (WS) {
+      tn = blockIdx.x % tiles_n;
+      tm = blockIdx.x / tiles_n;
+      step = gridDim.x / tiles_n;
+      tile = 0;
+    } else {
+      tile = blockIdx.x;
+      step = gridDim.x;
+      tm = tile / tiles_n;
+      tn = tile - tm * tiles_n;
+    }
+  }
+  __device__ bool valid() const { return WS ? tm < tiles_m : tile < tiles_m * tiles_n; }
+  __device__ void next() {
+    if (WS) {
+      tm += step;
+    } else {
+      tile += step;
+      tm = tile / tiles_n;
+      tn = tile - tm * tiles_n;
+    }
+  }
 };
 
 template <int BN, int BK, bool OUT_F32>
@@ -89,16 +121,21 @@ __device__ __forceinline__ float apply_act(float v, int act) {
   return v;
 }
 
-template <int BN, int BK, bool OUT_F32>
+// WS (weight stationary): the layer's whole weight slab for this CTA's n tile (num_kb x BN x BK) is loaded
+// into shared memory once and the pipeline stages carry A only.  For the thin-channel layers (32..128
+// channels, 208^2..52^2 pixels) re-fetching the weights with every tile doubled the L2 -> SM traffic.
+template <int BN, int BK, bool OUT_F32, bool WS>
 __global__ void __launch_bounds__(kThreads, 1)
 conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmR,
                  const ConvParams p) {
   using C = Cfg<BN, BK, OUT_F32>;
+  constexpr int STAGE = WS ? C::A_BYTES : C::STAGE_BYTES;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* stage_base = smem;
-  uint8_t* staging = smem + p.stages * C::STAGE_BYTES;
+  uint8_t* bres = smem;  // WS only
+  uint8_t* stage_base = smem + (WS ? p.bres_bytes : 0);
+  uint8_t* staging = stage_base + p.stages * STAGE;
   float* s_bias = reinterpret_cast<float*>(staging + C::STAGING_BYTES);
   uint64_t* bars = reinterpret_cast<uint64_t*>(s_bias + BN);
   uint64_t* full_bar = bars;                     // [kMaxStages]
@@ -106,11 +143,11 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   uint64_t* tmem_full = bars + 2 * kMaxStages;   // [2]
   uint64_t* tmem_empty = tmem_full + 2;          // [2]
   uint64_t* res_full = tmem_empty + 2;           // [1]
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(res_full + 1);
+  uint64_t* b_full = res_full + 1;               // [1] WS: resident weights landed
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(b_full + 1);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int total_tiles = p.tiles_m * p.tiles_n;
 
   // PDL: let the next layer's CTAs get scheduled as ours retire; everything up to pdl_wait() below touches
   // only our own smem / TMEM / kernel parameters, so it overlaps the previous layer's tail.
@@ -132,6 +169,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         ptx::mbar_init(&tmem_empty[a], 4);  // one arrive per epilogue warp
       }
       ptx::mbar_init(res_full, 1);
+      ptx::mbar_init(b_full, 1);
       ptx::fence_mbar_init();
     }
     __syncwarp();
@@ -148,9 +186,13 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     // ------------------------------------------------------------------ TMA producer
     if (ptx::elect_one()) {
       uint32_t stage = 0, phase = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
-        const int tm = tile / p.tiles_n, tn = tile - tm * p.tiles_n;
-        const int m0 = tm * kBM, n0 = tn * BN;
+      TileWalk<WS> tw(p.tiles_m, p.tiles_n);
+      if (WS && tw.valid()) {
+        ptx::mbar_arrive_expect_tx(b_full, p.bres_bytes);
+        for (int kb = 0; kb < p.num_kb; ++kb) ptx::tma_load_2d(&tmB, b_full, bres + kb * C::B_BYTES, kb * BK, tw.tn * BN);
+      }
+      for (; tw.valid(); tw.next()) {
+        const int m0 = tw.tm * kBM, n0 = tw.tn * BN;
         int cw = 0, ch = 0, cn = 0;
         if (p.im2col) {
           const int q0 = m0 % p.Wo;
@@ -162,16 +204,15 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         int tap = 0, cb = 0;
         for (int kb = 0; kb < p.num_kb; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1, p.debug, 0x100u + stage);
-          uint8_t* sa = stage_base + stage * C::STAGE_BYTES;
-          uint8_t* sb = sa + C::A_BYTES;
-          ptx::mbar_arrive_expect_tx(&full_bar[stage], C::STAGE_BYTES);
+          uint8_t* sa = stage_base + stage * STAGE;
+          ptx::mbar_arrive_expect_tx(&full_bar[stage], STAGE);
           if (p.im2col) {
             const int r = tap / 3, s = tap - r * 3;
             ptx::tma_load_im2col_4d(&tmA, &full_bar[stage], sa, cb * BK, cw, ch, cn, (uint16_t)s, (uint16_t)r);
           } else {
             ptx::tma_load_2d(&tmA, &full_bar[stage], sa, cb * BK, m0);
           }
-          ptx::tma_load_2d(&tmB, &full_bar[stage], sb, kb * BK, n0);
+          if (!WS) ptx::tma_load_2d(&tmB, &full_bar[stage], sa + C::A_BYTES, kb * BK, n0);
           if (++cb == p.kb_per_tap) { cb = 0; ++tap; }
           if (++stage == (uint32_t)p.stages) { stage = 0; phase ^= 1; }
         }
@@ -183,7 +224,9 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       constexpr uint32_t idesc = ptx::make_idesc_f16(kBM, BN);
       uint32_t stage = 0, phase = 0;
       int it = 0;
-      for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
+      TileWalk<WS> tw(p.tiles_m, p.tiles_n);
+      if (WS && tw.valid()) mbar_wait(b_full, 0, p.debug, 0x600u);
+      for (; tw.valid(); tw.next(), ++it) {
         const int acc = it & 1;
         const uint32_t acc_phase = (it >> 1) & 1;
         mbar_wait(&tmem_empty[acc], acc_phase ^ 1, p.debug, 0x200u + acc);
@@ -192,8 +235,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         for (int kb = 0; kb < p.num_kb; ++kb) {
           mbar_wait(&full_bar[stage], phase, p.debug, 0x300u + stage);
           ptx::tc_fence_after();
-          const uint32_t a_addr = ptx::smem_u32(stage_base + stage * C::STAGE_BYTES);
-          const uint32_t b_addr = a_addr + C::A_BYTES;
+          const uint32_t a_addr = ptx::smem_u32(stage_base + stage * STAGE);
+          const uint32_t b_addr = WS ? ptx::smem_u32(bres + kb * C::B_BYTES) : a_addr + C::A_BYTES;
 #pragma unroll
           for (int k = 0; k < BK / 16; ++k) {
             const uint64_t adesc = ptx::make_kmajor_desc(a_addr + k * 32, BK * 2);
@@ -213,9 +256,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const int etid = threadIdx.x - 64;  // 0..127
     const bool leader = (threadIdx.x == 64);
     int it = 0;
-    for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x, ++it) {
-      const int tm = tile / p.tiles_n, tn = tile - tm * p.tiles_n;
-      const int m0 = tm * kBM, n0 = tn * BN;
+    for (TileWalk<WS> tw(p.tiles_m, p.tiles_n); tw.valid(); tw.next(), ++it) {
+      const int m0 = tw.tm * kBM, n0 = tw.tn * BN;
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
       if (leader) {
@@ -322,7 +364,7 @@ int ensure_debug_word() {
   return ME_OK;
 }
 
-template <int BN, int BK, bool OUT_F32>
+template <int BN, int BK, bool OUT_F32, bool WS>
 int launch(const me_conv_desc* d, const void* x, const void* w, const float* bias, const void* residual, void* y,
            cudaStream_t stream) {
   using C = Cfg<BN, BK, OUT_F32>;
@@ -354,11 +396,13 @@ int launch(const me_conv_desc* d, const void* x, const void* w, const float* bia
   if (rc != ME_OK) return rc;
   p.debug = g_debug_dev;
 
-  int stages = (227 * 1024 - 1024 - C::STAGING_BYTES - C::TAIL_BYTES) / C::STAGE_BYTES;
+  constexpr int STAGE = WS ? C::A_BYTES : C::STAGE_BYTES;
+  p.bres_bytes = WS ? p.num_kb * C::B_BYTES : 0;
+  int stages = (227 * 1024 - 1024 - C::STAGING_BYTES - C::TAIL_BYTES - p.bres_bytes) / STAGE;
   if (stages > kMaxStages) stages = kMaxStages;
   ME_REQUIRE(stages >= 2, "conv: not enough shared memory for a 2-stage pipeline");
   p.stages = stages;
-  const int smem = C::smem_bytes(stages);
+  const int smem = 1024 + p.bres_bytes + stages * STAGE + C::STAGING_BYTES + C::TAIL_BYTES;
 
   CUtensorMap tmA, tmB, tmC, tmR;
   const CUtensorMapSwizzle swz_k = swizzle_for_row_bytes(BK * 2);
@@ -384,7 +428,7 @@ int launch(const me_conv_desc* d, const void* x, const void* w, const float* bia
     tmR = tmC;
   }
 
-  auto kern = conv_gemm_kernel<BN, BK, OUT_F32>;
+  auto kern = conv_gemm_kernel<BN, BK, OUT_F32, WS>;
   static bool attr_set = false;
   if (!attr_set) {
     ME_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
@@ -393,7 +437,14 @@ int launch(const me_conv_desc* d, const void* x, const void* w, const float* bia
   const int total = p.tiles_m * p.tiles_n;
   int grid = sm_count();
   if (grid <= 0) grid = 148;
-  if (grid > total) grid = total;
+  if (WS) {
+    int per_n = grid / p.tiles_n;  // CTAs that share one n tile
+    if (per_n > p.tiles_m) per_n = p.tiles_m;
+    ME_REQUIRE(per_n >= 1, "conv(ws): more n tiles than SMs");
+    grid = per_n * p.tiles_n;
+  } else if (grid > total) {
+    grid = total;
+  }
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(grid);
   cfg.blockDim = dim3(kThreads);
@@ -413,6 +464,16 @@ int launch(const me_conv_desc* d, const void* x, const void* w, const float* bia
 
 unsigned long long* conv_debug_word() { return g_debug_dev; }
 bool conv_pdl_enabled() { return pdl_enabled_impl(); }
+// ME_CONV_WS: 0 = never, 1 (default) = when profitable, 2 = whenever the slab fits (tests force it on small shapes)
+static int conv_ws_mode() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("ME_CONV_WS");
+    v = e ? (e[0] == '0' ? 0 : (e[0] == '2' ? 2 : 1)) : 1;
+  }
+  return v;
+}
+static bool conv_ws_enabled() { return conv_ws_mode() != 0; }
 int conv_ensure_debug_word() { return ensure_debug_word(); }
 
 // 0 = automatic, 1 = single-CTA tiles only, 2 = CTA pairs with N=128, 3 = CTA pairs with N=256 (where legal)
@@ -459,12 +520,28 @@ int me_conv_gemm(const me_conv_desc* d, const void* x, const void* w_packed, con
   const int bk = me_conv_k_block(d->cin);
   const bool f32 = d->out_f32 != 0;
   const int cout = d->cout;
-#define ME_GO(BN, BK, F32) return launch<BN, BK, F32>(d, x, w_packed, bias, residual, y, stream)
+  const int pad_ = (d->ksize - 1) / 2;
+  const long long m = 1LL * d->n * ((d->h + 2 * pad_ - d->ksize) / d->stride + 1) * ((d->w + 2 * pad_ - d->ksize) / d->stride + 1);
+  const int num_kb = d->ksize * d->ksize * (round_up(d->cin, bk) / bk);
+  // Weight-stationary tiles: the n tile's whole weight slab stays in shared memory.  Used when it fits next to
+  // >= 3 A stages and every CTA gets >= 4 m tiles to amortise the one-off load (ME_CONV_WS=0 disables).
+  auto ws_ok = [&](int bn) {
+    if (f32 || !conv_ws_enabled()) return false;
+    const int tiles_n = ceil_div(cout, bn), tiles_m = static_cast<int>((m + kBM - 1) / kBM);
+    const long long need = 1024LL + 1LL * num_kb * bn * bk * 2 + 3LL * kBM * bk * 2 + 1LL * kBM * bn * 2 + bn * 4 + 64 * 8 + 16;
+    const int sms = sm_count() > 0 ? sm_count() : 148;
+    if (need > 227 * 1024 || tiles_n > sms) return false;
+    if (conv_ws_mode() == 2) return true;
+    return tiles_n <= 4 && tiles_m >= 4 * (sms / tiles_n);
+  };
+#define ME_GO(BN, BK, F32)                                                                        \
+  do {                                                                                            \
+    if (!F32 && ws_ok(BN)) return launch<BN, BK, false, true>(d, x, w_packed, bias, residual, y, stream); \
+    return launch<BN, BK, F32, false>(d, x, w_packed, bias, residual, y, stream);                 \
+  } while (0)
   if (bk == 64 && !f32 && cout >= 128) {
     // CTA pairs (256 x BN tiles) halve the shared-memory bytes per flop; worth it once the layer has
     // enough pair tiles to fill the 74 SM pairs.
-    const int pad = (d->ksize - 1) / 2;
-    const long long m = 1LL * d->n * ((d->h + 2 * pad - d->ksize) / d->stride + 1) * ((d->w + 2 * pad - d->ksize) / d->stride + 1);
     const int mode = conv_mode();
     int pair_bn = 0;
     if (mode == 2) pair_bn = 128;

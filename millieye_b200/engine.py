@@ -87,7 +87,13 @@ class DarknetPlan:
         self.graph = None
         self.launches = 0
         self._tensors = tensors
-        self.x_in = torch.zeros((n, in_channels, size, size), dtype=torch.float32, device=device)
+        # Two input buffers (and one captured graph per buffer): the host->device copy of batch i+1 runs on a
+        # copy stream while the graph of batch i is still executing.
+        self._x_bufs = [torch.zeros((n, in_channels, size, size), dtype=torch.float32, device=device) for _ in range(2)]
+        self._slot = 0
+        self._graphs = [None, None]
+        self._slot_free = [None, None]   # event: last forward that read the buffer has finished
+        self._copy_stream = None
         self._build()
 
     # ------------------------------------------------------------------ plan construction
@@ -279,16 +285,44 @@ class DarknetPlan:
             cur.wait_stream(s)
         self.launches = len(self.ops) * self.splits
 
+    @property
+    def x_in(self):
+        """Input buffer of the current slot (what the first conv reads)."""
+        return self._x_bufs[self._slot]
+
+    def load_input(self, x):
+        """Stages the next batch: switches to the other input buffer and copies x into it.  A pinned host
+        tensor is copied on a separate stream, so the PCIe transfer overlaps the previous forward."""
+        self._slot ^= 1
+        buf = self._x_bufs[self._slot]
+        cur = torch.cuda.current_stream()
+        if x.is_cuda:
+            buf.copy_(x, non_blocking=True)
+            return
+        if self._copy_stream is None:
+            self._copy_stream = torch.cuda.Stream(device=self.device)
+        cs = self._copy_stream
+        if self._slot_free[self._slot] is not None:
+            cs.wait_event(self._slot_free[self._slot])
+        with torch.cuda.stream(cs):
+            buf.copy_(x, non_blocking=True)
+        cur.wait_stream(cs)
+
     def run(self, use_graph=True):
-        """Inputs must already be in self.x_in. Enqueues (or replays) the whole forward."""
+        """Inputs must already be staged with load_input(). Enqueues (or replays) the whole forward."""
         if not use_graph:
             self.enqueue_split()
-            return
-        if self.graph is None:
-            self.enqueue_split()  # warm-up: lazy one-time initialisation inside the library
-            torch.cuda.synchronize(self.device)
-            g = torch.cuda.CUDAGraph()
-            with torch.cuda.graph(g):
-                self.enqueue_split()
-            self.graph = g
-        self.graph.replay()
+        else:
+            if self._graphs[self._slot] is None:
+                self.enqueue_split()  # warm-up: lazy one-time initialisation inside the library
+                torch.cuda.synchronize(self.device)
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    self.enqueue_split()
+                self._graphs[self._slot] = g
+            self.graph = self._graphs[self._slot]
+            self.graph.replay()
+        ev = self._slot_free[self._slot]
+        if ev is None:
+            ev = self._slot_free[self._slot] = torch.cuda.Event()
+        ev.record()

@@ -123,7 +123,7 @@ class Darknet(nn.Module):
         dev = x.device if x.is_cuda else next(self.parameters()).device
         plan = self.plan_for(x.shape[0], x.shape[2], dev)
         with torch.cuda.device(dev):
-            plan.x_in.copy_(x, non_blocking=True)   # device->device, or pinned host->device
+            plan.load_input(x)   # device->device, or pinned host->device on the copy stream
             plan.run(self.use_cuda_graph)
         return plan
 

@@ -28,7 +28,7 @@ def main():
     net.to(dev)
     plan = net.plan_for(n, size, dev)
     plan.splits = 1
-    plan.x_in.copy_(torch.rand(n, 3, size, size, device=dev))
+    plan.load_input(torch.rand(n, 3, size, size, device=dev))
     plan.enqueue()
     torch.cuda.synchronize()
     kinds = []
