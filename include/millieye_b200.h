@@ -164,7 +164,8 @@ typedef struct me_head_weights {
 
 /* Builds the RoI list of Network.forward (my_models.py:459-492): per-image NMS survivors
  * with class_pred == class_idx (image proposals, image-major order) followed by the radar
- * boxes scaled by img_size.  img_boxes: fp32 [cap][9] = [i,x1,y1,x2,y2,conf,class_conf,
+ * boxes scaled by img_size (class_idx < 0: keep every class, rows of 1 + det_cols floats, see
+ * me_stage2_heads).  img_boxes: fp32 [cap][9] = [i,x1,y1,x2,y2,conf,class_conf,
  * class_pred,cls[class_idx]] for the image proposals; rois [cap][5]; counts[0] = image
  * proposals, counts[1] = image + radar proposals. */
 int me_build_proposals(const float* det, const int* det_count, int n, int max_det, int det_cols, int class_idx,
@@ -180,13 +181,27 @@ int me_fusion_heads(const void* hidden, int hidden_pitch, const void* radar_crop
                     const me_head_weights* hw, const float* img_boxes, const int* counts, int cap, float* regress,
                     float* refine, float* mask, me_stream_t stream);
 
+/* Stage-2 model (module2_mixed/my_models.py:96-163, 299-361): every class is kept (me_build_proposals with
+ * class_idx = -1 writes rows [i, x1,y1,x2,y2, conf, class_conf, class_pred, cls...] of 1 + det_cols floats),
+ * no radar branch; from hidden = leaky(net0(psroi)) computes regress[cap][4] and mask[cap] = column 1 of
+ * softmax(LeakyReLU(fc2(flatten(leaky(fc1(stack(sigmoid(net2(hidden)), yolo_vector))))))). */
+typedef struct me_stage2_weights {
+  const float* net1_w; const float* net1_b;   /* 4 x 256                         */
+  const float* net2_w; const float* net2_b;   /* num_vec x 256                   */
+  const float* fc1_w;  const float* fc1_b;    /* 32 x 2                          */
+  const float* fc2_w;  const float* fc2_b;    /* 2 x (32 * num_vec)              */
+} me_stage2_weights;
+int me_stage2_heads(const void* hidden, int hidden_pitch, const me_stage2_weights* hw, const float* boxes,
+                    int box_pitch, int num_vec, const int* counts, int cap, float* regress, float* mask,
+                    me_stream_t stream);
+
 /* Threshold, box regression, priority sort (my_models.py:516-539, box_regress :378-391).
  * out [cap][8] = [i,x1,y1,x2,y2,new_conf,class_score,class_pred] sorted by mask descending with
- * radar masks divided by 5; out_count[0] = rows.  regress_boxes = 0 skips the regression
+ * radar masks divided by 5; out_count[0] = rows; box_pitch = floats per img_boxes row (9, or 1 + det_cols).  regress_boxes = 0 skips the regression
  * (model_mode 2).  workspace >= me_finalize_workspace(cap) bytes. */
 size_t me_finalize_workspace(int cap);
 int me_finalize_output(const float* img_boxes, const float* rois, const float* refine, const float* regress,
-                       const float* mask, const int* counts, int cap, float thr_img, float thr_radar,
+                       const float* mask, const int* counts, int cap, int box_pitch, float thr_img, float thr_radar,
                        int regress_boxes, float* out, int* out_count, void* workspace, size_t workspace_bytes,
                        me_stream_t stream);
 

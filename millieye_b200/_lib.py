@@ -30,6 +30,10 @@ class HeadWeights(Structure):
         "fc1_w", "fc1_b", "fc2_w", "fc2_b")]
 
 
+class Stage2Weights(Structure):
+    _fields_ = [(n, c_void_p) for n in ("net1_w", "net1_b", "net2_w", "net2_b", "fc1_w", "fc1_b", "fc2_w", "fc2_b")]
+
+
 # name -> (restype, argtypes); kept in one table so tests can check it against the header.
 SIGNATURES = {
     "me_version": (c_int, []),
@@ -63,7 +67,9 @@ SIGNATURES = {
     "me_fusion_heads": (c_int, [c_void_p, c_int, c_void_p, c_int, POINTER(HeadWeights), c_void_p, c_void_p, c_int,
                                 c_void_p, c_void_p, c_void_p, c_void_p]),
     "me_finalize_workspace": (c_size_t, [c_int]),
-    "me_finalize_output": (c_int, [c_void_p] * 6 + [c_int, c_float, c_float, c_int, c_void_p, c_void_p, c_void_p,
+    "me_stage2_heads": (c_int, [c_void_p, c_int, POINTER(Stage2Weights), c_void_p, c_int, c_int, c_void_p, c_int, c_void_p,
+                                c_void_p, c_void_p]),
+    "me_finalize_output": (c_int, [c_void_p] * 6 + [c_int, c_int, c_float, c_float, c_int, c_void_p, c_void_p, c_void_p,
                                                     c_size_t, c_void_p]),
 }
 

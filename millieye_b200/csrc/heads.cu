@@ -52,16 +52,23 @@ build_proposals_kernel(const float* __restrict__ det, const int* __restrict__ de
       const int k = i - img * max_det;
       if (k < det_count[img]) {
         d = det + (1LL * img * max_det + k) * det_cols;
-        pass = (d[6] == static_cast<float>(class_idx));  // detection_i[:, 6] == self.class_idx
+        // m3: detection_i[:, 6] == self.class_idx (my_models.py:463); stage 2 keeps every class (m2 :325-330)
+        pass = class_idx < 0 || (d[6] == static_cast<float>(class_idx));
       }
     }
     const int slot = block_compact(pass, s_scan, &s_total);
     if (slot >= 0 && slot < cap) {
-      float* b = img_boxes + slot * 9;
-      b[0] = static_cast<float>(img);
+      if (class_idx < 0) {
+        float* b = img_boxes + 1LL * slot * (1 + det_cols);
+        b[0] = static_cast<float>(img);
+        for (int c = 0; c < det_cols; ++c) b[1 + c] = d[c];
+      } else {
+        float* b = img_boxes + slot * 9;
+        b[0] = static_cast<float>(img);
 #pragma unroll
-      for (int c = 0; c < 7; ++c) b[1 + c] = d[c];
-      b[8] = d[7 + class_idx];
+        for (int c = 0; c < 7; ++c) b[1 + c] = d[c];
+        b[8] = d[7 + class_idx];
+      }
       float* r = rois + slot * 5;
       r[0] = static_cast<float>(img);
       r[1] = d[0];
@@ -178,6 +185,65 @@ fusion_heads_kernel(const __half* __restrict__ hidden, int hidden_pitch, const _
   }
 }
 
+// Stage-2 variant (module2_mixed/my_models.py): refinement_head.forward :121-126 (FC 256->4, sigmoid FC 256->NV)
+// and ensemble_head.forward :153-161 (stack -> FC 2->32 + leaky -> flatten 32*NV -> FC -> LeakyReLU -> softmax);
+// the new confidence is column 1 of the softmax (:352).  One warp per RoI, lane = hidden unit of fc1.
+template <int NV>
+__global__ void __launch_bounds__(256)
+stage2_heads_kernel(const __half* __restrict__ hidden, int hidden_pitch, me_stage2_weights hw,
+                    const float* __restrict__ boxes, int box_pitch, const int* __restrict__ counts, int cap,
+                    float* __restrict__ regress, float* __restrict__ mask) {
+  const int lane = threadIdx.x & 31;
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int nwarps = (gridDim.x * blockDim.x) >> 5;
+  const int n_all = min(counts[1], cap);
+  for (int r = warp; r < n_all; r += nwarps) {
+    float hv[8];
+    {
+      const uint4 raw = *reinterpret_cast<const uint4*>(hidden + 1LL * r * hidden_pitch + lane * 8);
+      const __half2* p = reinterpret_cast<const __half2*>(&raw);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float2 f = __half22float2(p[e]);
+        hv[2 * e] = f.x;
+        hv[2 * e + 1] = f.y;
+      }
+    }
+    float reg[4];
+#pragma unroll
+    for (int o = 0; o < 4; ++o) {
+      const float* wrow = hw.net1_w + o * 256 + lane * 8;
+      float s = 0.f;
+#pragma unroll
+      for (int e = 0; e < 8; ++e) s = fmaf(hv[e], wrow[e], s);
+      reg[o] = warp_sum(s) + hw.net1_b[o];
+    }
+    const float* box = boxes + 1LL * r * box_pitch;
+    float o0 = 0.f, o1 = 0.f;
+#pragma unroll
+    for (int j = 0; j < NV; ++j) {
+      const float* wrow = hw.net2_w + j * 256 + lane * 8;
+      float s = 0.f;
+#pragma unroll
+      for (int e = 0; e < 8; ++e) s = fmaf(hv[e], wrow[e], s);
+      const float refv = sigmoidf_(warp_sum(s) + hw.net2_b[j]);
+      const float yolo = j == 0 ? box[5] : box[8 + (j - 1)];  // (obj_conf, class scores) m2 :347
+      const float hcell = leakyf_(fmaf(hw.fc1_w[lane * 2], refv, fmaf(hw.fc1_w[lane * 2 + 1], yolo, hw.fc1_b[lane])));
+      o0 = fmaf(hcell, hw.fc2_w[j * 32 + lane], o0);
+      o1 = fmaf(hcell, hw.fc2_w[NV * 32 + j * 32 + lane], o1);
+    }
+    o0 = leakyf_(warp_sum(o0) + hw.fc2_b[0]);
+    o1 = leakyf_(warp_sum(o1) + hw.fc2_b[1]);
+    const float mx = fmaxf(o0, o1);
+    const float e0 = expf(o0 - mx), e1 = expf(o1 - mx);
+    if (lane == 0) {
+#pragma unroll
+      for (int o = 0; o < 4; ++o) regress[r * 4 + o] = reg[o];
+      mask[r] = e1 / (e0 + e1);
+    }
+  }
+}
+
 __device__ __forceinline__ unsigned int desc_bits(float s) {
   unsigned int u = __float_as_uint(s);
   u = (u & 0x80000000u) ? ~u : (u | 0x80000000u);
@@ -188,7 +254,7 @@ __device__ __forceinline__ unsigned int desc_bits(float s) {
 __global__ void __launch_bounds__(kBlock)
 finalize_kernel(const float* __restrict__ img_boxes, const float* __restrict__ rois, const float* __restrict__ refine,
                 const float* __restrict__ regress, const float* __restrict__ mask, const int* __restrict__ counts,
-                int cap, float thr_img, float thr_radar, int do_regress, float* __restrict__ out,
+                int cap, int box_pitch, float thr_img, float thr_radar, int do_regress, float* __restrict__ out,
                 int* __restrict__ out_count, unsigned long long* __restrict__ keys) {
   __shared__ int s_scan[kBlock / 32];
   __shared__ int s_total;
@@ -253,8 +319,8 @@ finalize_kernel(const float* __restrict__ img_boxes, const float* __restrict__ r
     o[4] = y2;
     o[5] = mask[r];
     if (r < n_img) {
-      o[6] = img_boxes[r * 9 + 6];  // class score
-      o[7] = img_boxes[r * 9 + 7];  // class pred
+      o[6] = img_boxes[1LL * r * box_pitch + 6];  // class score
+      o[7] = img_boxes[1LL * r * box_pitch + 7];  // class pred
     } else {
       o[6] = refine[r * 2 + 1];
       o[7] = 0.f;
@@ -274,7 +340,7 @@ int me_build_proposals(const float* det, const int* det_count, int n, int max_de
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   ME_REQUIRE(det && det_count && img_boxes && rois && counts, "build_proposals: null argument");
   ME_REQUIRE(num_radar == 0 || radar_boxes, "build_proposals: radar boxes missing");
-  ME_REQUIRE(det_cols >= 8 && class_idx >= 0 && 7 + class_idx < det_cols, "build_proposals: bad det_cols/class_idx");
+  ME_REQUIRE(det_cols >= 8 && 7 + class_idx < det_cols, "build_proposals: bad det_cols/class_idx");
   ME_REQUIRE(cap > 0 && n > 0 && max_det > 0, "build_proposals: empty problem");
   build_proposals_kernel<<<1, kBlock, 0, stream>>>(det, det_count, n, max_det, det_cols, class_idx, radar_boxes, num_radar,
                                                    img_size, img_boxes, rois, counts, cap);
@@ -298,6 +364,22 @@ int me_fusion_heads(const void* hidden, int hidden_pitch, const void* radar_crop
   return ME_OK;
 }
 
+int me_stage2_heads(const void* hidden, int hidden_pitch, const me_stage2_weights* hw, const float* boxes, int box_pitch,
+                    int num_vec, const int* counts, int cap, float* regress, float* mask, me_stream_t stream_) {
+  using namespace me;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  ME_REQUIRE(hidden && hw && boxes && counts && regress && mask, "stage2_heads: null argument");
+  ME_REQUIRE(hidden_pitch >= 256 && hidden_pitch % 8 == 0, "stage2_heads: bad hidden pitch");
+  ME_REQUIRE(num_vec == 13, "stage2_heads: %d-entry class vectors unsupported (13 = 12 classes + objectness)", num_vec);
+  ME_REQUIRE(box_pitch >= 8 + (num_vec - 1), "stage2_heads: box rows too narrow");
+  int blocks = ceil_div(cap, 8);
+  if (blocks > 148 * 4) blocks = 148 * 4;
+  stage2_heads_kernel<13><<<blocks, 256, 0, stream>>>(static_cast<const __half*>(hidden), hidden_pitch, *hw, boxes,
+                                                      box_pitch, counts, cap, regress, mask);
+  ME_LAUNCH_CHECK();
+  return ME_OK;
+}
+
 size_t me_finalize_workspace(int cap) {
   if (cap <= 0) return 0;
   int kp = 1;
@@ -306,14 +388,16 @@ size_t me_finalize_workspace(int cap) {
 }
 
 int me_finalize_output(const float* img_boxes, const float* rois, const float* refine, const float* regress,
-                       const float* mask, const int* counts, int cap, float thr_img, float thr_radar, int regress_boxes,
+                       const float* mask, const int* counts, int cap, int box_pitch, float thr_img, float thr_radar,
+                       int regress_boxes,
                        float* out, int* out_count, void* workspace, size_t workspace_bytes, me_stream_t stream_) {
   using namespace me;
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   ME_REQUIRE(img_boxes && rois && refine && regress && mask && counts && out && out_count && workspace,
              "finalize: null argument");
   ME_REQUIRE(workspace_bytes >= me_finalize_workspace(cap), "finalize: workspace too small");
-  finalize_kernel<<<1, kBlock, 0, stream>>>(img_boxes, rois, refine, regress, mask, counts, cap, thr_img, thr_radar,
+  ME_REQUIRE(box_pitch >= 8, "finalize: box_pitch %d < 8", box_pitch);
+  finalize_kernel<<<1, kBlock, 0, stream>>>(img_boxes, rois, refine, regress, mask, counts, cap, box_pitch, thr_img, thr_radar,
                                             regress_boxes, out, out_count, static_cast<unsigned long long*>(workspace));
   ME_LAUNCH_CHECK();
   return ME_OK;

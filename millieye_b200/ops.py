@@ -223,11 +223,27 @@ def fusion_heads(hidden, hidden_pitch, crop, crop_pitch, head_weights, img_boxes
                                      stream_ptr()), "me_fusion_heads")
 
 
+def stage2_heads(hidden, hidden_pitch, weights, boxes, box_pitch, num_vec, counts, cap, regress, mask):
+    _need_cuda(hidden, boxes, counts, regress, mask)
+    check(_lib.lib().me_stage2_heads(ptr(hidden), hidden_pitch, byref(weights), ptr(boxes), box_pitch, num_vec,
+                                     ptr(counts), cap, ptr(regress), ptr(mask), stream_ptr()), "me_stage2_heads")
+
+
+def make_stage2_weights(tensors):
+    hw = _lib.Stage2Weights()
+    for name, _ in _lib.Stage2Weights._fields_:
+        t = tensors[name]
+        _need_cuda(t)
+        assert t.dtype == torch.float32 and t.is_contiguous()
+        setattr(hw, name, t.data_ptr())
+    return hw
+
+
 def finalize_output(img_boxes, rois, refine, regress, mask, counts, cap, thr_img, thr_radar, regress_boxes, out,
-                    out_count, ws):
+                    out_count, ws, box_pitch=9):
     _need_cuda(img_boxes, rois, refine, regress, mask, counts, out, out_count, ws)
     check(_lib.lib().me_finalize_output(ptr(img_boxes), ptr(rois), ptr(refine), ptr(regress), ptr(mask), ptr(counts),
-                                        cap, float(thr_img), float(thr_radar), 1 if regress_boxes else 0, ptr(out),
+                                        cap, box_pitch, float(thr_img), float(thr_radar), 1 if regress_boxes else 0, ptr(out),
                                         ptr(out_count), ptr(ws), ws.numel() * ws.element_size(), stream_ptr()),
           "me_finalize_output")
 

@@ -133,3 +133,43 @@ def network_forward(module_defs, sd, images, maps, radar_boxes, conf_thresh, mod
                             roi_score_map=roi_score_map, radar_score_map=radar_score_map, crop_img=crop_img,
                             crop_radar=crop_radar, reg=reg, ref_vec=ref_vec, masks=masks, positive=positive)
     return output
+
+
+def network_forward_stage2(module_defs, sd, images, conf_thresh, refine_threshold=0.0, class_num=12,
+                           use_torchvision=False):
+    """Stage-2 Network.forward with targets=None (reference module2_mixed/my_models.py:299-361): every class is
+    kept after NMS (:325-330), fcn_layers (= cnn_layers_1), ps_roi_align (:344), refinement_head (:121-126, Dropout
+    is the identity in eval), ensemble_head with a LeakyReLU before the softmax (:149-161), new confidence =
+    masks[:, 1] (:352), box regression, sort by the new confidence (:358), result on the CPU."""
+    feat, yolo_out = darknet_forward(module_defs, sd, images, prefix="base_detector.")
+    dets, _ = obox.non_max_suppression_cpp(yolo_out.clone().numpy(), conf_thresh, use_torchvision=use_torchvision)
+    rows = []
+    for i, d in enumerate(dets):
+        if d is not None:
+            b = np.zeros((len(d), 8 + class_num), dtype=np.float32)
+            b[:, 0] = i
+            b[:, 1:] = d
+            rows.append(b)
+    boxes = torch.from_numpy(np.concatenate(rows, 0)) if rows else torch.empty((0, 8 + class_num))
+    roi_score_map = img_cnn_layers(feat, sd, prefix="fcn_layers.")
+    if use_torchvision:
+        from torchvision.ops import ps_roi_align
+        crop = ps_roi_align(roi_score_map, boxes[:, :5], (7, 7), spatial_scale=1. / 16)
+    else:
+        crop = torch.from_numpy(oroi.ps_roi_align(roi_score_map.numpy(), boxes[:, :5].numpy(), 7, 1. / 16))
+    if len(boxes) == 0:
+        crop = crop.reshape(0, 10, 7, 7)
+    p = "refinement_head."
+    t = F.leaky_relu(F.linear(crop.flatten(start_dim=1), sd[p + "net0.0.weight"], sd[p + "net0.0.bias"]), 0.1)
+    reg = F.linear(t, sd[p + "net1.0.weight"], sd[p + "net1.0.bias"])
+    ref_vec = torch.sigmoid(F.linear(t, sd[p + "net2.0.weight"], sd[p + "net2.0.bias"]))
+    yolo_vec = torch.cat((boxes[:, 5:6], boxes[:, 8:]), 1)
+    e = "ensemble_head."
+    x = torch.stack((ref_vec, yolo_vec), -1)
+    x = F.leaky_relu(F.linear(x, sd[e + "fc1.0.weight"], sd[e + "fc1.0.bias"]), 0.1).flatten(start_dim=1)
+    x = F.leaky_relu(F.linear(x, sd[e + "fc2.0.weight"], sd[e + "fc2.0.bias"]), 0.1)
+    masks = torch.softmax(x, dim=1)
+    positive = masks[:, 1] > refine_threshold
+    out = torch.cat((boxes[positive, :1], box_regress(reg[positive], boxes[positive, 1:5]), masks[positive, 1:],
+                     boxes[positive, 6:8]), -1)
+    return out[torch.sort(out[:, 5], descending=True, stable=True).indices]

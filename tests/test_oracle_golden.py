@@ -130,3 +130,17 @@ def test_conv_flops_match_survey():
     assert odark.conv_flops(md, 416) / 1e9 == pytest.approx(65.864, abs=0.01)
     md = parse_model_config(configs.cfg_path("yolov3-tiny-12"))
     assert odark.conv_flops(md, 416) / 1e9 == pytest.approx(5.459, abs=0.01)
+
+
+def test_stage2_matches_reference(golden_dir):
+    """module2_mixed Network.forward (YOLO + R-CNN refinement, all 12 classes kept)."""
+    from millieye_b200.my_models_stage2 import Network, define_yolo
+    g = np.load(os.path.join(golden_dir, "stage2_tiny12_160.npz"))
+    model = Network(define_yolo(configs.cfg_path("yolov3-tiny-12")), conf_thresh=0.3)
+    sd = synth.fill_state_dict(model.state_dict(), seed=6, obj_bias=-1.0, head_gain=1.0)
+    assert list(sd.keys()) == list(g["keys"])
+    md = parse_model_config(configs.cfg_path("yolov3-tiny-12"))
+    with torch.no_grad():
+        out = ofus.network_forward_stage2(md, sd, synth.synth_images(2, 160, seed=6), 0.3)
+    assert tuple(out.shape) == g["out"].shape and out.shape[0] > 100
+    np.testing.assert_allclose(out.numpy(), g["out"], rtol=2e-4, atol=2e-4)
