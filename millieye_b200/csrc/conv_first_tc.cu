@@ -30,7 +30,9 @@ struct FCfg {
   static constexpr int STAGES = VEC ? 8 : 4;
   static constexpr int PROD_WARPS = VEC ? 8 : 16;
   static constexpr int ARRIVALS = VEC ? 32 : 128;  // producer threads per tile
-  static constexpr int THREADS = 32 * (PROD_WARPS + 1 + 4);
+  static constexpr int EPI_GROUPS = 2;             // two 4-warp epilogue groups alternate tiles
+  static constexpr int ACCS = 4;                   // TMEM accumulators in flight
+  static constexpr int THREADS = 32 * (PROD_WARPS + 1 + 4 * EPI_GROUPS);
   static constexpr int SMEM = STAGES * kABytes + 1024;
 };
 
@@ -73,9 +75,9 @@ conv_first_tc_kernel(const float* __restrict__ x, const __half* __restrict__ wk,
   uint8_t* s_a = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   __shared__ __align__(128) uint8_t s_b[COUT * kK * 2];
   __shared__ float s_bias[COUT];
-  __shared__ __align__(8) uint64_t full_bar[F::STAGES], empty_bar[F::STAGES], tmem_full[2], tmem_empty[2];
+  __shared__ __align__(8) uint64_t full_bar[F::STAGES], empty_bar[F::STAGES], tmem_full[FCfg<VEC>::ACCS], tmem_empty[FCfg<VEC>::ACCS];
   __shared__ uint32_t tmem_ptr;
-  constexpr int TMEM_COLS = (2 * COUT <= 32) ? 32 : (2 * COUT <= 64) ? 64 : 128;
+  constexpr int TMEM_COLS = (F::ACCS * COUT <= 32) ? 32 : (F::ACCS * COUT <= 64) ? 64 : (F::ACCS * COUT <= 128) ? 128 : 256;
   constexpr int MMA_WARP = F::PROD_WARPS;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -94,7 +96,7 @@ conv_first_tc_kernel(const float* __restrict__ x, const __half* __restrict__ wk,
         ptx::mbar_init(&full_bar[s], F::ARRIVALS);
         ptx::mbar_init(&empty_bar[s], 1);
       }
-      for (int a = 0; a < 2; ++a) {
+      for (int a = 0; a < F::ACCS; ++a) {
         ptx::mbar_init(&tmem_full[a], 1);
         ptx::mbar_init(&tmem_empty[a], 4);
       }
@@ -195,8 +197,8 @@ conv_first_tc_kernel(const float* __restrict__ x, const __half* __restrict__ wk,
       uint32_t stage = 0, phase = 0;
       int it = 0;
       for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++it) {
-        const int acc = it & 1;
-        mbar_wait_spin(&tmem_empty[acc], ((it >> 1) & 1) ^ 1);
+        const int acc = it & (F::ACCS - 1);
+        mbar_wait_spin(&tmem_empty[acc], ((it / F::ACCS) & 1) ^ 1);
         mbar_wait_spin(&full_bar[stage], phase);
         ptx::tc_fence_after();
         const uint32_t a_addr = ptx::smem_u32(s_a + stage * kABytes);
@@ -215,10 +217,11 @@ conv_first_tc_kernel(const float* __restrict__ x, const __half* __restrict__ wk,
     // ------------------------------------------------------------ epilogue (last 4 warps)
     const int q = warp & 3;
     const int row = q * 32 + lane;
-    int it = 0;
-    for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++it) {
-      const int acc = it & 1;
-      mbar_wait_spin(&tmem_full[acc], (it >> 1) & 1);
+    const int group = (warp - (MMA_WARP + 1)) >> 2;  // this group takes tiles it = group, group + 2, ...
+    for (int it = group; blockIdx.x + it * gridDim.x < tiles; it += F::EPI_GROUPS) {
+      const int tile = blockIdx.x + it * gridDim.x;
+      const int acc = it & (F::ACCS - 1);
+      mbar_wait_spin(&tmem_full[acc], (it / F::ACCS) & 1);
       ptx::tc_fence_after();
       const uint32_t taddr = tmem_base + acc * COUT + (static_cast<uint32_t>(q * 32) << 16);
       const int pix = tile * kTileM + row;
