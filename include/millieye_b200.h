@@ -205,6 +205,27 @@ int me_finalize_output(const float* img_boxes, const float* rois, const float* r
                        int regress_boxes, float* out, int* out_count, void* workspace, size_t workspace_bytes,
                        me_stream_t stream);
 
+/* ---- radar point cloud -> network input map (f1 + f2) ----------------------- */
+typedef struct me_radar_cfg {
+  double calib[12];        /* fx, cx, fy, cy, k1, k2, t1, t2, k3, trans_x, trans_y, trans_z
+                              (load_calib, data_collection/utils/utils.py:63-76)                        */
+  int img_w, img_h;        /* camera frame: FOV filter and histogram range (640 x 480)                  */
+  double max_depth;        /* keep depth < max_depth      (prepare_data.py:41,108; run_mp.py:248)       */
+  double min_velocity;     /* keep |v| >= min_velocity    (prepare_data.py:39,108)                      */
+  int bin_w, bin_h;        /* round(img/scale), scale = max(img_w, img_h)/32 (utils/datasets.py:70-71)  */
+  double edges_w[33];      /* np.linspace(0, img_w, bin_w + 1) - histogram2d's bin edges               */
+  double edges_h[33];      /* np.linspace(0, img_h, bin_h + 1)                                          */
+  int out_size;            /* S/16 side of the map fed to the network (datasets.py:320-322)             */
+} me_radar_cfg;
+
+/* points: fp32 [n][cap][4] = radar (x, y, z, velocity), counts[n] live points per frame.
+ * Per frame: from_3d_to_2d (float64, int64 truncation) -> FOV/depth/velocity filter -> plot_radar_heatmap
+ * (count / mean depth / |mean velocity| histograms, clipped to 0..1) -> pad_to_square -> bilinear resize
+ * (align_corners=True).  maps_out: fp32 [n][3][out_size][out_size].  Optional uvzv_out [n][cap][4] +
+ * kept_out[n]: the filtered (u, v, depth, velocity) list the reference hands to DBSCAN (prepare_data.py:110). */
+int me_radar_maps(const float* points, const int* counts, int n, int cap, const me_radar_cfg* cfg,
+                  float* maps_out, float* uvzv_out, int* kept_out, me_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -30,6 +30,12 @@ class HeadWeights(Structure):
         "fc1_w", "fc1_b", "fc2_w", "fc2_b")]
 
 
+class RadarCfg(Structure):
+    _fields_ = [("calib", c_double * 12), ("img_w", c_int), ("img_h", c_int), ("max_depth", c_double),
+                ("min_velocity", c_double), ("bin_w", c_int), ("bin_h", c_int), ("edges_w", c_double * 33),
+                ("edges_h", c_double * 33), ("out_size", c_int)]
+
+
 class Stage2Weights(Structure):
     _fields_ = [(n, c_void_p) for n in ("net1_w", "net1_b", "net2_w", "net2_b", "fc1_w", "fc1_b", "fc2_w", "fc2_b")]
 
@@ -67,6 +73,7 @@ SIGNATURES = {
     "me_fusion_heads": (c_int, [c_void_p, c_int, c_void_p, c_int, POINTER(HeadWeights), c_void_p, c_void_p, c_int,
                                 c_void_p, c_void_p, c_void_p, c_void_p]),
     "me_finalize_workspace": (c_size_t, [c_int]),
+    "me_radar_maps": (c_int, [c_void_p, c_void_p, c_int, c_int, POINTER(RadarCfg), c_void_p, c_void_p, c_void_p, c_void_p]),
     "me_stage2_heads": (c_int, [c_void_p, c_int, POINTER(Stage2Weights), c_void_p, c_int, c_int, c_void_p, c_int, c_void_p,
                                 c_void_p, c_void_p]),
     "me_finalize_output": (c_int, [c_void_p] * 6 + [c_int, c_int, c_float, c_float, c_int, c_void_p, c_void_p, c_void_p,

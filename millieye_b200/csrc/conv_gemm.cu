@@ -44,6 +44,7 @@ struct ConvParams {
   int im2col;
   int stages;
   int bres_bytes;  // weight-stationary mode: bytes of the resident weight slab (num_kb * B_BYTES)
+  int dbg;         // ME_CONV_DBG attribution mask: 1 skip epilogue, 2 skip operand loads, 4 skip MMAs
   const float* bias;
   unsigned long long* debug;  // host-mapped word, written before a watchdog trap
 };
@@ -205,6 +206,12 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         for (int kb = 0; kb < p.num_kb; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1, p.debug, 0x100u + stage);
           uint8_t* sa = stage_base + stage * STAGE;
+          if (p.dbg & 2) {  // attribution run: no operand traffic, barrier protocol intact
+            ptx::mbar_arrive(&full_bar[stage]);
+            if (++cb == p.kb_per_tap) { cb = 0; ++tap; }
+            if (++stage == (uint32_t)p.stages) { stage = 0; phase ^= 1; }
+            continue;
+          }
           ptx::mbar_arrive_expect_tx(&full_bar[stage], STAGE);
           if (p.im2col) {
             const int r = tap / 3, s = tap - r * 3;
@@ -239,6 +246,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           const uint32_t b_addr = WS ? ptx::smem_u32(bres + kb * C::B_BYTES) : a_addr + C::A_BYTES;
 #pragma unroll
           for (int k = 0; k < BK / 16; ++k) {
+            if (p.dbg & 4) break;  // attribution run: no tensor work
             const uint64_t adesc = ptx::make_kmajor_desc(a_addr + k * 32, BK * 2);
             const uint64_t bdesc = ptx::make_kmajor_desc(b_addr + k * 32, BK * 2);
             ptx::umma_f16_ss(d_tmem, adesc, bdesc, idesc, (kb | k) != 0 ? 1u : 0u);
@@ -279,6 +287,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
 #pragma unroll 1
       for (int c = 0; c < BN; c += 32) {
         uint32_t r[32];
+        if (p.dbg & 1) break;  // attribution run: accumulators released unread
         ptx::tmem_ld_32x32b_x32(t_row + c, r);
         ptx::tmem_ld_wait();
         float v[32];
@@ -326,7 +335,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       if (lane == 0) ptx::mbar_arrive(&tmem_empty[acc]);  // accumulator may be overwritten
       ptx::fence_proxy_async_smem();                       // staging writes -> visible to TMA
       ptx::named_bar_sync(kEpiBarrierId, kEpiThreads);
-      if (leader) {
+      if (leader && !(p.dbg & 1)) {
 #pragma unroll
         for (int sub = 0; sub < C::NUM_SUB; ++sub)
           ptx::tma_store_2d(&tmC, staging + sub * C::SUB_BYTES, n0 + sub * C::SUB_COLS, m0);
@@ -395,6 +404,14 @@ int launch(const me_conv_desc* d, const void* x, const void* w, const float* bia
   int rc = ensure_debug_word();
   if (rc != ME_OK) return rc;
   p.debug = g_debug_dev;
+  {
+    static int dbg = -1;
+    if (dbg < 0) {
+      const char* e = getenv("ME_CONV_DBG");
+      dbg = e ? atoi(e) : 0;
+    }
+    p.dbg = dbg;
+  }
 
   constexpr int STAGE = WS ? C::A_BYTES : C::STAGE_BYTES;
   p.bres_bytes = WS ? p.num_kb * C::B_BYTES : 0;

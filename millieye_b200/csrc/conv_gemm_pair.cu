@@ -16,6 +16,7 @@
 //            both CTAs release the accumulator on the leader's tmem_empty barrier (8 arrivals).
 #include "common.cuh"
 #include "ptx.cuh"
+#include <cstdlib>
 
 namespace me {
 
@@ -44,6 +45,7 @@ struct PairParams {
   int has_res;
   int im2col;
   int stages;
+  int dbg;  // ME_CONV_DBG bit mask for attribution runs: 1 skip epilogue, 2 skip operand loads, 4 skip MMAs
   const float* bias;
   unsigned long long* debug;
 };
@@ -168,6 +170,12 @@ conv_gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
           uint8_t* sa = stage_base + stage * C::STAGE_BYTES;
           uint8_t* sb = sa + C::A_BYTES;
           const uint32_t full_leader = ptx::mapa(ptx::smem_u32(&full_bar[stage]), 0);
+          if (p.dbg & 2) {  // attribution run: no operand traffic, the barrier protocol stays intact
+            if (leader) ptx::mbar_arrive(&full_bar[stage]);
+            if (++cb == p.kb_per_tap) { cb = 0; ++tap; }
+            if (++stage == (uint32_t)p.stages) { stage = 0; phase ^= 1; }
+            continue;
+          }
           if (leader) ptx::mbar_arrive_expect_tx(&full_bar[stage], 2 * C::STAGE_BYTES);  // both CTAs' bytes
           if (p.im2col) {
             const int r = tap / 3, s = tap - r * 3;
@@ -201,6 +209,7 @@ conv_gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
           const uint32_t b_addr = a_addr + C::A_BYTES;
 #pragma unroll
           for (int k = 0; k < kBK / 16; ++k) {
+            if (p.dbg & 4) break;  // attribution run: no tensor work
             const uint64_t adesc = ptx::make_kmajor_desc(a_addr + k * 32, kBK * 2);
             const uint64_t bdesc = ptx::make_kmajor_desc(b_addr + k * 32, kBK * 2);
             ptx::umma_f16_ss_pair(d_tmem, adesc, bdesc, idesc, (kb | k) != 0 ? 1u : 0u);
@@ -242,6 +251,7 @@ conv_gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
       const uint32_t t_row = tmem_base + acc * BN + (static_cast<uint32_t>(q * 32) << 16);
 #pragma unroll 1
       for (int c = 0; c < BN; c += 32) {
+        if (p.dbg & 1) break;  // attribution run: accumulators are released unread
         uint32_t r[32];
         ptx::tmem_ld_32x32b_x32(t_row + c, r);
         ptx::tmem_ld_wait();
@@ -278,7 +288,7 @@ conv_gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
       if (lane == 0) ptx::mbar_arrive_cluster(ptx::mapa(ptx::smem_u32(&tmem_empty[acc]), 0));
       ptx::fence_proxy_async_smem();
       ptx::named_bar_sync(kEpiBarrierId, kEpiThreads);
-      if (eleader && m0 < p.M) {
+      if (eleader && m0 < p.M && !(p.dbg & 1)) {
 #pragma unroll
         for (int sub = 0; sub < C::NUM_SUB; ++sub)
           ptx::tma_store_2d(&tmC, staging + sub * C::SUB_BYTES, n0 + sub * C::SUB_COLS, m0);
@@ -323,6 +333,14 @@ int launch_pair(const me_conv_desc* d, const void* x, const void* w, const float
   int rc = conv_ensure_debug_word();
   if (rc != ME_OK) return rc;
   p.debug = conv_debug_word();
+  {
+    static int dbg = -1;
+    if (dbg < 0) {
+      const char* e = getenv("ME_CONV_DBG");
+      dbg = e ? atoi(e) : 0;
+    }
+    p.dbg = dbg;
+  }
 
   int stages = (227 * 1024 - 1024 - C::STAGING_BYTES - C::TAIL_BYTES) / C::STAGE_BYTES;
   if (stages > kMaxStages) stages = kMaxStages;
