@@ -44,6 +44,7 @@ struct ConvParams {
   int im2col;
   int stages;
   int bres_bytes;  // weight-stationary mode: bytes of the resident weight slab (num_kb * B_BYTES)
+  int kps;         // K blocks per pipeline stage (one mbarrier round trip)
   int dbg;         // ME_CONV_DBG attribution mask: 1 skip epilogue, 2 skip operand loads, 4 skip MMAs
   const float* bias;
   unsigned long long* debug;  // host-mapped word, written before a watchdog trap
@@ -136,7 +137,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* bres = smem;  // WS only
   uint8_t* stage_base = smem + (WS ? p.bres_bytes : 0);
-  uint8_t* staging = stage_base + p.stages * STAGE;
+  uint8_t* staging = stage_base + p.stages * p.kps * STAGE;
   float* s_bias = reinterpret_cast<float*>(staging + C::STAGING_BYTES);
   uint64_t* bars = reinterpret_cast<uint64_t*>(s_bias + BN);
   uint64_t* full_bar = bars;                     // [kMaxStages]
@@ -203,24 +204,29 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           cn = t / p.Ho;
         }
         int tap = 0, cb = 0;
-        for (int kb = 0; kb < p.num_kb; ++kb) {
+        // One barrier round trip (wait empty -> expect_tx -> loads) covers p.kps consecutive K blocks: a thin
+        // layer's K block is only a few dozen MMA clocks, far less than the ~300 clocks a round trip costs.
+        for (int kb0 = 0; kb0 < p.num_kb; kb0 += p.kps) {
           mbar_wait(&empty_bar[stage], phase ^ 1, p.debug, 0x100u + stage);
-          uint8_t* sa = stage_base + stage * STAGE;
           if (p.dbg & 2) {  // attribution run: no operand traffic, barrier protocol intact
             ptx::mbar_arrive(&full_bar[stage]);
-            if (++cb == p.kb_per_tap) { cb = 0; ++tap; }
-            if (++stage == (uint32_t)p.stages) { stage = 0; phase ^= 1; }
-            continue;
-          }
-          ptx::mbar_arrive_expect_tx(&full_bar[stage], STAGE);
-          if (p.im2col) {
-            const int r = tap / 3, s = tap - r * 3;
-            ptx::tma_load_im2col_4d(&tmA, &full_bar[stage], sa, cb * BK, cw, ch, cn, (uint16_t)s, (uint16_t)r);
           } else {
-            ptx::tma_load_2d(&tmA, &full_bar[stage], sa, cb * BK, m0);
+            ptx::mbar_arrive_expect_tx(&full_bar[stage], p.kps * STAGE);
           }
-          if (!WS) ptx::tma_load_2d(&tmB, &full_bar[stage], sa + C::A_BYTES, kb * BK, n0);
-          if (++cb == p.kb_per_tap) { cb = 0; ++tap; }
+          for (int j = 0; j < p.kps; ++j) {
+            const int kb = kb0 + j;
+            uint8_t* sa = stage_base + (stage * p.kps + j) * STAGE;
+            if (!(p.dbg & 2)) {
+              if (p.im2col) {
+                const int r = tap / 3, s = tap - r * 3;
+                ptx::tma_load_im2col_4d(&tmA, &full_bar[stage], sa, cb * BK, cw, ch, cn, (uint16_t)s, (uint16_t)r);
+              } else {
+                ptx::tma_load_2d(&tmA, &full_bar[stage], sa, cb * BK, m0);
+              }
+              if (!WS) ptx::tma_load_2d(&tmB, &full_bar[stage], sa + C::A_BYTES, kb * BK, n0);
+            }
+            if (++cb == p.kb_per_tap) { cb = 0; ++tap; }
+          }
           if (++stage == (uint32_t)p.stages) { stage = 0; phase ^= 1; }
         }
       }
@@ -239,17 +245,20 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         mbar_wait(&tmem_empty[acc], acc_phase ^ 1, p.debug, 0x200u + acc);
         ptx::tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * BN;
-        for (int kb = 0; kb < p.num_kb; ++kb) {
+        for (int kb0 = 0; kb0 < p.num_kb; kb0 += p.kps) {
           mbar_wait(&full_bar[stage], phase, p.debug, 0x300u + stage);
           ptx::tc_fence_after();
-          const uint32_t a_addr = ptx::smem_u32(stage_base + stage * STAGE);
-          const uint32_t b_addr = WS ? ptx::smem_u32(bres + kb * C::B_BYTES) : a_addr + C::A_BYTES;
+          for (int j = 0; j < p.kps; ++j) {
+            const int kb = kb0 + j;
+            const uint32_t a_addr = ptx::smem_u32(stage_base + (stage * p.kps + j) * STAGE);
+            const uint32_t b_addr = WS ? ptx::smem_u32(bres + kb * C::B_BYTES) : a_addr + C::A_BYTES;
 #pragma unroll
-          for (int k = 0; k < BK / 16; ++k) {
-            if (p.dbg & 4) break;  // attribution run: no tensor work
-            const uint64_t adesc = ptx::make_kmajor_desc(a_addr + k * 32, BK * 2);
-            const uint64_t bdesc = ptx::make_kmajor_desc(b_addr + k * 32, BK * 2);
-            ptx::umma_f16_ss(d_tmem, adesc, bdesc, idesc, (kb | k) != 0 ? 1u : 0u);
+            for (int k = 0; k < BK / 16; ++k) {
+              if (p.dbg & 4) break;  // attribution run: no tensor work
+              const uint64_t adesc = ptx::make_kmajor_desc(a_addr + k * 32, BK * 2);
+              const uint64_t bdesc = ptx::make_kmajor_desc(b_addr + k * 32, BK * 2);
+              ptx::umma_f16_ss(d_tmem, adesc, bdesc, idesc, (kb | k) != 0 ? 1u : 0u);
+            }
           }
           ptx::umma_commit(&empty_bar[stage]);  // frees the smem stage when these MMAs retire
           if (++stage == (uint32_t)p.stages) { stage = 0; phase ^= 1; }
@@ -362,6 +371,30 @@ bool pdl_enabled_impl() {
 }
 inline bool pdl_enabled() { return pdl_enabled_impl(); }
 
+bool conv_kps_enabled();
+
+// K blocks handled per pipeline stage (= per mbarrier round trip of producer and MMA issuer).  Attribution runs
+// (profiles/round1/attribution_early.log) showed a round trip costs ~300 clocks on each side while a 128 x BN x 64
+// K block is 64..256 tensor clocks on one CTA, so thin layers were bound by barrier latency, not by loads or MMAs.
+// Prefer a whole filter row (3 taps) for 3x3 layers whose tap is one K block, else the largest of 4 / 2 that
+// divides the K loop, as long as >= 3 stages (>= 2 for the filter-row case) still fit.  ME_CONV_KPS=1: off.
+int choose_kps(int ksize, int kb_per_tap, int num_kb, int stage_bytes, int budget) {
+  if (!conv_kps_enabled()) return 1;
+  if (ksize == 3 && kb_per_tap == 1 && budget / (3 * stage_bytes) >= 2) return 3;
+  for (int k : {4, 2})
+    if (num_kb % k == 0 && budget / (k * stage_bytes) >= 3) return k;
+  return 1;
+}
+
+bool conv_kps_enabled() {
+  static int v = -1;
+  if (v < 0) {
+    const char* e = getenv("ME_CONV_KPS");
+    v = (e && e[0] == '1') ? 0 : 1;
+  }
+  return v != 0;
+}
+
 unsigned long long* g_debug_host = nullptr;
 unsigned long long* g_debug_dev = nullptr;
 
@@ -415,11 +448,13 @@ int launch(const me_conv_desc* d, const void* x, const void* w, const float* bia
 
   constexpr int STAGE = WS ? C::A_BYTES : C::STAGE_BYTES;
   p.bres_bytes = WS ? p.num_kb * C::B_BYTES : 0;
-  int stages = (227 * 1024 - 1024 - C::STAGING_BYTES - C::TAIL_BYTES - p.bres_bytes) / STAGE;
+  const int budget = 227 * 1024 - 1024 - C::STAGING_BYTES - C::TAIL_BYTES - p.bres_bytes;
+  p.kps = choose_kps(d->ksize, p.kb_per_tap, p.num_kb, STAGE, budget);
+  int stages = budget / (p.kps * STAGE);
   if (stages > kMaxStages) stages = kMaxStages;
   ME_REQUIRE(stages >= 2, "conv: not enough shared memory for a 2-stage pipeline");
   p.stages = stages;
-  const int smem = 1024 + p.bres_bytes + stages * STAGE + C::STAGING_BYTES + C::TAIL_BYTES;
+  const int smem = 1024 + p.bres_bytes + stages * p.kps * STAGE + C::STAGING_BYTES + C::TAIL_BYTES;
 
   CUtensorMap tmA, tmB, tmC, tmR;
   const CUtensorMapSwizzle swz_k = swizzle_for_row_bytes(BK * 2);
@@ -486,6 +521,7 @@ static int conv_ws_mode() {
   static int v = -1;
   if (v < 0) {
     const char* e = getenv("ME_CONV_WS");
+    // per-layer probes (profiles/round1/kps_ws_probe.log): 208^2 3x3 32->64 goes 222 -> 165 us with resident weights
     v = e ? (e[0] == '0' ? 0 : (e[0] == '2' ? 2 : 1)) : 1;
   }
   return v;
@@ -545,10 +581,17 @@ int me_conv_gemm(const me_conv_desc* d, const void* x, const void* w_packed, con
   auto ws_ok = [&](int bn) {
     if (f32 || !conv_ws_enabled()) return false;
     const int tiles_n = ceil_div(cout, bn), tiles_m = static_cast<int>((m + kBM - 1) / kBM);
-    const long long need = 1024LL + 1LL * num_kb * bn * bk * 2 + 3LL * kBM * bk * 2 + 1LL * kBM * bn * 2 + bn * 4 + 64 * 8 + 16;
     const int sms = sm_count() > 0 ? sm_count() : 148;
-    if (need > 227 * 1024 || tiles_n > sms) return false;
+    const int a_bytes = kBM * bk * 2, b_bytes = bn * bk * 2;
+    const int budget = 227 * 1024 - 1024 - kBM * bn * 2 - (bn * 4 + 64 * 8 + 16);
+    const int budget_ws = budget - num_kb * b_bytes;
+    if (budget_ws < 3 * a_bytes || tiles_n > sms) return false;
     if (conv_ws_mode() == 2) return true;
+    // keep the weights resident only if that does not cost K-block grouping or pipeline depth
+    const int kb_per_tap = round_up(d->cin, bk) / bk;
+    const int kps_ws = choose_kps(d->ksize, kb_per_tap, num_kb, a_bytes, budget_ws);
+    const int kps_plain = choose_kps(d->ksize, kb_per_tap, num_kb, a_bytes + b_bytes, budget);
+    if (kps_ws < kps_plain || budget_ws / (kps_ws * a_bytes) < 3) return false;
     return tiles_n <= 4 && tiles_m >= 4 * (sms / tiles_n);
   };
 #define ME_GO(BN, BK, F32)                                                                        \
