@@ -161,6 +161,7 @@ def run_gpu(args):
     import torch.distributed as dist
     from millieye_b200 import ops
     from millieye_b200.dist import gather_detections
+    from millieye_b200.engine import capture_graph
     from oracle import darknet as odark
     from oracle.parse_config import parse_model_config
     from millieye_b200 import configs
@@ -232,10 +233,8 @@ def run_gpu(args):
     conv_ms = None
     if rank == 0:
         conv_ops = {i for i, b in enumerate(_op_kinds(plan)) if b == "conv"}
-        g = torch.cuda.CUDAGraph()
         torch.cuda.synchronize()
-        with torch.cuda.graph(g):
-            plan.enqueue_split(only=conv_ops)
+        g = capture_graph(lambda: plan.enqueue_split(only=conv_ops))
         for _ in range(3):
             g.replay()
         torch.cuda.synchronize()

@@ -17,6 +17,9 @@ namespace {
 
 constexpr int kSelThreads = 1024;
 constexpr int kMaxSmemKeys = 16384;
+constexpr int kSmemBoxes = 2048;
+constexpr int kMatrixK = 512;     // up to this many candidates the suppression matrix is built in shared memory
+constexpr int kCompactIters = 16;  // rows / kSelThreads handled by the single-scan compaction  // sorted candidate boxes are staged in shared memory up to this many
 
 struct Layout {
   // per-image slices of the workspace (all sized by `rows`, keys by pow2(rows))
@@ -60,62 +63,43 @@ __device__ inline Layout layout_for(void* ws, int rows, int img) {
   return L;
 }
 
-// One warp per prediction row: cxcywh -> xyxy, objectness filter, class max / first arg-max.
-__global__ void nms_prepare_kernel(float* __restrict__ pred, int n, int rows, int nc, float conf_thresh, int inplace,
-                                   void* ws) {
-  const int lane = threadIdx.x & 31;
-  const long long warp_id = (blockIdx.x * 1LL * blockDim.x + threadIdx.x) >> 5;
-  const long long nwarps = (1LL * gridDim.x * blockDim.x) >> 5;
+// One thread per prediction row: cxcywh -> xyxy (in place if asked), objectness filter, and - for the few rows that
+// pass - class max / first arg-max.  (A warp per row left 31 lanes idle on the ~99 % of rows that fail the filter
+// and serialised the row's five loads behind one lane: 71 us for 32 x 10647 rows.)
+__global__ void __launch_bounds__(256)
+nms_prepare_kernel(float* __restrict__ pred, int n, int rows, int nc, float conf_thresh, int inplace, void* ws) {
+  const long long total = 1LL * n * rows;
   const int attrs = 5 + nc;
-  for (long long rr = warp_id; rr < 1LL * n * rows; rr += nwarps) {
+  for (long long rr = blockIdx.x * 1LL * blockDim.x + threadIdx.x; rr < total; rr += 1LL * gridDim.x * blockDim.x) {
     const int img = static_cast<int>(rr / rows);
     const int row = static_cast<int>(rr - 1LL * img * rows);
     float* src = pred + rr * attrs;
     Layout L = layout_for(ws, rows, img);
-    float conf = 0.f;
-    if (lane == 0) {
-      const float cx = src[0], cy = src[1], w = src[2], h = src[3];
-      conf = src[4];
-      // xywh2xyxy, utils.py:68-74: x - w / 2, x + w / 2 (the halving is exact)
-      const float hw = __fdiv_rn(w, 2.f), hh = __fdiv_rn(h, 2.f);
-      const float x1 = __fsub_rn(cx, hw), y1 = __fsub_rn(cy, hh);
-      const float x2 = __fadd_rn(cx, hw), y2 = __fadd_rn(cy, hh);
-      L.box[row * 4 + 0] = x1;
-      L.box[row * 4 + 1] = y1;
-      L.box[row * 4 + 2] = x2;
-      L.box[row * 4 + 3] = y2;
-      L.conf[row] = conf;
-      if (inplace) {
-        src[0] = x1;
-        src[1] = y1;
-        src[2] = x2;
-        src[3] = y2;
-      }
+    const float cx = src[0], cy = src[1], w = src[2], h = src[3], conf = src[4];
+    // xywh2xyxy, utils.py:68-74: x - w / 2, x + w / 2 (the halving is exact)
+    const float hw = __fdiv_rn(w, 2.f), hh = __fdiv_rn(h, 2.f);
+    const float x1 = __fsub_rn(cx, hw), y1 = __fsub_rn(cy, hh);
+    const float x2 = __fadd_rn(cx, hw), y2 = __fadd_rn(cy, hh);
+    *reinterpret_cast<float4*>(L.box + row * 4) = make_float4(x1, y1, x2, y2);
+    L.conf[row] = conf;
+    if (inplace) {
+      src[0] = x1;
+      src[1] = y1;
+      src[2] = x2;
+      src[3] = y2;
     }
-    conf = __shfl_sync(0xffffffffu, conf, 0);
-    if (!(conf >= conf_thresh)) continue;  // warp-uniform
-    float best = -INFINITY;
-    int best_i = 0x7fffffff;
-    for (int c = lane; c < nc; c += 32) {
+    if (!(conf >= conf_thresh)) continue;
+    float best = src[5];
+    int best_i = 0;
+    for (int c = 1; c < nc; ++c) {
       const float v = src[5 + c];
-      if (v > best) {  // strict: the first maximum inside this lane's stride wins
+      if (v > best) {  // strict: the first maximum wins (torch.max tie rule)
         best = v;
         best_i = c;
       }
     }
-#pragma unroll
-    for (int off = 16; off > 0; off >>= 1) {
-      const float ov = __shfl_xor_sync(0xffffffffu, best, off);
-      const int oi = __shfl_xor_sync(0xffffffffu, best_i, off);
-      if (ov > best || (ov == best && oi < best_i)) {
-        best = ov;
-        best_i = oi;
-      }
-    }
-    if (lane == 0) {
-      L.cls_conf[row] = best;
-      L.cls_idx[row] = best_i == 0x7fffffff ? 0 : best_i;
-    }
+    L.cls_conf[row] = best;
+    L.cls_idx[row] = best_i;
   }
 }
 
@@ -129,7 +113,7 @@ __device__ __forceinline__ unsigned int score_desc_bits(float s) {
 // One block per image: compaction (row order) -> bitonic sort of (score desc, row asc) keys ->
 // greedy suppression, stopping once max_det boxes are kept.
 __global__ void __launch_bounds__(kSelThreads, 1)
-nms_select_kernel(const float* __restrict__ pred, int rows, int nc, float conf_thresh, double nms_thresh, int max_det,
+nms_select_kernel(const float* __restrict__ pred, int rows, int nc, float conf_thresh, float nms_thresh_f, int max_det,
                   float* __restrict__ det, int* __restrict__ det_count, int* __restrict__ det_index, void* ws) {
   extern __shared__ unsigned long long s_dyn[];
   __shared__ int s_scan[kSelThreads / 32];
@@ -137,6 +121,7 @@ nms_select_kernel(const float* __restrict__ pred, int rows, int nc, float conf_t
   __shared__ float s_red[kSelThreads / 32];
   __shared__ float s_maxc;
   __shared__ int s_keep[256];
+  __shared__ int s_cnt[kCompactIters * (kSelThreads / 32)];
 
   const int img = blockIdx.x;
   const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
@@ -146,36 +131,90 @@ nms_select_kernel(const float* __restrict__ pred, int rows, int nc, float conf_t
   const int pow2 = next_pow2(rows);
   unsigned long long* keys = (pow2 <= kMaxSmemKeys) ? s_dyn : L.keys;
   unsigned char* supp = reinterpret_cast<unsigned char*>(s_dyn + (pow2 <= kMaxSmemKeys ? pow2 : 0));
+  // staging area for the sorted boxes: the greedy loop reads box i once per survivor, and a global/L2 round trip
+  // per survivor (~0.7 us x up to 200) was most of this kernel's 84 us
+  float* sm_box = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(supp) + rows + 15) & ~uintptr_t(15));
+  float* sm_area = sm_box + kSmemBoxes * 4;
+  int* sm_cls = reinterpret_cast<int*>(sm_area + kSmemBoxes);
+  uint32_t* sm_mask = reinterpret_cast<uint32_t*>(sm_cls + kSmemBoxes);  // [kMatrixK][kMatrixK / 32]
 
   // ---- 1. order-preserving compaction of candidate rows into keys[0..k)
-  if (tid == 0) s_k = 0;
-  __syncthreads();
-  for (int base = 0; base < rows; base += kSelThreads) {
-    const int row = base + tid;
-    const bool pass = row < rows && (L.conf[row] >= conf_thresh);
-    const unsigned int ballot = __ballot_sync(0xffffffffu, pass);
-    if (lane == 0) s_scan[wid] = __popc(ballot);
+  const int iters = (rows + kSelThreads - 1) / kSelThreads;
+  if (iters <= kCompactIters) {
+    // all loads first, one scan over the (iteration, warp) pass counts: 3 block barriers instead of 4 per 1024 rows
+    float cv[kCompactIters];
+    unsigned int bal[kCompactIters];
+#pragma unroll
+    for (int it = 0; it < kCompactIters; ++it) {
+      const int row = it * kSelThreads + tid;
+      cv[it] = (it < iters && row < rows) ? L.conf[row] : 0.f;
+    }
+#pragma unroll
+    for (int it = 0; it < kCompactIters; ++it) {
+      const int row = it * kSelThreads + tid;
+      const bool pass = it < iters && row < rows && (cv[it] >= conf_thresh);
+      bal[it] = __ballot_sync(0xffffffffu, pass);
+      if (lane == 0) s_cnt[it * (kSelThreads / 32) + wid] = __popc(bal[it]);
+    }
     __syncthreads();
     if (wid == 0) {
-      int v = s_scan[lane];
-      int incl = v;
+      // entries are ordered (iteration, warp) = row order; lane l owns `iters` consecutive entries
+      int sum = 0;
+      for (int e = 0; e < iters; ++e) sum += s_cnt[lane * iters + e];
+      int incl = sum;
 #pragma unroll
       for (int off = 1; off < 32; off <<= 1) {
         const int t = __shfl_up_sync(0xffffffffu, incl, off);
         if (lane >= off) incl += t;
       }
-      s_scan[lane] = incl - v;  // exclusive prefix of the warp totals
-      if (lane == 31) s_red[0] = __int_as_float(incl);
+      int run = incl - sum;
+      for (int e = 0; e < iters; ++e) {
+        const int c = s_cnt[lane * iters + e];
+        s_cnt[lane * iters + e] = run;
+        run += c;
+      }
+      if (lane == 31) s_k = incl;
     }
     __syncthreads();
-    const int k0 = s_k;
-    if (pass) {
-      const int pos = k0 + s_scan[wid] + __popc(ballot & ((1u << lane) - 1));
-      keys[pos] = (static_cast<unsigned long long>(score_desc_bits(L.conf[row])) << 32) | static_cast<unsigned int>(row);
+#pragma unroll
+    for (int it = 0; it < kCompactIters; ++it) {
+      if ((bal[it] >> lane) & 1u) {
+        const int row = it * kSelThreads + tid;
+        const int pos = s_cnt[it * (kSelThreads / 32) + wid] + __popc(bal[it] & ((1u << lane) - 1));
+        keys[pos] = (static_cast<unsigned long long>(score_desc_bits(cv[it])) << 32) | static_cast<unsigned int>(row);
+      }
     }
     __syncthreads();
-    if (tid == 0) s_k = k0 + __float_as_int(s_red[0]);
+  } else {
+    if (tid == 0) s_k = 0;
     __syncthreads();
+    for (int base = 0; base < rows; base += kSelThreads) {
+      const int row = base + tid;
+      const bool pass = row < rows && (L.conf[row] >= conf_thresh);
+      const unsigned int ballot = __ballot_sync(0xffffffffu, pass);
+      if (lane == 0) s_scan[wid] = __popc(ballot);
+      __syncthreads();
+      if (wid == 0) {
+        int v = s_scan[lane];
+        int incl = v;
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+          const int t = __shfl_up_sync(0xffffffffu, incl, off);
+          if (lane >= off) incl += t;
+        }
+        s_scan[lane] = incl - v;  // exclusive prefix of the warp totals
+        if (lane == 31) s_red[0] = __int_as_float(incl);
+      }
+      __syncthreads();
+      const int k0 = s_k;
+      if (pass) {
+        const int pos = k0 + s_scan[wid] + __popc(ballot & ((1u << lane) - 1));
+        keys[pos] = (static_cast<unsigned long long>(score_desc_bits(L.conf[row])) << 32) | static_cast<unsigned int>(row);
+      }
+      __syncthreads();
+      if (tid == 0) s_k = k0 + __float_as_int(s_red[0]);
+      __syncthreads();
+    }
   }
   const int k = s_k;
   if (k == 0) {
@@ -225,6 +264,10 @@ nms_select_kernel(const float* __restrict__ pred, int rows, int nc, float conf_t
     __syncthreads();
   }
   const float span = trick ? __fadd_rn(s_maxc, 1.f) : 0.f;  // max_coordinate + 1
+  const bool in_smem = k <= kSmemBoxes;
+  float* sbox = in_smem ? sm_box : L.sbox;
+  float* sarea = in_smem ? sm_area : L.sarea;
+  int* scls = in_smem ? sm_cls : L.scls;
   for (int i = tid; i < k; i += kSelThreads) {
     const int row = static_cast<int>(keys[i] & 0xffffffffu);
     float4 b = *reinterpret_cast<const float4*>(L.box + row * 4);
@@ -236,37 +279,81 @@ nms_select_kernel(const float* __restrict__ pred, int rows, int nc, float conf_t
       b.z = __fadd_rn(b.z, off);
       b.w = __fadd_rn(b.w, off);
     }
-    *reinterpret_cast<float4*>(L.sbox + i * 4) = b;
-    L.sarea[i] = __fmul_rn(__fsub_rn(b.z, b.x), __fsub_rn(b.w, b.y));
-    L.scls[i] = cls;
+    *reinterpret_cast<float4*>(sbox + i * 4) = b;
+    sarea[i] = __fmul_rn(__fsub_rn(b.z, b.x), __fsub_rn(b.w, b.y));
+    scls[i] = cls;
     supp[i] = 0;
   }
   __syncthreads();
 
   // ---- 4. greedy suppression in score order
   int kept = 0;
-  for (int i = 0; i < k; ++i) {
-    if (supp[i]) continue;  // block-uniform
-    if (tid == 0) s_keep[kept] = i;
-    ++kept;
-    if (kept == max_det) break;
-    const float4 bi = *reinterpret_cast<const float4*>(L.sbox + i * 4);
-    const float ai = L.sarea[i];
-    const int ci = L.scls[i];
-    for (int j = i + 1 + tid; j < k; j += kSelThreads) {
-      if (supp[j]) continue;
-      if (!trick && L.scls[j] != ci) continue;
-      const float4 bj = *reinterpret_cast<const float4*>(L.sbox + j * 4);
-      const float xx1 = fmaxf(bi.x, bj.x), yy1 = fmaxf(bi.y, bj.y);
-      const float xx2 = fminf(bi.z, bj.z), yy2 = fminf(bi.w, bj.w);
-      const float w = fmaxf(0.f, __fsub_rn(xx2, xx1)), h = fmaxf(0.f, __fsub_rn(yy2, yy1));
-      const float inter = __fmul_rn(w, h);
-      const float ovr = __fdiv_rn(inter, __fsub_rn(__fadd_rn(ai, L.sarea[j]), inter));
-      if (static_cast<double>(ovr) > nms_thresh) supp[j] = 1;
+  if (k <= kMatrixK) {
+    // 4a. suppression matrix: one warp per (box i, 32-candidate word), lanes = candidates, ballot = the word.
+    // Bit j of row i says "i suppresses j" (j > i).  All pairs are independent, so 32 warps stay busy; the greedy
+    // loop with one block barrier per survivor cost ~930 clocks per survivor (105 k clocks for k = 200).
+    const int W = (k + 31) >> 5;
+    for (int t = wid; t < k * W; t += kSelThreads / 32) {
+      const int i = t / W, w = t - i * W;
+      const int j = w * 32 + lane;
+      bool hit = false;
+      if (w >= (i >> 5) && j > i && j < k && (trick || scls[j] == scls[i])) {
+        const float4 bi = *reinterpret_cast<const float4*>(sbox + i * 4);
+        const float4 bj = *reinterpret_cast<const float4*>(sbox + j * 4);
+        const float xx1 = fmaxf(bi.x, bj.x), yy1 = fmaxf(bi.y, bj.y);
+        const float xx2 = fminf(bi.z, bj.z), yy2 = fminf(bi.w, bj.w);
+        const float bw = fmaxf(0.f, __fsub_rn(xx2, xx1)), bh = fmaxf(0.f, __fsub_rn(yy2, yy1));
+        const float inter = __fmul_rn(bw, bh);
+        const float ovr = __fdiv_rn(inter, __fsub_rn(__fadd_rn(sarea[i], sarea[j]), inter));
+        hit = ovr > nms_thresh_f;
+      }
+      const unsigned int word = __ballot_sync(0xffffffffu, hit);
+      if (lane == 0) sm_mask[t] = word;
+    }
+    __syncthreads();
+    // 4b. one warp walks the candidates in score order; lane w carries word w of the "removed" set and the
+    // next row of the matrix is fetched while the current candidate is examined
+    if (wid == 0) {
+      unsigned int removed = 0;
+      unsigned int next_row = lane < W ? sm_mask[lane] : 0u;
+      for (int i = 0; i < k; ++i) {
+        const unsigned int row_i = next_row;
+        if (i + 1 < k) next_row = lane < W ? sm_mask[(i + 1) * W + lane] : 0u;
+        const unsigned int word = __shfl_sync(0xffffffffu, removed, i >> 5);
+        if ((word >> (i & 31)) & 1u) continue;
+        if (lane == 0) s_keep[kept] = i;
+        ++kept;
+        if (kept == max_det) break;
+        removed |= row_i;
+      }
+      if (lane == 0) s_k = kept;
+    }
+    __syncthreads();
+    kept = s_k;
+  } else {
+    for (int i = 0; i < k; ++i) {
+      if (supp[i]) continue;  // block-uniform
+      if (tid == 0) s_keep[kept] = i;
+      ++kept;
+      if (kept == max_det) break;
+      const float4 bi = *reinterpret_cast<const float4*>(sbox + i * 4);
+      const float ai = sarea[i];
+      const int ci = scls[i];
+      for (int j = i + 1 + tid; j < k; j += kSelThreads) {
+        if (supp[j]) continue;
+        if (!trick && scls[j] != ci) continue;
+        const float4 bj = *reinterpret_cast<const float4*>(sbox + j * 4);
+        const float xx1 = fmaxf(bi.x, bj.x), yy1 = fmaxf(bi.y, bj.y);
+        const float xx2 = fminf(bi.z, bj.z), yy2 = fminf(bi.w, bj.w);
+        const float w = fmaxf(0.f, __fsub_rn(xx2, xx1)), h = fmaxf(0.f, __fsub_rn(yy2, yy1));
+        const float inter = __fmul_rn(w, h);
+        const float ovr = __fdiv_rn(inter, __fsub_rn(__fadd_rn(ai, sarea[j]), inter));
+        if (ovr > nms_thresh_f) supp[j] = 1;
+      }
+      __syncthreads();
     }
     __syncthreads();
   }
-  __syncthreads();
 
   // ---- 5. gather survivors: [x1,y1,x2,y2,conf,class_conf,class_pred,cls...]
   if (tid == 0) det_count[img] = kept;
@@ -307,21 +394,24 @@ int me_filter_nms(float* pred, int n, int rows, int num_classes, float conf_thre
   ME_REQUIRE(max_det >= 1 && max_det <= 256, "filter_nms: max_det %d out of range (1..256)", max_det);
   ME_REQUIRE(rows <= (1 << 20), "filter_nms: too many rows");
   ME_REQUIRE(workspace_bytes >= me_filter_nms_workspace(n, rows, num_classes), "filter_nms: workspace too small");
-  const long long warps = 1LL * n * rows;
-  long long blocks = (warps * 32 + 255) / 256;
+  long long blocks = (1LL * n * rows + 255) / 256;
   if (blocks > 148 * 32) blocks = 148 * 32;
   nms_prepare_kernel<<<static_cast<int>(blocks), 256, 0, stream>>>(pred, n, rows, num_classes, conf_thresh,
                                                                    xyxy_inplace, workspace);
   ME_LAUNCH_CHECK();
   const int pow2 = next_pow2(rows);
-  const size_t smem = (pow2 <= kMaxSmemKeys ? static_cast<size_t>(pow2) * 8 : 0) + static_cast<size_t>(rows) + 16;
+  const size_t smem = (pow2 <= kMaxSmemKeys ? static_cast<size_t>(pow2) * 8 : 0) + static_cast<size_t>(rows) + 32 +
+                      static_cast<size_t>(kSmemBoxes) * 24 + static_cast<size_t>(kMatrixK) * (kMatrixK / 32) * 4;
+  // (double)ovr > nms_thresh for a float ovr  <=>  ovr > the largest float that is <= nms_thresh
+  float thresh_f = static_cast<float>(nms_thresh);
+  if (static_cast<double>(thresh_f) > nms_thresh) thresh_f = nextafterf(thresh_f, -INFINITY);
   static bool attr_set = false;
   if (!attr_set) {
-    ME_CUDA(cudaFuncSetAttribute(nms_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    ME_CUDA(cudaFuncSetAttribute(nms_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
     attr_set = true;
   }
-  ME_REQUIRE(smem <= 200 * 1024, "filter_nms: %d rows need %zu B of shared memory", rows, smem);
-  nms_select_kernel<<<n, kSelThreads, smem, stream>>>(pred, rows, num_classes, conf_thresh, nms_thresh, max_det, det,
+  ME_REQUIRE(smem <= 220 * 1024, "filter_nms: %d rows need %zu B of shared memory", rows, smem);
+  nms_select_kernel<<<n, kSelThreads, smem, stream>>>(pred, rows, num_classes, conf_thresh, thresh_f, max_det, det,
                                                       det_count, det_index, workspace);
   ME_LAUNCH_CHECK();
   return ME_OK;

@@ -6,6 +6,8 @@ and shortcut are resolved at plan time into channel slices and a fused residual 
 kernels left are conv GEMMs, the 3-channel first conv, max-pool, upsample and the YOLO decode -
 and the launch sequence is captured in a CUDA graph that later forwards replay.
 """
+import gc
+
 import torch
 
 from . import ops
@@ -66,6 +68,23 @@ def describe_blocks(module_defs):
         blocks.append(b)
         chans.append(out_c)
     return hyper, blocks
+
+
+def capture_graph(fn):
+    """Captures fn() into a CUDA graph with the cyclic garbage collector paused.  A collection that runs in the
+    middle of a capture can finalise an older plan's CUDAGraph (plans sit in reference cycles with their modules);
+    cudaGraphExecDestroy is not permitted while a stream is capturing and invalidates the capture in progress."""
+    g = torch.cuda.CUDAGraph()
+    gc.collect()
+    was_enabled = gc.isenabled()
+    gc.disable()
+    try:
+        with torch.cuda.graph(g, capture_error_mode="thread_local"):
+            fn()
+    finally:
+        if was_enabled:
+            gc.enable()
+    return g
 
 
 class DarknetPlan:
@@ -316,10 +335,7 @@ class DarknetPlan:
             if self._graphs[self._slot] is None:
                 self.enqueue_split()  # warm-up: lazy one-time initialisation inside the library
                 torch.cuda.synchronize(self.device)
-                g = torch.cuda.CUDAGraph()
-                with torch.cuda.graph(g):
-                    self.enqueue_split()
-                self._graphs[self._slot] = g
+                self._graphs[self._slot] = capture_graph(self.enqueue_split)
             self.graph = self._graphs[self._slot]
             self.graph.replay()
         ev = self._slot_free[self._slot]
