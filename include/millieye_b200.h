@@ -44,6 +44,10 @@ int me_last_error(char* buf, size_t n);
 int me_device_info(int* sm_count, int* cc_major, int* cc_minor);
 /* Debug word written by a kernel whose pipeline wait timed out (0 = never). */
 int me_debug_status(unsigned long long* host_word);
+/* Profiling aid (tools/conv_trace.py): while dev_words != NULL every me_conv_gemm launch writes 16
+ * clock64 words per CTA (phase time stamps and barrier-wait totals) to dev_words[16 * blockIdx.x ...];
+ * NULL switches it off.  Not part of the reference's interface. */
+int me_conv_set_trace(unsigned long long* dev_words);
 
 /* ---- conv + BN + activation (A2/A8/A9 of SURVEY §8a) ------------------------------ */
 /* K-block (channels per pipeline stage) the GEMM uses for `cin` input channels; the packed

@@ -46,6 +46,7 @@ SIGNATURES = {
     "me_last_error": (c_int, [c_char_p, c_size_t]),
     "me_device_info": (c_int, [POINTER(c_int), POINTER(c_int), POINTER(c_int)]),
     "me_debug_status": (c_int, [POINTER(c_ulonglong)]),
+    "me_conv_set_trace": (c_int, [c_void_p]),
     "me_conv_k_block": (c_int, [c_int]),
     "me_conv_cin_pad": (c_int, [c_int]),
     "me_pack_conv_weights": (c_int, [c_void_p] * 6 + [c_float, c_int, c_int, c_int, c_int, c_void_p, c_void_p,

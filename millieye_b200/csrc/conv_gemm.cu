@@ -27,9 +27,8 @@ int conv_gemm_pair(int bn, const me_conv_desc* d, const void* x, const void* w, 
 namespace {
 
 constexpr int kBM = 128;
-constexpr int kThreads = 192;
-constexpr int kEpiThreads = 128;
-constexpr uint32_t kEpiBarrierId = 1;
+constexpr int kEpiThreads = 128;        // one epilogue group = 4 warps = the four TMEM lane quarters
+constexpr uint32_t kEpiBarrierId = 1;   // named barrier of group g is kEpiBarrierId + g
 constexpr int kMaxStages = 8;
 
 struct ConvParams {
@@ -45,10 +44,23 @@ struct ConvParams {
   int stages;
   int bres_bytes;  // weight-stationary mode: bytes of the resident weight slab (num_kb * B_BYTES)
   int kps;         // K blocks per pipeline stage (one mbarrier round trip)
-  int dbg;         // ME_CONV_DBG attribution mask: 1 skip epilogue, 2 skip operand loads, 4 skip MMAs
+  int dbg;         // ME_CONV_DBG attribution mask: 1 skip epilogue, 2 skip operand loads, 4 skip MMAs, 16 no stage commits
   const float* bias;
   unsigned long long* debug;  // host-mapped word, written before a watchdog trap
+  unsigned long long* trace;  // me_conv_set_trace: 16 clock64 words per CTA (tools/conv_trace.py), else nullptr
 };
+
+// Timed wait for the trace mode: adds the cycles spent in the wait to *acc.
+#define ME_TRACED_WAIT(acc, ...)            \
+  do {                                      \
+    if (p.trace) {                          \
+      const long long t_ = clock64();       \
+      mbar_wait(__VA_ARGS__);               \
+      (acc) += clock64() - t_;              \
+    } else {                                \
+      mbar_wait(__VA_ARGS__);               \
+    }                                       \
+  } while (0)
 
 // Tile order of one persistent CTA.  Default: tile = blockIdx.x + i * gridDim.x over the (m, n) tile grid,
 // n fastest, so the CTAs that share an A tile run together.  Weight-stationary: the CTA keeps ONE n tile
@@ -81,7 +93,7 @@ struct TileWalk {
   }
 };
 
-template <int BN, int BK, bool OUT_F32>
+template <int BN, int BK, bool OUT_F32, int EG_>
 struct Cfg {
   static constexpr int A_BYTES = kBM * BK * 2;
   static constexpr int B_BYTES = BN * BK * 2;
@@ -91,11 +103,18 @@ struct Cfg {
   static constexpr int SUB_COLS = SUB_ROW_BYTES / ESIZE;
   static constexpr int NUM_SUB = BN / SUB_COLS;
   static constexpr int SUB_BYTES = kBM * SUB_ROW_BYTES;
-  static constexpr int STAGING_BYTES = NUM_SUB * SUB_BYTES;
+  static constexpr int STAGING_BYTES = NUM_SUB * SUB_BYTES;  // per epilogue group
+  // Two epilogue groups alternate tiles (group g owns TMEM accumulator g and its own staging tile): on the
+  // thin layers one group's tcgen05.ld -> math -> st.shared -> TMA store chain (plus the residual load) took
+  // longer than the tile's MMAs, so the tensor pipe idled on tmem_empty (tools/conv_trace.py, profiles/round1).
+  // A second staging tile costs pipeline stages, so the dispatcher (me_conv_gemm) picks EG per layer.
+  static constexpr int EG = EG_;
+  static_assert(EG == 1 || EG == 2, "epilogue groups");
+  static constexpr int THREADS = 64 + EG * kEpiThreads;
   static constexpr int SWZ_BITS = (SUB_ROW_BYTES == 128) ? 3 : (SUB_ROW_BYTES == 64) ? 2 : 1;
   static constexpr int TMEM_COLS = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
-  static constexpr int TAIL_BYTES = BN * 4 + 64 * 8 + 16;  // bias + barriers + tmem ptr
-  static constexpr int smem_bytes(int stages) { return 1024 + stages * STAGE_BYTES + STAGING_BYTES + TAIL_BYTES; }
+  static constexpr int TAIL_BYTES = EG * BN * 4 + 64 * 8 + 16;  // bias (per group) + barriers + tmem ptr
+  static constexpr int EPI_BYTES = EG * STAGING_BYTES + TAIL_BYTES;
   static_assert(BN % 32 == 0 && BN <= 256, "BN");
   static_assert(BK == 16 || BK == 32 || BK == 64, "BK");
   static_assert(A_BYTES % 1024 == 0 && B_BYTES % 1024 == 0, "tiles must keep 1024B alignment");
@@ -126,30 +145,32 @@ __device__ __forceinline__ float apply_act(float v, int act) {
 // WS (weight stationary): the layer's whole weight slab for this CTA's n tile (num_kb x BN x BK) is loaded
 // into shared memory once and the pipeline stages carry A only.  For the thin-channel layers (32..128
 // channels, 208^2..52^2 pixels) re-fetching the weights with every tile doubled the L2 -> SM traffic.
-template <int BN, int BK, bool OUT_F32, bool WS>
-__global__ void __launch_bounds__(kThreads, 1)
+template <int BN, int BK, bool OUT_F32, bool WS, int EG>
+__global__ void __launch_bounds__((Cfg<BN, BK, OUT_F32, EG>::THREADS), 1)
 conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                  const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmR,
                  const ConvParams p) {
-  using C = Cfg<BN, BK, OUT_F32>;
+  using C = Cfg<BN, BK, OUT_F32, EG>;
   constexpr int STAGE = WS ? C::A_BYTES : C::STAGE_BYTES;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* bres = smem;  // WS only
   uint8_t* stage_base = smem + (WS ? p.bres_bytes : 0);
   uint8_t* staging = stage_base + p.stages * p.kps * STAGE;
-  float* s_bias = reinterpret_cast<float*>(staging + C::STAGING_BYTES);
-  uint64_t* bars = reinterpret_cast<uint64_t*>(s_bias + BN);
+  float* s_bias = reinterpret_cast<float*>(staging + C::EG * C::STAGING_BYTES);  // [EG][BN]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_bias + C::EG * BN);
   uint64_t* full_bar = bars;                     // [kMaxStages]
   uint64_t* empty_bar = bars + kMaxStages;       // [kMaxStages]
   uint64_t* tmem_full = bars + 2 * kMaxStages;   // [2]
   uint64_t* tmem_empty = tmem_full + 2;          // [2]
-  uint64_t* res_full = tmem_empty + 2;           // [1]
-  uint64_t* b_full = res_full + 1;               // [1] WS: resident weights landed
+  uint64_t* res_full = tmem_empty + 2;           // [2] one per epilogue group
+  uint64_t* b_full = res_full + 2;               // [1] WS: resident weights landed
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(b_full + 1);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  unsigned long long* tr = p.trace ? p.trace + 16ull * blockIdx.x : nullptr;
+  if (tr && threadIdx.x == 0) tr[0] = clock64();
 
   // PDL: let the next layer's CTAs get scheduled as ours retire; everything up to pdl_wait() below touches
   // only our own smem / TMEM / kernel parameters, so it overlaps the previous layer's tail.
@@ -170,7 +191,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         ptx::mbar_init(&tmem_full[a], 1);
         ptx::mbar_init(&tmem_empty[a], 4);  // one arrive per epilogue warp
       }
-      ptx::mbar_init(res_full, 1);
+      ptx::mbar_init(&res_full[0], 1);
+      ptx::mbar_init(&res_full[1], 1);
       ptx::mbar_init(b_full, 1);
       ptx::fence_mbar_init();
     }
@@ -182,12 +204,15 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
+  if (tr && threadIdx.x == 0) tr[1] = clock64();
   ptx::pdl_wait();  // inputs written by the previous kernel are complete and visible from here on
+  if (tr && threadIdx.x == 0) tr[2] = clock64();
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer
     if (ptx::elect_one()) {
       uint32_t stage = 0, phase = 0;
+      long long w_empty = 0;
       TileWalk<WS> tw(p.tiles_m, p.tiles_n);
       if (WS && tw.valid()) {
         ptx::mbar_arrive_expect_tx(b_full, p.bres_bytes);
@@ -207,8 +232,9 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         // One barrier round trip (wait empty -> expect_tx -> loads) covers p.kps consecutive K blocks: a thin
         // layer's K block is only a few dozen MMA clocks, far less than the ~300 clocks a round trip costs.
         for (int kb0 = 0; kb0 < p.num_kb; kb0 += p.kps) {
-          mbar_wait(&empty_bar[stage], phase ^ 1, p.debug, 0x100u + stage);
-          if (p.dbg & 2) {  // attribution run: no operand traffic, barrier protocol intact
+          if (!(p.dbg & 16)) ME_TRACED_WAIT(w_empty, &empty_bar[stage], phase ^ 1, p.debug, 0x100u + stage);
+          if (p.dbg & 16) {  // attribution run: no stage barriers at all (with bit 2)
+          } else if (p.dbg & 2) {  // attribution run: no operand traffic, barrier protocol intact
             ptx::mbar_arrive(&full_bar[stage]);
           } else {
             ptx::mbar_arrive_expect_tx(&full_bar[stage], p.kps * STAGE);
@@ -230,6 +256,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           if (++stage == (uint32_t)p.stages) { stage = 0; phase ^= 1; }
         }
       }
+      if (tr) { tr[3] = w_empty; tr[4] = clock64(); }
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------------ MMA issuer
@@ -237,16 +264,18 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       constexpr uint32_t idesc = ptx::make_idesc_f16(kBM, BN);
       uint32_t stage = 0, phase = 0;
       int it = 0;
+      long long w_full = 0, w_acc = 0, t_first = 0;
       TileWalk<WS> tw(p.tiles_m, p.tiles_n);
       if (WS && tw.valid()) mbar_wait(b_full, 0, p.debug, 0x600u);
       for (; tw.valid(); tw.next(), ++it) {
         const int acc = it & 1;
         const uint32_t acc_phase = (it >> 1) & 1;
-        mbar_wait(&tmem_empty[acc], acc_phase ^ 1, p.debug, 0x200u + acc);
+        ME_TRACED_WAIT(w_acc, &tmem_empty[acc], acc_phase ^ 1, p.debug, 0x200u + acc);
         ptx::tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * BN;
         for (int kb0 = 0; kb0 < p.num_kb; kb0 += p.kps) {
-          mbar_wait(&full_bar[stage], phase, p.debug, 0x300u + stage);
+          if (!(p.dbg & 16)) ME_TRACED_WAIT(w_full, &full_bar[stage], phase, p.debug, 0x300u + stage);
+          if (tr && t_first == 0) { t_first = clock64(); w_full = 0; }
           ptx::tc_fence_after();
           for (int j = 0; j < p.kps; ++j) {
             const int kb = kb0 + j;
@@ -260,82 +289,119 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
               ptx::umma_f16_ss(d_tmem, adesc, bdesc, idesc, (kb | k) != 0 ? 1u : 0u);
             }
           }
-          ptx::umma_commit(&empty_bar[stage]);  // frees the smem stage when these MMAs retire
+          // (attribution bit 16, with bit 2: no per-stage commit and the producer does not wait for one)
+          if (!(p.dbg & 16)) ptx::umma_commit(&empty_bar[stage]);  // frees the smem stage when these MMAs retire
           if (++stage == (uint32_t)p.stages) { stage = 0; phase ^= 1; }
         }
         ptx::umma_commit(&tmem_full[acc]);  // accumulator complete -> epilogue
       }
+      if (tr) { tr[5] = w_full; tr[6] = w_acc; tr[7] = t_first; tr[8] = clock64(); tr[14] = it; }
     }
   } else {
-    // ------------------------------------------------------------------ epilogue (warps 2..5)
-    const int q = warp & 3;            // TMEM lane quarter this warp may read
-    const int row = q * 32 + lane;     // tile row == TMEM lane
-    const int etid = threadIdx.x - 64;  // 0..127
-    const bool leader = (threadIdx.x == 64);
-    int it = 0;
-    for (TileWalk<WS> tw(p.tiles_m, p.tiles_n); tw.valid(); tw.next(), ++it) {
-      const int m0 = tw.tm * kBM, n0 = tw.tn * BN;
-      const int acc = it & 1;
-      const uint32_t acc_phase = (it >> 1) & 1;
-      if (leader) {
-        ptx::tma_store_wait_read0();  // previous tile's store has drained the staging tile
-        if (p.has_res) {
-          ptx::mbar_arrive_expect_tx(res_full, C::STAGING_BYTES);
+    // ------------------------------------------------------------------ epilogue (warps 2..5 [, 6..9])
+    const int g = (C::EG == 2) ? ((warp - 2) >> 2) : 0;  // epilogue group
+    const int q = warp & 3;                              // TMEM lane quarter this warp may read
+    const int row = q * 32 + lane;                       // tile row == TMEM lane
+    const int etid = (threadIdx.x - 64) & (kEpiThreads - 1);
+    const bool leader = (etid == 0);
+    const bool tleader = leader && g == 0;               // trace words come from group 0
+    uint8_t* stg = staging + g * C::STAGING_BYTES;
+    float* bias_s = s_bias + g * BN;
+    uint64_t* res_bar = &res_full[g];
+    const uint32_t bar_id = kEpiBarrierId + g;
+    long long w_tfull = 0, w_other = 0, t_work = 0, t_first_full = 0;
+    TileWalk<WS> tw(p.tiles_m, p.tiles_n);
+    if (C::EG == 2 && g == 1) tw.next();
+    // The residual tile is TMA-loaded into the staging tile the result will overwrite.  The load for a group's
+    // NEXT tile is issued right after the store of the current one has drained the staging tile, a whole tile
+    // period before it is needed.
+    auto load_residual = [&](const TileWalk<WS>& t) {
+      ptx::mbar_arrive_expect_tx(res_bar, C::STAGING_BYTES);
 #pragma unroll
-          for (int sub = 0; sub < C::NUM_SUB; ++sub)
-            ptx::tma_load_2d(&tmR, res_full, staging + sub * C::SUB_BYTES, n0 + sub * C::SUB_COLS, m0);
-        }
-      }
-      for (int i = etid; i < BN; i += kEpiThreads) s_bias[i] = p.bias[n0 + i];
-      ptx::named_bar_sync(kEpiBarrierId, kEpiThreads);
+      for (int sub = 0; sub < C::NUM_SUB; ++sub)
+        ptx::tma_load_2d(&tmR, res_bar, stg + sub * C::SUB_BYTES, t.tn * BN + sub * C::SUB_COLS, t.tm * kBM);
+    };
+    if (p.has_res && leader && tw.valid()) load_residual(tw);
+    for (int lit = 0; tw.valid(); ++lit) {
+      const int m0 = tw.tm * kBM, n0 = tw.tn * BN;
+      const int acc = (C::EG == 2) ? g : (lit & 1);
+      const uint32_t acc_phase = (C::EG == 2) ? (lit & 1) : ((lit >> 1) & 1);
+      const long long te0 = (tr && tleader) ? clock64() : 0;
+      if (leader && !p.has_res) ptx::tma_store_wait_read0();  // previous store has drained the staging tile
+      for (int i = etid; i < BN; i += kEpiThreads) bias_s[i] = p.bias[n0 + i];
+      ptx::named_bar_sync(bar_id, kEpiThreads);
+      const long long te1 = (tr && tleader) ? clock64() : 0;
       mbar_wait(&tmem_full[acc], acc_phase, p.debug, 0x400u + acc);
       ptx::tc_fence_after();
-      if (p.has_res) mbar_wait(res_full, it & 1, p.debug, 0x500u);
+      const long long te2 = (tr && tleader) ? clock64() : 0;
+      if (p.has_res) mbar_wait(res_bar, lit & 1, p.debug, 0x500u + g);
+      const long long te3 = (tr && tleader) ? clock64() : 0;
+      if (tr && tleader) {
+        w_other += (te1 - te0) + (te3 - te2);
+        w_tfull += te2 - te1;
+        if (lit == 0) t_first_full = te2;
+      }
 
       const uint32_t t_row = tmem_base + acc * BN + (static_cast<uint32_t>(q * 32) << 16);
-#pragma unroll 1
-      for (int c = 0; c < BN; c += 32) {
-        uint32_t r[32];
-        if (p.dbg & 1) break;  // attribution run: accumulators released unread
-        ptx::tmem_ld_32x32b_x32(t_row + c, r);
-        ptx::tmem_ld_wait();
-        float v[32];
+      if (!(p.dbg & 1)) {  // attribution run: accumulators released unread
+        constexpr int NCH = BN / 32;
+        uint32_t r[2][32];
+        ptx::tmem_ld_32x32b_x32(t_row, r[0]);
 #pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = apply_act(__uint_as_float(r[j]) + s_bias[c + j], p.act);
-        if constexpr (OUT_F32) {
-          // 32 fp32 columns = one 128B staging row of sub-tile c/32
-          uint8_t* sub = staging + (c / C::SUB_COLS) * C::SUB_BYTES;
-          const uint32_t rbase = row * C::SUB_ROW_BYTES + (c % C::SUB_COLS) * 4;
+        for (int ci = 0; ci < NCH; ++ci) {
+          const int c = ci * 32;
+          ptx::tmem_ld_wait_regs(r[ci & 1]);
+          if (ci + 1 < NCH) ptx::tmem_ld_32x32b_x32(t_row + c + 32, r[(ci + 1) & 1]);  // in flight during the math
+          float v[32];
 #pragma unroll
-          for (int j = 0; j < 8; ++j) {
-            uint32_t off = rbase + j * 16;
-            off ^= ((off >> 7) & ((1u << C::SWZ_BITS) - 1)) << 4;
-            *reinterpret_cast<float4*>(sub + off) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+          for (int j4 = 0; j4 < 8; ++j4) {
+            const float4 b4 = *reinterpret_cast<const float4*>(bias_s + c + 4 * j4);
+            v[4 * j4 + 0] = __uint_as_float(r[ci & 1][4 * j4 + 0]) + b4.x;
+            v[4 * j4 + 1] = __uint_as_float(r[ci & 1][4 * j4 + 1]) + b4.y;
+            v[4 * j4 + 2] = __uint_as_float(r[ci & 1][4 * j4 + 2]) + b4.z;
+            v[4 * j4 + 3] = __uint_as_float(r[ci & 1][4 * j4 + 3]) + b4.w;
           }
-        } else {
-          uint8_t* sub = staging + (c / C::SUB_COLS) * C::SUB_BYTES;
-          const uint32_t rbase = row * C::SUB_ROW_BYTES + (c % C::SUB_COLS) * 2;
+          if (p.act == ME_ACT_LEAKY) {
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            uint32_t off = rbase + j * 16;
-            off ^= ((off >> 7) & ((1u << C::SWZ_BITS) - 1)) << 4;
-            uint4* dst = reinterpret_cast<uint4*>(sub + off);
-            float* vv = v + 8 * j;
-            if (p.has_res) {
-              const uint4 rr = *dst;
-              const __half2* rh = reinterpret_cast<const __half2*>(&rr);
+            for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.1f * v[j]);  // == v > 0 ? v : 0.1 v
+          } else if (p.act == ME_ACT_SIGMOID) {
 #pragma unroll
-              for (int e = 0; e < 4; ++e) {
-                const float2 f = __half22float2(rh[e]);
-                vv[2 * e] += f.x;
-                vv[2 * e + 1] += f.y;
-              }
+            for (int j = 0; j < 32; ++j) v[j] = 1.f / (1.f + __expf(-v[j]));
+          }
+          uint8_t* sub = stg + (c / C::SUB_COLS) * C::SUB_BYTES;
+          if constexpr (OUT_F32) {
+            // 32 fp32 columns = one 128B staging row of sub-tile c/32
+            const uint32_t rbase = row * C::SUB_ROW_BYTES + (c % C::SUB_COLS) * 4;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              uint32_t off = rbase + j * 16;
+              off ^= ((off >> 7) & ((1u << C::SWZ_BITS) - 1)) << 4;
+              *reinterpret_cast<float4*>(sub + off) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
             }
-            uint4 o;
-            __half2* oh = reinterpret_cast<__half2*>(&o);
+          } else {
+            const uint32_t rbase = row * C::SUB_ROW_BYTES + (c % C::SUB_COLS) * 2;
 #pragma unroll
-            for (int e = 0; e < 4; ++e) oh[e] = __floats2half2_rn(vv[2 * e], vv[2 * e + 1]);
-            *dst = o;
+            for (int j = 0; j < 4; ++j) {
+              uint32_t off = rbase + j * 16;
+              off ^= ((off >> 7) & ((1u << C::SWZ_BITS) - 1)) << 4;
+              uint4* dst = reinterpret_cast<uint4*>(sub + off);
+              float* vv = v + 8 * j;
+              if (p.has_res) {
+                const uint4 rr = *dst;
+                const __half2* rh = reinterpret_cast<const __half2*>(&rr);
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                  const float2 f = __half22float2(rh[e]);
+                  vv[2 * e] += f.x;
+                  vv[2 * e + 1] += f.y;
+                }
+              }
+              uint4 o;
+              __half2* oh = reinterpret_cast<__half2*>(&o);
+#pragma unroll
+              for (int e = 0; e < 4; ++e) oh[e] = __floats2half2_rn(vv[2 * e], vv[2 * e + 1]);
+              *dst = o;
+            }
           }
         }
       }
@@ -343,20 +409,31 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(&tmem_empty[acc]);  // accumulator may be overwritten
       ptx::fence_proxy_async_smem();                       // staging writes -> visible to TMA
-      ptx::named_bar_sync(kEpiBarrierId, kEpiThreads);
-      if (leader && !(p.dbg & 1)) {
+      ptx::named_bar_sync(bar_id, kEpiThreads);
+      tw.next();
+      if (C::EG == 2) tw.next();
+      if (leader) {
+        if (!(p.dbg & 1)) {
 #pragma unroll
-        for (int sub = 0; sub < C::NUM_SUB; ++sub)
-          ptx::tma_store_2d(&tmC, staging + sub * C::SUB_BYTES, n0 + sub * C::SUB_COLS, m0);
-        ptx::tma_store_commit();
+          for (int sub = 0; sub < C::NUM_SUB; ++sub)
+            ptx::tma_store_2d(&tmC, stg + sub * C::SUB_BYTES, n0 + sub * C::SUB_COLS, m0);
+          ptx::tma_store_commit();
+        }
+        if (p.has_res && tw.valid()) {
+          ptx::tma_store_wait_read0();
+          load_residual(tw);
+        }
       }
+      if (tr && tleader) t_work += clock64() - te3;
     }
     if (leader) ptx::tma_store_wait_all0();
+    if (tr && tleader) { tr[9] = w_tfull; tr[10] = w_other; tr[11] = t_work; tr[12] = clock64(); tr[15] = t_first_full; }
   }
 
   ptx::tc_fence_before();
   __syncthreads();
   ptx::tc_fence_after();
+  if (tr && threadIdx.x == 0) tr[13] = clock64();
   if (warp == 1) ptx::tmem_dealloc(tmem_base, C::TMEM_COLS);
 }
 
@@ -397,6 +474,7 @@ bool conv_kps_enabled() {
 
 unsigned long long* g_debug_host = nullptr;
 unsigned long long* g_debug_dev = nullptr;
+unsigned long long* g_trace_dev = nullptr;  // me_conv_set_trace
 
 int ensure_debug_word() {
   if (g_debug_host) return ME_OK;
@@ -406,10 +484,10 @@ int ensure_debug_word() {
   return ME_OK;
 }
 
-template <int BN, int BK, bool OUT_F32, bool WS>
+template <int BN, int BK, bool OUT_F32, bool WS, int EG>
 int launch(const me_conv_desc* d, const void* x, const void* w, const float* bias, const void* residual, void* y,
            cudaStream_t stream) {
-  using C = Cfg<BN, BK, OUT_F32>;
+  using C = Cfg<BN, BK, OUT_F32, EG>;
   const int pad = (d->ksize - 1) / 2;
   const int Ho = (d->h + 2 * pad - d->ksize) / d->stride + 1;
   const int Wo = (d->w + 2 * pad - d->ksize) / d->stride + 1;
@@ -437,6 +515,7 @@ int launch(const me_conv_desc* d, const void* x, const void* w, const float* bia
   int rc = ensure_debug_word();
   if (rc != ME_OK) return rc;
   p.debug = g_debug_dev;
+  p.trace = g_trace_dev;
   {
     static int dbg = -1;
     if (dbg < 0) {
@@ -448,13 +527,13 @@ int launch(const me_conv_desc* d, const void* x, const void* w, const float* bia
 
   constexpr int STAGE = WS ? C::A_BYTES : C::STAGE_BYTES;
   p.bres_bytes = WS ? p.num_kb * C::B_BYTES : 0;
-  const int budget = 227 * 1024 - 1024 - C::STAGING_BYTES - C::TAIL_BYTES - p.bres_bytes;
+  const int budget = 227 * 1024 - 1024 - C::EPI_BYTES - p.bres_bytes;
   p.kps = choose_kps(d->ksize, p.kb_per_tap, p.num_kb, STAGE, budget);
   int stages = budget / (p.kps * STAGE);
   if (stages > kMaxStages) stages = kMaxStages;
   ME_REQUIRE(stages >= 2, "conv: not enough shared memory for a 2-stage pipeline");
   p.stages = stages;
-  const int smem = 1024 + p.bres_bytes + stages * p.kps * STAGE + C::STAGING_BYTES + C::TAIL_BYTES;
+  const int smem = 1024 + p.bres_bytes + stages * p.kps * STAGE + C::EPI_BYTES;
 
   CUtensorMap tmA, tmB, tmC, tmR;
   const CUtensorMapSwizzle swz_k = swizzle_for_row_bytes(BK * 2);
@@ -480,7 +559,7 @@ int launch(const me_conv_desc* d, const void* x, const void* w, const float* bia
     tmR = tmC;
   }
 
-  auto kern = conv_gemm_kernel<BN, BK, OUT_F32, WS>;
+  auto kern = conv_gemm_kernel<BN, BK, OUT_F32, WS, EG>;
   static bool attr_set = false;
   if (!attr_set) {
     ME_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
@@ -499,7 +578,7 @@ int launch(const me_conv_desc* d, const void* x, const void* w, const float* bia
   }
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = dim3(grid);
-  cfg.blockDim = dim3(kThreads);
+  cfg.blockDim = dim3(C::THREADS);
   cfg.dynamicSmemBytes = smem;
   cfg.stream = stream;
   cudaLaunchAttribute attr[1];
@@ -515,6 +594,7 @@ int launch(const me_conv_desc* d, const void* x, const void* w, const float* bia
 }  // namespace
 
 unsigned long long* conv_debug_word() { return g_debug_dev; }
+unsigned long long* conv_trace_buffer() { return g_trace_dev; }
 bool conv_pdl_enabled() { return pdl_enabled_impl(); }
 // ME_CONV_WS: 0 = never, 1 (default) = when profitable, 2 = whenever the slab fits (tests force it on small shapes)
 static int conv_ws_mode() {
@@ -527,6 +607,7 @@ static int conv_ws_mode() {
   return v;
 }
 static bool conv_ws_enabled() { return conv_ws_mode() != 0; }
+
 int conv_ensure_debug_word() { return ensure_debug_word(); }
 
 // 0 = automatic, 1 = single-CTA tiles only, 2 = CTA pairs with N=128, 3 = CTA pairs with N=256 (where legal)
@@ -550,6 +631,11 @@ extern "C" {
 
 int me_conv_k_block(int cin) { return cin > 32 ? 64 : (cin > 16 ? 32 : 16); }
 int me_conv_cin_pad(int cin) { return me::round_up(cin, me_conv_k_block(cin)); }
+
+int me_conv_set_trace(unsigned long long* dev_words) {
+  me::g_trace_dev = dev_words;
+  return ME_OK;
+}
 
 int me_debug_status(unsigned long long* host_word) {
   if (host_word) *host_word = me::g_debug_host ? *me::g_debug_host : 0ull;
@@ -578,12 +664,12 @@ int me_conv_gemm(const me_conv_desc* d, const void* x, const void* w_packed, con
   const int num_kb = d->ksize * d->ksize * (round_up(d->cin, bk) / bk);
   // Weight-stationary tiles: the n tile's whole weight slab stays in shared memory.  Used when it fits next to
   // >= 3 A stages and every CTA gets >= 4 m tiles to amortise the one-off load (ME_CONV_WS=0 disables).
-  auto ws_ok = [&](int bn) {
+  auto ws_ok = [&](int bn, int eg) {
     if (f32 || !conv_ws_enabled()) return false;
     const int tiles_n = ceil_div(cout, bn), tiles_m = static_cast<int>((m + kBM - 1) / kBM);
     const int sms = sm_count() > 0 ? sm_count() : 148;
     const int a_bytes = kBM * bk * 2, b_bytes = bn * bk * 2;
-    const int budget = 227 * 1024 - 1024 - kBM * bn * 2 - (bn * 4 + 64 * 8 + 16);
+    const int budget = 227 * 1024 - 1024 - eg * kBM * bn * 2 - (eg * bn * 4 + 64 * 8 + 16);  // Cfg::EPI_BYTES, fp16
     const int budget_ws = budget - num_kb * b_bytes;
     if (budget_ws < 3 * a_bytes || tiles_n > sms) return false;
     if (conv_ws_mode() == 2) return true;
@@ -594,10 +680,10 @@ int me_conv_gemm(const me_conv_desc* d, const void* x, const void* w_packed, con
     if (kps_ws < kps_plain || budget_ws / (kps_ws * a_bytes) < 3) return false;
     return tiles_n <= 4 && tiles_m >= 4 * (sms / tiles_n);
   };
-#define ME_GO(BN, BK, F32)                                                                        \
-  do {                                                                                            \
-    if (!F32 && ws_ok(BN)) return launch<BN, BK, false, true>(d, x, w_packed, bias, residual, y, stream); \
-    return launch<BN, BK, F32, false>(d, x, w_packed, bias, residual, y, stream);                 \
+#define ME_GO(BN, BK, F32, EG)                                                                            \
+  do {                                                                                                    \
+    if (!F32 && ws_ok(BN, EG)) return launch<BN, BK, false, true, EG>(d, x, w_packed, bias, residual, y, stream); \
+    return launch<BN, BK, F32, false, EG>(d, x, w_packed, bias, residual, y, stream);                     \
   } while (0)
   if (bk == 64 && !f32 && cout >= 128) {
     // CTA pairs (256 x BN tiles) halve the shared-memory bytes per flop; worth it once the layer has
@@ -606,28 +692,40 @@ int me_conv_gemm(const me_conv_desc* d, const void* x, const void* w_packed, con
     int pair_bn = 0;
     if (mode == 2) pair_bn = 128;
     else if (mode == 3) pair_bn = cout >= 256 ? 256 : 128;
-    // measured on B200 (profiles/round1): pairs win on 3x3 layers with >= 256 output channels and enough rows
-    // to fill 74 pairs more than twice; 1x1 layers and 128-channel layers are faster on single-CTA tiles.
-    else if (mode == 0 && d->ksize == 3 && cout >= 256 && m >= 16384) pair_bn = 256;
+    // measured on B200 (profiles/round1): pairs win on 3x3 layers with >= 256 output channels; 1x1 layers and
+    // 128-channel layers are faster on single-CTA tiles.  (13^2 x 32 frames = 5408 rows: pair256 52.7 us vs
+    // 57.2 us on single-CTA tiles, profiles/round1/attr_r1e.log)
+    else if (mode == 0 && d->ksize == 3 && cout >= 256 && m >= 4096) pair_bn = 256;
     if (pair_bn) return conv_gemm_pair(pair_bn, d, x, w_packed, bias, residual, y, stream);
   }
+  // Epilogue groups (see Cfg): two for the thin tiles (N <= 64), whose epilogue outlasts their MMAs, and for short-K
+  // 1x1 layers with N = 128 (52^2 256->128: -23 %); the 3x3 and long-K N = 128 layers keep one group because the
+  // second 32 KB staging tile would cost them the K-block grouping (26^2 512->256: +24 % with two groups).
+  // An SS-mode tcgen05.mma costs ~100-130 clocks whatever N <= 128 is (the A-operand fetch; tools/conv_trace.py,
+  // profiles/round1/attr_r1f.log), which is why the 3x3 layers with >= 256 output channels run as N = 256 pair tiles.
+  // Single-CTA 128 x 256 tiles for the 1x1 layers were measured and dropped (26^2 512->256: 23.5k vs 18k clocks,
+  // the 128 x 256 epilogue tail costs more than the faster main loop saves; profiles/round1/trace_r1g.txt).
+  const bool eg2_128 = d->ksize == 1 && num_kb <= 6;
   if (bk == 64) {
     if (f32) {
-      if (cout >= 128) ME_GO(128, 64, true);
-      if (cout >= 64) ME_GO(64, 64, true);
-      ME_GO(32, 64, true);
+      if (cout >= 128) ME_GO(128, 64, true, 1);
+      if (cout >= 64) ME_GO(64, 64, true, 2);
+      ME_GO(32, 64, true, 2);
     }
-    if (cout >= 128) ME_GO(128, 64, false);
-    if (cout >= 64) ME_GO(64, 64, false);
-    ME_GO(32, 64, false);
+    if (cout >= 128) {
+      if (eg2_128) ME_GO(128, 64, false, 2);
+      ME_GO(128, 64, false, 1);
+    }
+    if (cout >= 64) ME_GO(64, 64, false, 2);
+    ME_GO(32, 64, false, 2);
   } else if (bk == 32) {
     ME_REQUIRE(!f32, "conv: fp32 output needs cin > 32");
-    if (cout >= 64) ME_GO(64, 32, false);
-    ME_GO(32, 32, false);
+    if (cout >= 64) ME_GO(64, 32, false, 2);
+    ME_GO(32, 32, false, 2);
   } else {
     ME_REQUIRE(!f32, "conv: fp32 output needs cin > 32");
-    if (cout >= 64) ME_GO(64, 16, false);
-    ME_GO(32, 16, false);
+    if (cout >= 64) ME_GO(64, 16, false, 2);
+    ME_GO(32, 16, false, 2);
   }
 #undef ME_GO
   return ME_OK;

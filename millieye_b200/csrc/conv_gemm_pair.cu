@@ -12,8 +12,10 @@
 //            count lands on the LEADER CTA's full barrier (cp.async.bulk.tensor ... .cta_group::2).
 //   warp 1   leader only: waits the full barrier, issues tcgen05.mma.cta_group::2 (M=256, N=BN) and
 //            multicast-commits to the empty / tmem_full barriers of both CTAs.
-//   warps 2-5 epilogue over this CTA's 128 accumulator rows (own TMEM), same fused epilogue + TMA store;
-//            both CTAs release the accumulator on the leader's tmem_empty barrier (8 arrivals).
+//   warps 2-9 epilogue over this CTA's 128 accumulator rows (own TMEM): warps 2-5 take the tile's first BN/2
+//            columns, warps 6-9 the rest (the last tile's epilogue is exposed at the end of the kernel, so its
+//            latency matters); same fused epilogue + TMA store; both CTAs release the accumulator on the
+//            leader's tmem_empty barrier (16 arrivals).
 #include "common.cuh"
 #include "ptx.cuh"
 #include <cstdlib>
@@ -24,12 +26,13 @@ namespace me {
 unsigned long long* conv_debug_word();
 int conv_ensure_debug_word();
 bool conv_pdl_enabled();
+unsigned long long* conv_trace_buffer();
 
 namespace {
 
 constexpr int kBM = 128;       // rows per CTA (256 per pair)
-constexpr int kThreads = 192;
-constexpr int kEpiThreads = 128;
+constexpr int kThreads = 320;
+constexpr int kEpiThreads = 256;   // 8 epilogue warps: two per TMEM lane quarter, each takes half of the tile's columns
 constexpr uint32_t kEpiBarrierId = 1;
 constexpr int kMaxStages = 8;
 constexpr int kBK = 64;
@@ -48,7 +51,19 @@ struct PairParams {
   int dbg;  // ME_CONV_DBG bit mask for attribution runs: 1 skip epilogue, 2 skip operand loads, 4 skip MMAs
   const float* bias;
   unsigned long long* debug;
+  unsigned long long* trace;  // see conv_gemm.cu
 };
+
+#define ME_TRACED_WAIT(acc, ...)            \
+  do {                                      \
+    if (p.trace) {                          \
+      const long long t_ = clock64();       \
+      mbar_wait(__VA_ARGS__);               \
+      (acc) += clock64() - t_;              \
+    } else {                                \
+      mbar_wait(__VA_ARGS__);               \
+    }                                       \
+  } while (0)
 
 template <int BN>
 struct PCfg {
@@ -113,6 +128,8 @@ conv_gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
   const int pair = static_cast<int>(ptx::cluster_id_x());
   const int npairs = static_cast<int>(ptx::num_clusters_x());
   const int total_tiles = p.tiles_m * p.tiles_n;
+  unsigned long long* tr = p.trace ? p.trace + 16ull * blockIdx.x : nullptr;
+  if (tr && threadIdx.x == 0) tr[0] = clock64();
 
   ptx::pdl_launch_dependents();  // see conv_gemm.cu
   if (warp == 0 && ptx::elect_one()) {
@@ -129,7 +146,7 @@ conv_gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
       }
       for (int a = 0; a < 2; ++a) {
         ptx::mbar_init(&tmem_full[a], 1);
-        ptx::mbar_init(&tmem_empty[a], 8);  // 4 epilogue warps x 2 CTAs
+        ptx::mbar_init(&tmem_empty[a], 16);  // 8 epilogue warps x 2 CTAs
       }
       ptx::mbar_init(res_full, 1);
       ptx::fence_mbar_init();
@@ -145,12 +162,15 @@ conv_gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
+  if (tr && threadIdx.x == 0) tr[1] = clock64();
   ptx::pdl_wait();
+  if (tr && threadIdx.x == 0) tr[2] = clock64();
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer (both CTAs)
     if (ptx::elect_one()) {
       uint32_t stage = 0, phase = 0;
+      long long w_empty = 0;
       for (int tile = pair; tile < total_tiles; tile += npairs) {
         const int tm = tile / p.tiles_n, tn = tile - tm * p.tiles_n;
         int m0 = tm * 2 * kBM + static_cast<int>(rank) * kBM;         // this CTA's 128 rows
@@ -166,7 +186,7 @@ conv_gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
         }
         int tap = 0, cb = 0;
         for (int kb = 0; kb < p.num_kb; ++kb) {
-          mbar_wait(&empty_bar[stage], phase ^ 1, p.debug, 0x100u + stage);
+          ME_TRACED_WAIT(w_empty, &empty_bar[stage], phase ^ 1, p.debug, 0x100u + stage);
           uint8_t* sa = stage_base + stage * C::STAGE_BYTES;
           uint8_t* sb = sa + C::A_BYTES;
           const uint32_t full_leader = ptx::mapa(ptx::smem_u32(&full_bar[stage]), 0);
@@ -188,6 +208,7 @@ conv_gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
           if (++stage == (uint32_t)p.stages) { stage = 0; phase ^= 1; }
         }
       }
+      if (tr) { tr[3] = w_empty; tr[4] = clock64(); }
     }
     __syncwarp();
   } else if (warp == 1) {
@@ -196,14 +217,16 @@ conv_gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
       constexpr uint32_t idesc = ptx::make_idesc_f16(2 * kBM, BN);
       uint32_t stage = 0, phase = 0;
       int it = 0;
+      long long w_full = 0, w_acc = 0, t_first = 0;
       for (int tile = pair; tile < total_tiles; tile += npairs, ++it) {
         const int acc = it & 1;
         const uint32_t acc_phase = (it >> 1) & 1;
-        mbar_wait(&tmem_empty[acc], acc_phase ^ 1, p.debug, 0x200u + acc);
+        ME_TRACED_WAIT(w_acc, &tmem_empty[acc], acc_phase ^ 1, p.debug, 0x200u + acc);
         ptx::tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * BN;
         for (int kb = 0; kb < p.num_kb; ++kb) {
-          mbar_wait(&full_bar[stage], phase, p.debug, 0x300u + stage);
+          ME_TRACED_WAIT(w_full, &full_bar[stage], phase, p.debug, 0x300u + stage);
+          if (tr && t_first == 0) { t_first = clock64(); w_full = 0; }
           ptx::tc_fence_after();
           const uint32_t a_addr = ptx::smem_u32(stage_base + stage * C::STAGE_BYTES);
           const uint32_t b_addr = a_addr + C::A_BYTES;
@@ -219,68 +242,100 @@ conv_gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
         }
         ptx::umma_commit_pair(&tmem_full[acc], 0b11);       // accumulator ready in both CTAs
       }
+      if (tr) { tr[5] = w_full; tr[6] = w_acc; tr[7] = t_first; tr[8] = clock64(); tr[14] = it; }
     }
     __syncwarp();
   } else {
-    // ------------------------------------------------------------------ epilogue (warps 2..5, both CTAs)
+    // ------------------------------------------------------------------ epilogue (warps 2..9, both CTAs)
     const int q = warp & 3;
     const int row = q * 32 + lane;
+    const int half = (warp - 2) >> 2;   // which BN/2 columns this warp converts
     const int etid = threadIdx.x - 64;
     const bool eleader = (threadIdx.x == 64);
+    long long w_tfull = 0, w_other = 0, t_work = 0, t_first_full = 0;
+    auto load_residual = [&](int tile) {
+      const int tm = tile / p.tiles_n, tn = tile - tm * p.tiles_n;
+      const int m0 = tm * 2 * kBM + static_cast<int>(rank) * kBM;
+      ptx::mbar_arrive_expect_tx(res_full, C::STAGING_BYTES);
+#pragma unroll
+      for (int sub = 0; sub < C::NUM_SUB; ++sub)
+        ptx::tma_load_2d(&tmR, res_full, staging + sub * C::SUB_BYTES, tn * BN + sub * C::SUB_COLS, m0 < p.M ? m0 : 0);
+    };
+    // residual tiles are prefetched into the staging tile as soon as the previous store has drained it
+    if (p.has_res && eleader && pair < total_tiles) load_residual(pair);
     int it = 0;
     for (int tile = pair; tile < total_tiles; tile += npairs, ++it) {
       const int tm = tile / p.tiles_n, tn = tile - tm * p.tiles_n;
       const int m0 = tm * 2 * kBM + static_cast<int>(rank) * kBM, n0 = tn * BN;
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
-      if (eleader) {
-        ptx::tma_store_wait_read0();
-        if (p.has_res) {
-          ptx::mbar_arrive_expect_tx(res_full, C::STAGING_BYTES);
-#pragma unroll
-          for (int sub = 0; sub < C::NUM_SUB; ++sub)
-            ptx::tma_load_2d(&tmR, res_full, staging + sub * C::SUB_BYTES, n0 + sub * C::SUB_COLS, m0 < p.M ? m0 : 0);
-        }
-      }
+      const long long te0 = (tr && eleader) ? clock64() : 0;
+      if (eleader && !p.has_res) ptx::tma_store_wait_read0();
       for (int i = etid; i < BN; i += kEpiThreads) s_bias[i] = p.bias[n0 + i];
       ptx::named_bar_sync(kEpiBarrierId, kEpiThreads);
+      const long long te1 = (tr && eleader) ? clock64() : 0;
       mbar_wait(&tmem_full[acc], acc_phase, p.debug, 0x400u + acc);
       ptx::tc_fence_after();
+      const long long te2 = (tr && eleader) ? clock64() : 0;
       if (p.has_res) mbar_wait(res_full, it & 1, p.debug, 0x500u);
+      const long long te3 = (tr && eleader) ? clock64() : 0;
+      if (tr && eleader) {
+        w_other += (te1 - te0) + (te3 - te2);
+        w_tfull += te2 - te1;
+        if (it == 0) t_first_full = te2;
+      }
 
-      const uint32_t t_row = tmem_base + acc * BN + (static_cast<uint32_t>(q * 32) << 16);
-#pragma unroll 1
-      for (int c = 0; c < BN; c += 32) {
-        if (p.dbg & 1) break;  // attribution run: accumulators are released unread
-        uint32_t r[32];
-        ptx::tmem_ld_32x32b_x32(t_row + c, r);
-        ptx::tmem_ld_wait();
-        float v[32];
+      if (!(p.dbg & 1)) {  // attribution run: accumulators are released unread
+        constexpr int NCH = BN / 64;  // 32-column chunks per warp
+        const int c_base = half * (BN / 2);
+        const uint32_t t_row = tmem_base + acc * BN + c_base + (static_cast<uint32_t>(q * 32) << 16);
+        uint32_t r[2][32];
+        ptx::tmem_ld_32x32b_x32(t_row, r[0]);
 #pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = apply_act(__uint_as_float(r[j]) + s_bias[c + j], p.act);
-        uint8_t* sub = staging + (c / C::SUB_COLS) * C::SUB_BYTES;
-        const uint32_t rbase = row * 128 + (c % C::SUB_COLS) * 2;
+        for (int ci = 0; ci < NCH; ++ci) {
+          const int c = c_base + ci * 32;
+          ptx::tmem_ld_wait_regs(r[ci & 1]);
+          if (ci + 1 < NCH) ptx::tmem_ld_32x32b_x32(t_row + (ci + 1) * 32, r[(ci + 1) & 1]);
+          float v[32];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          uint32_t off = rbase + j * 16;
-          off ^= ((off >> 7) & 7u) << 4;
-          uint4* dst = reinterpret_cast<uint4*>(sub + off);
-          float* vv = v + 8 * j;
-          if (p.has_res) {
-            const uint4 rr = *dst;
-            const __half2* rh = reinterpret_cast<const __half2*>(&rr);
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const float2 f = __half22float2(rh[e]);
-              vv[2 * e] += f.x;
-              vv[2 * e + 1] += f.y;
-            }
+          for (int j4 = 0; j4 < 8; ++j4) {
+            const float4 b4 = *reinterpret_cast<const float4*>(s_bias + c + 4 * j4);
+            v[4 * j4 + 0] = __uint_as_float(r[ci & 1][4 * j4 + 0]) + b4.x;
+            v[4 * j4 + 1] = __uint_as_float(r[ci & 1][4 * j4 + 1]) + b4.y;
+            v[4 * j4 + 2] = __uint_as_float(r[ci & 1][4 * j4 + 2]) + b4.z;
+            v[4 * j4 + 3] = __uint_as_float(r[ci & 1][4 * j4 + 3]) + b4.w;
           }
-          uint4 o;
-          __half2* oh = reinterpret_cast<__half2*>(&o);
+          if (p.act == ME_ACT_LEAKY) {
 #pragma unroll
-          for (int e = 0; e < 4; ++e) oh[e] = __floats2half2_rn(vv[2 * e], vv[2 * e + 1]);
-          *dst = o;
+            for (int j = 0; j < 32; ++j) v[j] = fmaxf(v[j], 0.1f * v[j]);
+          } else if (p.act == ME_ACT_SIGMOID) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = apply_act(v[j], ME_ACT_SIGMOID);
+          }
+          uint8_t* sub = staging + (c / C::SUB_COLS) * C::SUB_BYTES;
+          const uint32_t rbase = row * 128 + (c % C::SUB_COLS) * 2;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            uint32_t off = rbase + j * 16;
+            off ^= ((off >> 7) & 7u) << 4;
+            uint4* dst = reinterpret_cast<uint4*>(sub + off);
+            float* vv = v + 8 * j;
+            if (p.has_res) {
+              const uint4 rr = *dst;
+              const __half2* rh = reinterpret_cast<const __half2*>(&rr);
+#pragma unroll
+              for (int e = 0; e < 4; ++e) {
+                const float2 f = __half22float2(rh[e]);
+                vv[2 * e] += f.x;
+                vv[2 * e + 1] += f.y;
+              }
+            }
+            uint4 o;
+            __half2* oh = reinterpret_cast<__half2*>(&o);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) oh[e] = __floats2half2_rn(vv[2 * e], vv[2 * e + 1]);
+            *dst = o;
+          }
         }
       }
       ptx::tc_fence_before();
@@ -288,19 +343,28 @@ conv_gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
       if (lane == 0) ptx::mbar_arrive_cluster(ptx::mapa(ptx::smem_u32(&tmem_empty[acc]), 0));
       ptx::fence_proxy_async_smem();
       ptx::named_bar_sync(kEpiBarrierId, kEpiThreads);
-      if (eleader && m0 < p.M && !(p.dbg & 1)) {
+      if (eleader) {
+        if (m0 < p.M && !(p.dbg & 1)) {
 #pragma unroll
-        for (int sub = 0; sub < C::NUM_SUB; ++sub)
-          ptx::tma_store_2d(&tmC, staging + sub * C::SUB_BYTES, n0 + sub * C::SUB_COLS, m0);
-        ptx::tma_store_commit();
+          for (int sub = 0; sub < C::NUM_SUB; ++sub)
+            ptx::tma_store_2d(&tmC, staging + sub * C::SUB_BYTES, n0 + sub * C::SUB_COLS, m0);
+          ptx::tma_store_commit();
+        }
+        if (p.has_res && tile + npairs < total_tiles) {
+          ptx::tma_store_wait_read0();
+          load_residual(tile + npairs);
+        }
       }
+      if (tr && eleader) t_work += clock64() - te3;
     }
     if (eleader) ptx::tma_store_wait_all0();
+    if (tr && eleader) { tr[9] = w_tfull; tr[10] = w_other; tr[11] = t_work; tr[12] = clock64(); tr[15] = t_first_full; }
   }
 
   ptx::tc_fence_before();
   ptx::cluster_sync();  // the peer may still be reading our barriers / issuing MMAs on our TMEM
   ptx::tc_fence_after();
+  if (tr && threadIdx.x == 0) tr[13] = clock64();
   if (warp == 1) ptx::tmem_dealloc_pair(tmem_base, C::TMEM_COLS);
 }
 
@@ -333,6 +397,7 @@ int launch_pair(const me_conv_desc* d, const void* x, const void* w, const float
   int rc = conv_ensure_debug_word();
   if (rc != ME_OK) return rc;
   p.debug = conv_debug_word();
+  p.trace = conv_trace_buffer();
   {
     static int dbg = -1;
     if (dbg < 0) {

@@ -72,6 +72,11 @@ CONV_CASES = {
     "fc_490_256": dict(n=300, h=1, w=1, cin=490, cout=256, k=1, s=1, act=1, bn=False),
     "3x3_single_pixel_rows": dict(n=5, h=1, w=7, cin=64, cout=32, k=3, s=1, act=1),
     "3x3_many_tiles": dict(n=4, h=52, w=52, cin=64, cout=128, k=3, s=1, act=1),
+    # several tiles per CTA: both epilogue groups, residual prefetch into the staging tile, N=256 tiles
+    "3x3_res_thin_multi": dict(n=8, h=104, w=104, cin=32, cout=64, k=3, s=1, act=1, res=True),
+    "3x3_res_pair_multi": dict(n=8, h=52, w=52, cin=128, cout=256, k=3, s=1, act=1, res=True),
+    "1x1_256_128_multi": dict(n=8, h=52, w=52, cin=256, cout=128, k=1, s=1, act=1),
+    "1x1_512_256_bn256": dict(n=8, h=26, w=26, cin=512, cout=256, k=1, s=1, act=1, res=True),
 }
 
 
