@@ -7,7 +7,7 @@
 A step = one pass of the hot path over one batch of 32 synthetic 416x416 frames:
 Darknet-53 (yolov3.cfg) forward -> YOLO decode -> confidence filter + NMS, fp16 compute.
 `value`  : frames/s with the input batch already resident in HBM.
-`e2e`    : frames/s through the public API (Darknet.forward_device + non_max_suppression results) with
+`e2e`    : frames/s through the public API (millieye_b200.models.DetectPipeline: Darknet forward + NMS) with
            the batch in pinned HOST memory - H2D copy of the images and D2H read of the detections
            inside the timed region.
 One JSON line on stdout (rank 0).
@@ -34,6 +34,25 @@ METRIC = "frames/sec at 416x416 batch32"
 # synthetic head statistics: objectness logits come out ~ N(-3.3, 0.8), so a few hundred of the 10 647 boxes per frame
 # pass the 0.2 confidence filter and the NMS has real work (random-init heads give conf ~ 0.5 everywhere)
 WEIGHTS = dict(obj_bias=-2.5, head_gain=3.0)
+
+
+_JSON_FD = None
+
+
+def quiet_stdout():
+    """Keeps fd 1 for the JSON line only: libraries that write to stdout on their own (NCCL prints its version
+    banner there on the first communicator) are sent to stderr."""
+    global _JSON_FD
+    if _JSON_FD is None:
+        sys.stdout.flush()
+        _JSON_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line):
+    sys.stdout.flush()
+    data = (json.dumps(line) + "\n").encode()
+    os.write(_JSON_FD if _JSON_FD is not None else 1, data)
 
 
 def peaks():
@@ -154,7 +173,7 @@ def run_reference(args):
                 config=dict(workload=f"Darknet-53 YOLOv3 inference, batch {BATCH}, {SIZE}x{SIZE}", cpu_sample_batch=CPU_BATCH),
                 cpu_baseline=dict(value=fps, unit="frames/s", cores=threads, kind="port", sample=sample),
                 e2e=dict(value=fps, unit="frames/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0))
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def run_gpu(args):
@@ -182,18 +201,14 @@ def run_gpu(args):
     host = [torch.rand(BATCH, 3, SIZE, SIZE, generator=gen).pin_memory() for _ in range(n_inputs)]
     resident = [h.to(device) for h in host]
     plan = net.plan_for(BATCH, SIZE, device)
-    nms = ops.NmsBuffers(BATCH, plan.rows_total, plan.attrs - 5, 200, device)
-    host_det = torch.empty_like(nms.det, device="cpu").pin_memory()
-    host_cnt = torch.empty_like(nms.count, device="cpu").pin_memory()
+    from millieye_b200.models import DetectPipeline
+    pipe = DetectPipeline(net, CONF_THRESH, 0.5, 200, gather=world > 1)
+    last = {}
 
     def step(x, e2e):
-        net.forward_device(x)                       # H2D (pinned) or D2D into the plan's input, then graph replay
-        ops.filter_nms(plan.yolo_out, CONF_THRESH, 0.5, 200, xyxy_inplace=True, buffers=nms)
-        if world > 1:
-            gather_detections(nms.det, nms.count)
-        if e2e:
-            host_det.copy_(nms.det, non_blocking=True)
-            host_cnt.copy_(nms.count, non_blocking=True)
+        # H2D (pinned, copy stream) or D2D into the plan's input, graph replay; then filter + NMS (+ all_gather,
+        # + D2H read of the detections in the e2e arm) on the pipeline's second stream
+        last["rec"] = pipe.submit(x, readback=e2e)
 
     launches_per_step = plan_launches = None
 
@@ -227,7 +242,8 @@ def run_gpu(args):
     ms_dev = timed(False)
     clocks = sampler.stop() if sampler else None
     ms_e2e = timed(True)
-    counts = host_cnt.tolist()
+    rec = last["rec"].wait()
+    counts = rec.host_cnt.tolist()
 
     # conv-only time: the same launch list without decode / NMS, for the tensor roofline
     conv_ms = None
@@ -261,7 +277,7 @@ def run_gpu(args):
     fps_e2e = world * BATCH * args.steps / ms_e2e * 1e3
     achieved = flops_frame * BATCH / (conv_ms * 1e-3) / 1e12
     h2d = BATCH * 3 * SIZE * SIZE * 4
-    d2h = host_det.numel() * 4 + host_cnt.numel() * 4
+    d2h = rec.host_det.numel() * 4 + rec.host_cnt.numel() * 4
 
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
@@ -287,6 +303,8 @@ def run_gpu(args):
                             + (", one all_gather of detections per step" if world > 1 else ""),
                             l2="3 rotating input batches (64 MB each) and ~4 GB of activations per step exceed the 126 MB L2; "
                                "no explicit flush",
+                            pipeline="DetectPipeline: filter+NMS (+all_gather, +D2H read in the e2e arm) of batch i run on a "
+                                     "second stream while the convolutions of batch i+1 run; all of it inside the timed region",
                             sub_batches=plan.splits, detections_last_step=int(sum(counts))),
                 clocks=clocks,
                 e2e=dict(value=fps_e2e, unit="frames/s", h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h,
@@ -300,7 +318,7 @@ def run_gpu(args):
                                    "(74 tcgen05 GEMMs + the tensor-core first conv per sub-batch; sub-batches run on parallel streams), "
                                    "CUDA events around graph replays"),
                 cpu_baseline=cpu)
-    print(json.dumps(line), flush=True)
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
 
@@ -328,6 +346,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
+    quiet_stdout()
     if args.impl == "reference":
         run_reference(args)
     else:

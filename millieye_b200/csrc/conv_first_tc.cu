@@ -74,7 +74,7 @@ conv_first_tc_kernel(const float* __restrict__ x, const __half* __restrict__ wk,
   extern __shared__ uint8_t smem_raw[];
   uint8_t* s_a = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   __shared__ __align__(128) uint8_t s_b[COUT * kK * 2];
-  __shared__ float s_bias[COUT];
+  __shared__ __align__(16) float s_bias[COUT];
   __shared__ __align__(8) uint64_t full_bar[F::STAGES], empty_bar[F::STAGES], tmem_full[FCfg<VEC>::ACCS], tmem_empty[FCfg<VEC>::ACCS];
   __shared__ uint32_t tmem_ptr;
   constexpr int TMEM_COLS = (F::ACCS * COUT <= 32) ? 32 : (F::ACCS * COUT <= 64) ? 64 : (F::ACCS * COUT <= 128) ? 128 : 256;
@@ -226,29 +226,45 @@ conv_first_tc_kernel(const float* __restrict__ x, const __half* __restrict__ wk,
       const uint32_t taddr = tmem_base + acc * COUT + (static_cast<uint32_t>(q * 32) << 16);
       const int pix = tile * kTileM + row;
       __half* dst = y + 1LL * pix * out_pitch;
+      // 32-byte sectors are written whole: one 256-bit store per 16 channels when the row pitch allows it
+      const bool wide = (out_pitch & 15) == 0 && (reinterpret_cast<uintptr_t>(y) & 31) == 0;
+      uint32_t r[2][16];
+      ptx::tmem_ld_32x32b_x16(taddr, r[0]);
 #pragma unroll
-      for (int c = 0; c < COUT; c += 16) {
-        uint32_t r[16];
-        ptx::tmem_ld_32x32b_x16(taddr + c, r);
-        ptx::tmem_ld_wait();
+      for (int ci = 0; ci < COUT / 16; ++ci) {
+        const int c = ci * 16;
+        ptx::tmem_ld_wait_regs16(r[ci & 1]);
+        if (ci + 1 < COUT / 16) ptx::tmem_ld_32x32b_x16(taddr + c + 16, r[(ci + 1) & 1]);
         uint4 o[2];
         __half2* oh = reinterpret_cast<__half2*>(o);
 #pragma unroll
-        for (int e = 0; e < 8; ++e) {
-          float a = __uint_as_float(r[2 * e]) + s_bias[c + 2 * e];
-          float b = __uint_as_float(r[2 * e + 1]) + s_bias[c + 2 * e + 1];
+        for (int e4 = 0; e4 < 4; ++e4) {
+          const float4 b4 = *reinterpret_cast<const float4*>(s_bias + c + 4 * e4);
+          float v0 = __uint_as_float(r[ci & 1][4 * e4 + 0]) + b4.x;
+          float v1 = __uint_as_float(r[ci & 1][4 * e4 + 1]) + b4.y;
+          float v2 = __uint_as_float(r[ci & 1][4 * e4 + 2]) + b4.z;
+          float v3 = __uint_as_float(r[ci & 1][4 * e4 + 3]) + b4.w;
           if (act == ME_ACT_LEAKY) {
-            a = a > 0.f ? a : 0.1f * a;
-            b = b > 0.f ? b : 0.1f * b;
+            v0 = fmaxf(v0, 0.1f * v0);
+            v1 = fmaxf(v1, 0.1f * v1);
+            v2 = fmaxf(v2, 0.1f * v2);
+            v3 = fmaxf(v3, 0.1f * v3);
           } else if (act == ME_ACT_SIGMOID) {
-            a = 1.f / (1.f + __expf(-a));
-            b = 1.f / (1.f + __expf(-b));
+            v0 = 1.f / (1.f + __expf(-v0));
+            v1 = 1.f / (1.f + __expf(-v1));
+            v2 = 1.f / (1.f + __expf(-v2));
+            v3 = 1.f / (1.f + __expf(-v3));
           }
-          oh[e] = __floats2half2_rn(a, b);
+          oh[2 * e4] = __floats2half2_rn(v0, v1);
+          oh[2 * e4 + 1] = __floats2half2_rn(v2, v3);
         }
         if (pix < total_px) {
-          *reinterpret_cast<uint4*>(dst + c) = o[0];
-          *reinterpret_cast<uint4*>(dst + c + 8) = o[1];
+          if (wide) {
+            ptx::st_global_256(dst + c, o[0], o[1]);
+          } else {
+            *reinterpret_cast<uint4*>(dst + c) = o[0];
+            *reinterpret_cast<uint4*>(dst + c + 8) = o[1];
+          }
         }
       }
       ptx::tc_fence_before();

@@ -112,6 +112,7 @@ class DarknetPlan:
         self._slot = 0
         self._graphs = [None, None]
         self._slot_free = [None, None]   # event: last forward that read the buffer has finished
+        self._out_busy = [None, None]    # event: a consumer on another stream is done with this slot's yolo_out
         self._copy_stream = None
         self._build()
 
@@ -174,7 +175,9 @@ class DarknetPlan:
                 rows_total += len(b["anchors"]) * hw[i] * hw[i]
                 self.attrs = 5 + b["classes"]
         self.rows_total = rows_total
-        self.yolo_out = torch.zeros((n, rows_total, self.attrs), dtype=torch.float32, device=self.device)
+        # one decoded-output buffer per slot: post-processing of batch i (another stream) overlaps the forward of i+1
+        self._yolo_bufs = [torch.zeros((n, rows_total, self.attrs), dtype=torch.float32, device=self.device)
+                           for _ in range(2)]
 
         views = [None] * nb
         row_off = 0
@@ -305,6 +308,16 @@ class DarknetPlan:
         self.launches = len(self.ops) * self.splits
 
     @property
+    def yolo_out(self):
+        """Decoded predictions of the current slot (written by the last run())."""
+        return self._yolo_bufs[self._slot]
+
+    def hold_output(self, event):
+        """A consumer running on another stream records `event` when it no longer needs the current slot's
+        yolo_out; the next run() that writes this slot waits for it."""
+        self._out_busy[self._slot] = event
+
+    @property
     def x_in(self):
         """Input buffer of the current slot (what the first conv reads)."""
         return self._x_bufs[self._slot]
@@ -329,6 +342,10 @@ class DarknetPlan:
 
     def run(self, use_graph=True):
         """Inputs must already be staged with load_input(). Enqueues (or replays) the whole forward."""
+        busy = self._out_busy[self._slot]
+        if busy is not None:
+            torch.cuda.current_stream().wait_event(busy)
+            self._out_busy[self._slot] = None
         if not use_graph:
             self.enqueue_split()
         else:

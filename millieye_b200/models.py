@@ -198,3 +198,55 @@ class Darknet(nn.Module):
                 else:
                     conv.bias.data.cpu().numpy().tofile(fh)
                 conv.weight.data.cpu().numpy().tofile(fh)
+
+
+class DetectPipeline:
+    """Detector forward + non_max_suppression_cpp (utils/utils.py:337-378) as a two-stage device pipeline for
+    streams of batches (run_sp.py:213-214 / run_mp.py:314-320 call the two back to back for every frame): the
+    confidence filter + NMS, the optional all-gather over ranks and the device->host read of batch i run on a second
+    CUDA stream while the main stream already executes the convolutions of batch i+1.  Every submit() returns the
+    record of its batch; record.wait() blocks the host until that batch's detections are complete."""
+
+    class Record:
+        def __init__(self, nms, host_det, host_cnt):
+            self.nms, self.host_det, self.host_cnt = nms, host_det, host_cnt
+            self.det, self.count = nms.det, nms.count
+            self.done = torch.cuda.Event()
+
+        def wait(self):
+            self.done.synchronize()
+            return self
+
+    def __init__(self, net, conf_thresh, nms_thresh=0.5, max_det=200, gather=False):
+        self.net, self.conf_thresh, self.nms_thresh, self.max_det, self.gather = net, conf_thresh, nms_thresh, max_det, gather
+        self._records = {}
+        self._side = None
+
+    def submit(self, x, readback=False):
+        plan = self.net.forward_device(x)
+        dev = plan.device
+        with torch.cuda.device(dev):
+            if self._side is None:
+                self._side = torch.cuda.Stream(device=dev)
+            key = (id(plan), plan._slot)
+            rec = self._records.get(key)
+            if rec is None:
+                nms = ops.NmsBuffers(plan.n, plan.rows_total, plan.attrs - 5, self.max_det, dev)
+                rec = self._records[key] = DetectPipeline.Record(
+                    nms, torch.empty_like(nms.det, device="cpu").pin_memory(),
+                    torch.empty_like(nms.count, device="cpu").pin_memory())
+            self._side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(self._side):
+                ops.filter_nms(plan.yolo_out, self.conf_thresh, self.nms_thresh, self.max_det, xyxy_inplace=True,
+                               buffers=rec.nms)
+                rec.det, rec.count = rec.nms.det, rec.nms.count
+                if self.gather:
+                    from .dist import gather_detections
+                    rec.det, rec.count = gather_detections(rec.nms.det, rec.nms.count)
+                if readback:
+                    rec.host_det.copy_(rec.nms.det, non_blocking=True)
+                    rec.host_cnt.copy_(rec.nms.count, non_blocking=True)
+                rec.done.record()
+            plan.hold_output(rec.done)
+        return rec
+

@@ -221,3 +221,35 @@ def test_stage2_golden(golden_dir):
             matched += 1
     assert matched >= 0.97 * len(ref)
     assert np.all(np.diff(o[:, 5]) <= 0)                     # sorted by the new confidence
+
+
+def test_detect_pipeline_matches_sequential():
+    """DetectPipeline (NMS of batch i on a second stream while batch i+1 runs) returns, for every batch of a
+    stream, exactly the detections of the sequential forward -> filter_nms path, device and host copies alike."""
+    from millieye_b200 import ops
+    from millieye_b200.models import DetectPipeline
+    net = Darknet(configs.cfg_path("yolov3-tiny-12")).eval()
+    net.load_state_dict(synth.fill_state_dict(net.state_dict(), seed=2, obj_bias=-1.0))
+    net.to(DEV)
+    batches = [synth.synth_images(3, 160, seed=10 + i) for i in range(5)]
+    want = []
+    for x in batches:
+        plan = net.forward_device(x.to(DEV))
+        b = ops.filter_nms(plan.yolo_out, 0.1, 0.5, 200, xyxy_inplace=True)
+        torch.cuda.synchronize()
+        want.append((b.det.cpu().clone(), b.count.cpu().clone()))
+    assert sum(int(c.sum()) for _, c in want) > 0
+    pipe = DetectPipeline(net, 0.1)
+    pinned = [x.pin_memory() for x in batches]
+    got = []
+    for x in pinned:                      # host batches: H2D on the copy stream, NMS + readback on the side stream
+        rec = pipe.submit(x, readback=True).wait()
+        got.append((rec.host_det.clone(), rec.host_cnt.clone()))
+    recs = [pipe.submit(x.to(DEV), readback=True) for x in batches[:2]]   # two batches in flight, both slots
+    for (d, c), (wd, wc) in zip(got, want):
+        assert torch.equal(c, wc)
+        for i in range(d.shape[0]):
+            assert torch.equal(d[i, :int(c[i])], wd[i, :int(c[i])])
+    for rec, (wd, wc) in zip(recs, want[:2]):
+        rec.wait()
+        assert torch.equal(rec.host_cnt, wc)
