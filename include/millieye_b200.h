@@ -209,6 +209,35 @@ int me_finalize_output(const float* img_boxes, const float* rois, const float* r
                        int regress_boxes, float* out, int* out_count, void* workspace, size_t workspace_bytes,
                        me_stream_t stream);
 
+/* ---- stage-3 labelling and loss (f3; my_models.py:545-640) --------------------- */
+/* obtain_iou_labels (my_models.py:317-375, multi_boxes true as Network.forward calls it, :555) over the proposal
+ * buffers of the forward: for each of the counts[1] proposals the best IoU (bbox_iou with the +1 pixel convention,
+ * utils/utils.py:255-281, first maximum) among the targets of the same image and predicted class, and that target's
+ * box; 0 / zeros when no target matches.  targets_xyxy: fp32 [num_targets][6] = [image, class, x1, y1, x2, y2] in
+ * pixels (the rewrite of :548-549 is the caller's).  iou_labels [cap], target_location [cap][4]; bit-exact. */
+int me_stage3_labels(const float* img_boxes, int box_pitch, const float* rois, const int* counts, int cap,
+                     const float* targets_xyxy, int num_targets, float* iou_labels, float* target_location,
+                     me_stream_t stream);
+
+typedef struct me_stage3_loss_cfg {
+  float iou_hi;       /* positives: iou_label > iou_hi (iou_thresh[1] = 0.7, my_models.py:556)            */
+  float alpha;        /* FocalLoss alpha (0.75, :420); gamma is 2                                          */
+  float lambda_conf;  /* loss = masks_loss + conf_loss / lambda_conf (loss_lambda[0] = 6, :635)            */
+  float thr_img;      /* refine_threshold_img / _radar: positive_masks of the metric (:516-519)            */
+  float thr_radar;
+} me_stage3_loss_cfg;
+
+/* Losses and counters of my_models.py:586-635 from the forward's buffers, the labels above and the caller's
+ * sample_filter (uint8 [cap]: every positive plus the negatives drawn at :600 - the draw stays on the host so that
+ * python's `random` state governs it, as in the reference).  out10 (device, fp32):
+ *   [0] masks_loss (FocalLoss, sum, image proposals in the sample)   [1] conf_loss (BCE sum over the sample)
+ *   [2] loss_xy  [3] loss_wh (SmoothL1 sums over positives)          [4] category_loss (BCE sum over positives)
+ *   [5] loss = [0] + [1] / lambda_conf                               [6] positives  [7] positive_masks  [8] true positives
+ *   [9] proposals. */
+int me_stage3_loss(const float* rois, const float* refine, const float* regress, const float* mask, const int* counts,
+                   int cap, const float* iou_labels, const float* target_location, const unsigned char* sample_filter,
+                   const me_stage3_loss_cfg* cfg, float* out10, me_stream_t stream);
+
 /* ---- radar point cloud -> network input map (f1 + f2) ----------------------- */
 typedef struct me_radar_cfg {
   double calib[12];        /* fx, cx, fy, cy, k1, k2, t1, t2, k3, trans_x, trans_y, trans_z

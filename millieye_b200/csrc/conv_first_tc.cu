@@ -17,6 +17,7 @@
 //   !VEC (any width): one pixel per thread, 27 scalar loads; 4 groups of 4 warps / 4 stages.
 #include "common.cuh"
 #include "ptx.cuh"
+#include <cstdlib>
 
 namespace me {
 namespace {
@@ -69,7 +70,7 @@ __device__ __forceinline__ void store_row(uint8_t* tile, int row, const float (&
 template <int COUT, bool VEC>
 __global__ void __launch_bounds__(FCfg<VEC>::THREADS, 1)
 conv_first_tc_kernel(const float* __restrict__ x, const __half* __restrict__ wk, const float* __restrict__ bias,
-                     __half* __restrict__ y, int n, int h, int w, int cin, int out_pitch, int act, int tiles) {
+                     __half* __restrict__ y, int n, int h, int w, int cin, int out_pitch, int act, int tiles, int dbg) {
   using F = FCfg<VEC>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* s_a = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -127,7 +128,7 @@ conv_first_tc_kernel(const float* __restrict__ x, const __half* __restrict__ wk,
         for (int j = 0; j < 4; ++j)
 #pragma unroll
           for (int i = 0; i < 27; ++i) v[j][i] = 0.f;
-        if (pix < total_px) {
+        if (pix < total_px && !(dbg & 2)) {  // ME_FIRST_DBG bit 2: attribution run without the image loads
           const int px = pix % w;
           const int t = pix / w;
           const int py = t % h;
@@ -153,8 +154,10 @@ conv_first_tc_kernel(const float* __restrict__ x, const __half* __restrict__ wk,
           }
         }
         mbar_wait_spin(&empty_bar[stage], phase ^ 1);
+        if (!(dbg & 4)) {  // bit 4: no tile build either
 #pragma unroll
-        for (int j = 0; j < 4; ++j) store_row(a_tile, lane * 4 + j, v[j]);
+          for (int j = 0; j < 4; ++j) store_row(a_tile, lane * 4 + j, v[j]);
+        }
       } else {
         const int row = threadIdx.x & 127;
         const int pix = tile * kTileM + row;
@@ -258,7 +261,7 @@ conv_first_tc_kernel(const float* __restrict__ x, const __half* __restrict__ wk,
           oh[2 * e4] = __floats2half2_rn(v0, v1);
           oh[2 * e4 + 1] = __floats2half2_rn(v2, v3);
         }
-        if (pix < total_px) {
+        if (pix < total_px && !(dbg & 1)) {  // bit 1: attribution run without the output stores
           if (wide) {
             ptx::st_global_256(dst + c, o[0], o[1]);
           } else {
@@ -295,7 +298,12 @@ int launch_first(const float* x, const __half* wk, const float* bias, __half* y,
     ME_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, F::SMEM));
     attr_set = true;
   }
-  kern<<<grid, F::THREADS, F::SMEM, stream>>>(x, wk, bias, y, n, h, w, cin, out_pitch, act, tiles);
+  static int dbg = -1;
+  if (dbg < 0) {
+    const char* e = getenv("ME_FIRST_DBG");
+    dbg = e ? atoi(e) : 0;
+  }
+  kern<<<grid, F::THREADS, F::SMEM, stream>>>(x, wk, bias, y, n, h, w, cin, out_pitch, act, tiles, dbg);
   ME_LAUNCH_CHECK();
   return ME_OK;
 }

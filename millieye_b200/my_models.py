@@ -174,6 +174,18 @@ class _FusionPlan:
         self.final_ws = torch.zeros((ws_bytes * 8,), dtype=torch.uint8, device=device)
         self.launches = 0
 
+    def ensure_loss_buffers(self, num_targets):
+        """Buffers of the labelling + loss branch (allocated on first use; inference never pays for them)."""
+        f32 = dict(dtype=torch.float32, device=self.device)
+        if getattr(self, "iou_labels", None) is None:
+            self.iou_labels = torch.zeros((self.cap,), **f32)
+            self.target_location = torch.zeros((self.cap, 4), **f32)
+            self.sample_filter = torch.zeros((self.cap,), dtype=torch.uint8, device=self.device)
+            self.loss_out = torch.zeros((16,), **f32)
+            self.targets_dev = torch.zeros((64, 6), **f32)
+        if self.targets_dev.shape[0] < num_targets:
+            self.targets_dev = torch.zeros((1 << (num_targets - 1).bit_length(), 6), **f32)
+
     def score_maps(self):
         """img_cnn_layers + radar_cnn_layers (my_models.py:486-487)."""
         n, g = self.n, self.g
@@ -257,8 +269,13 @@ class Network(nn.Module):
         radar_boxes_location (n,5) [frame, x1,y1,x2,y2] in 0..1 - scaled by S IN PLACE like the reference (:491);
         model_mode 0 fusion / 1 YOLO only / 2 radar only.  Returns output (K,8) on the device."""
         if targets is not None:
-            raise MeError("the stage-3 training branch (my_models.py:545-640) is not part of this round's "
-                          "accelerated path; run inference (targets=None)")
+            if model_mode != 0:
+                raise MeError("targets are only used with model_mode 0 (reference my_models.py:476-480 returns / "
+                              "changes thresholds before the loss branch in the other modes)")
+            if any(m.training for m in (self.img_cnn_layers, self.radar_cnn_layers, self.refinement_head)):
+                raise MeError("Network.forward(targets=...) runs the labelling + loss branch (my_models.py:545-640) with "
+                              "running BatchNorm statistics: call .eval() first.  Batch-statistics BatchNorm and the "
+                              "backward pass of the fusion heads are not built (DESIGN.md, out of scope this round)")
         base = self.base_detector
         plan_b = base.forward_device(images)
         dev = plan_b.device
@@ -281,4 +298,53 @@ class Network(nn.Module):
             plan.heads(float(self.refine_threshold_img), float(self.refine_threshold_radar), model_mode != 2)
             self.refinement_head.count += 1
             k = int(plan.out_count.item())                               # the forward's only host sync
-            return plan.out[:k].clone()
+            output = plan.out[:k].clone()
+            if targets is None:
+                return output
+            return self._loss_branch(plan, images.shape[3], targets, output)
+
+    def _loss_branch(self, plan, img_size, targets, output):
+        """Reference my_models.py:545-640 on the forward's device buffers: labels (me_stage3_labels), balanced
+        sampling with python's `random` on the host like the reference (:600), losses + counters (me_stage3_loss).
+        `targets` (m,6) [image, class, cx, cy, w, h] in 0..1 is rewritten IN PLACE to pixel x1y1x2y2 as the reference
+        does (:548-549).  Returns (loss, output, metric, radar_attention); loss carries no autograd graph."""
+        import random
+
+        import numpy as np
+
+        from .utils import xywh2xyxy
+        targets[:, 2:] = xywh2xyxy(targets[:, 2:])
+        targets[:, 2:] *= img_size
+        t = int(targets.shape[0])
+        plan.ensure_loss_buffers(t)
+        if t:
+            plan.targets_dev[:t].copy_(targets.to(torch.float32), non_blocking=True)
+        ops.stage3_labels(plan.img_boxes, plan.rois, plan.counts, plan.cap, plan.targets_dev, t, plan.iou_labels,
+                          plan.target_location)
+        n_img, n_all = (int(v) for v in plan.counts.tolist())
+        iou = plan.iou_labels[:n_all].cpu().numpy()
+        pos, neg = iou > self.iou_thresh[1], iou < self.iou_thresh[0]
+        pos_idx, neg_idx = np.where(pos)[0], np.where(neg)[0]
+        top_k = min(len(pos_idx) * self.balance_factor, len(neg_idx))
+        keep = pos.copy()
+        if top_k > 0:
+            keep[neg_idx[random.sample(range(len(neg_idx)), k=top_k)]] = True
+        plan.sample_filter.zero_()
+        if n_all:
+            plan.sample_filter[:n_all].copy_(torch.from_numpy(keep.astype(np.uint8)), non_blocking=True)
+        ops.stage3_loss(plan.rois, plan.refine, plan.regress, plan.mask, plan.counts, plan.cap, plan.iou_labels,
+                        plan.target_location, plan.sample_filter, plan.loss_out, self.iou_thresh[1], self.alpha,
+                        self.loss_lambda[0], float(self.refine_threshold_img), float(self.refine_threshold_radar))
+        vals = plan.loss_out.cpu()
+        conf_1 = torch.cat((plan.img_boxes[:n_img, 5], plan.refine[n_img:n_all, 0])).cpu()
+        conf_2 = plan.mask[:n_all].cpu()
+        lab = torch.from_numpy(iou)
+        confs = dict(conf_1_pos=conf_1[lab > 0.5], conf_1_neg=conf_1[lab < 0.5],
+                     conf_2_pos=conf_2[lab > 0.5], conf_2_neg=conf_2[lab < 0.5])
+        metric = dict(total=n_all, true=torch.tensor(int(vals[6])), positive=torch.tensor(int(vals[7])), tp=vals[8].clone(),
+                      conf=confs)
+        self.last_losses = dict(masks_loss=float(vals[0]), conf_loss=float(vals[1]), loss_xy=float(vals[2]),
+                                loss_wh=float(vals[3]), category_loss=float(vals[4]))
+        g = plan.g
+        radar_attention = plan.radar_score[..., 0].to(torch.float32).reshape(plan.n, 1, g, g)
+        return plan.loss_out[5].clone(), output, metric, radar_attention

@@ -257,3 +257,25 @@ def make_head_weights(tensors):
         assert t.dtype == torch.float32 and t.is_contiguous()
         setattr(hw, name, t.data_ptr())
     return hw
+
+
+def stage3_labels(img_boxes, rois, counts, cap, targets_xyxy, num_targets, iou_labels, target_location):
+    """obtain_iou_labels on the proposal buffers (reference my_models.py:317-375); targets_xyxy (>= num_targets, 6) fp32 cuda."""
+    _need_cuda(img_boxes, rois, counts, iou_labels, target_location)
+    if num_targets:
+        _need_cuda(targets_xyxy)
+    check(_lib.lib().me_stage3_labels(ptr(img_boxes), img_boxes.shape[1], ptr(rois), ptr(counts), cap,
+                                      ptr(targets_xyxy) if num_targets else None, num_targets, ptr(iou_labels),
+                                      ptr(target_location), stream_ptr()), "me_stage3_labels")
+
+
+def stage3_loss(rois, refine, regress, mask, counts, cap, iou_labels, target_location, sample_filter, out10, iou_hi, alpha,
+                lambda_conf, thr_img, thr_radar):
+    """Losses + counters of reference my_models.py:586-635 -> out10 (see include/millieye_b200.h)."""
+    _need_cuda(rois, refine, regress, mask, counts, iou_labels, target_location, sample_filter, out10)
+    assert sample_filter.dtype == torch.uint8 and out10.dtype == torch.float32 and out10.numel() >= 10
+    cfg = _lib.Stage3LossCfg(float(iou_hi), float(alpha), float(lambda_conf), float(thr_img), float(thr_radar))
+    check(_lib.lib().me_stage3_loss(ptr(rois), ptr(refine), ptr(regress), ptr(mask), ptr(counts), cap, ptr(iou_labels),
+                                    ptr(target_location), ptr(sample_filter), byref(cfg), ptr(out10), stream_ptr()),
+          "me_stage3_loss")
+

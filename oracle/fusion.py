@@ -131,8 +131,22 @@ def network_forward(module_defs, sd, images, maps, radar_boxes, conf_thresh, mod
     if return_intermediates:
         return output, dict(feat=feat, yolo_out=yolo_out, img_boxes=img_boxes, box_locations=box_locations,
                             roi_score_map=roi_score_map, radar_score_map=radar_score_map, crop_img=crop_img,
-                            crop_radar=crop_radar, reg=reg, ref_vec=ref_vec, masks=masks, positive=positive)
+                            crop_radar=crop_radar, reg=reg, ref_vec=ref_vec, masks=masks, positive=positive,
+                            all_boxes=all_boxes, n_img=n_img)
     return output
+
+
+def network_forward_train(module_defs, sd, images, maps, radar_boxes, conf_thresh, targets, sample_filter=None, **kw):
+    """Network.forward with targets (my_models.py:545-640), heads in eval mode: the inference forward followed by
+    the labelling + loss branch (oracle/stage3_loss.py).  targets (m,6) [image, class, cx, cy, w, h] in 0..1 (a copy is
+    converted; the reference rewrites the caller's tensor).  Returns (loss, output, metric, radar_attention, aux)."""
+    from . import stage3_loss as s3
+    output, im = network_forward(module_defs, sd, images, maps, radar_boxes, conf_thresh, return_intermediates=True, **kw)
+    tpx = s3.targets_to_pixels(np.asarray(targets, dtype=np.float32), images.shape[3])
+    aux = s3.stage3_losses(im["all_boxes"].numpy(), im["masks"].numpy(), im["ref_vec"].numpy(), im["reg"].numpy(),
+                           im["n_img"], im["positive"].numpy(), tpx, sample_filter=sample_filter)
+    attention = im["radar_score_map"][:, :1].numpy()
+    return aux["loss"], output, aux["metric"], attention, aux
 
 
 def network_forward_stage2(module_defs, sd, images, conf_thresh, refine_threshold=0.0, class_num=12,

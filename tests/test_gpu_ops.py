@@ -295,3 +295,83 @@ def test_roi_gathers_empty_and_degenerate():
     np.testing.assert_allclose(ra[:4, :490], ref_ra.reshape(4, -1), atol=2e-3)
     ps, ra, _, _ = _run_roi(feat, rfeat, np.zeros((0, 5), np.float32), 8)
     assert np.all(ps == 0) and np.all(ra == 0)
+
+
+# ------------------------------------------------------------------------------- stage-3 labelling + loss
+def _stage3_case(seed, n_img=500, n_radar=200, frames=8, n_t=60, cap=1024):
+    rng = np.random.default_rng(seed)
+    R = n_img + n_radar
+
+    def boxes(k):
+        c = rng.uniform(20, 396, (k, 2)).astype(np.float32)
+        wh = rng.uniform(8, 120, (k, 2)).astype(np.float32)
+        return np.concatenate((c - wh / 2, c + wh / 2), 1).astype(np.float32)
+
+    tg = np.zeros((n_t, 6), np.float32)
+    tg[:, 0] = rng.integers(0, frames - 1, n_t)          # the last frame has no ground truth at all
+    tg[:, 1] = rng.integers(0, 3, n_t)
+    tg[:, 2:] = boxes(n_t)
+    tg[5] = tg[4]                                         # identical targets: the first maximum must win
+    rows = np.zeros((cap, 9), np.float32)
+    rois = np.zeros((cap, 5), np.float32)
+    rois[:R, 0] = np.sort(rng.integers(0, frames, R))
+    rois[:R, 1:] = boxes(R)
+    for k in range(0, R, 3):                              # every third proposal sits on / near a target of its frame
+        cand = np.where((tg[:, 0] == rois[k, 0]) & (tg[:, 1] == 0))[0]   # class_num is 1: positives are class 0 (:629-630)
+        if len(cand):
+            j = cand[k % len(cand)]
+            rois[k, 1:] = tg[j, 2:] + (rng.normal(0, (0.0, 2.0, 9.0)[(k // 3) % 3], 4)).astype(np.float32)
+    far = [k for k in range(n_img) if k % 3]                 # unrelated proposals of other classes: filtered by class
+    rows[far, 7] = rng.integers(0, 3, len(far))
+    rows[:n_img, 0] = rois[:n_img, 0]
+    rows[:n_img, 1:5] = rois[:n_img, 1:]
+    rows[:n_img, 5] = rng.uniform(0.02, 0.99, n_img)
+    rows[n_img:, 7] = 0
+    refine = rng.uniform(0.001, 0.999, (cap, 2)).astype(np.float32)
+    refine[3, 0] = 1.0                                    # log(1 - x) = -inf -> clamped at -100 like BCELoss
+    regress = rng.normal(0, 0.5, (cap, 4)).astype(np.float32)
+    mask = rng.uniform(0.001, 0.999, cap).astype(np.float32)
+    return dict(rows=rows, rois=rois, refine=refine, regress=regress, mask=mask, targets=tg, n_img=n_img, R=R, cap=cap)
+
+
+@pytest.mark.parametrize("seed,n_img,n_radar,n_t", [(0, 500, 200, 60), (1, 0, 37, 12), (2, 300, 0, 0), (3, 1024 - 24, 24, 150)])
+def test_stage3_labels_and_loss_vs_oracle(seed, n_img, n_radar, n_t):
+    """me_stage3_labels bit-exact against the oracle's obtain_iou_labels (python loop, fp32 steps), me_stage3_loss
+    against the oracle's losses (fp32 terms; sums differ only in order: 2e-6 relative)."""
+    import random
+    from oracle import stage3_loss as s3
+    c = _stage3_case(seed, n_img, n_radar, n_t=max(n_t, 6))
+    tg = c["targets"][:n_t]
+    R, cap = c["R"], c["cap"]
+    dev = lambda a, dt=None: torch.from_numpy(a).to(DEV) if dt is None else torch.from_numpy(a).to(DEV, dt)
+    rows, rois, counts = dev(c["rows"]), dev(c["rois"]), torch.tensor([n_img, R], dtype=torch.int32, device=DEV)
+    lab = torch.full((cap,), -1.0, device=DEV)
+    loc = torch.full((cap, 4), -1.0, device=DEV)
+    tdev = dev(tg) if n_t else torch.zeros((1, 6), device=DEV)
+    ops.stage3_labels(rows, rois, counts, cap, tdev, n_t, lab, loc)
+    boxes6 = np.concatenate((c["rois"][:R, :1], c["rows"][:R, 7:8], c["rois"][:R, 1:]), 1)
+    want_lab, want_loc = s3.obtain_iou_labels(boxes6, tg.reshape(-1, 6), True)
+    got_lab, got_loc = lab.cpu().numpy(), loc.cpu().numpy()
+    assert np.array_equal(got_lab[:R], want_lab.reshape(-1)) and np.array_equal(got_loc[:R], want_loc)
+    assert not got_lab[R:].any() and not got_loc[R:].any()
+    if n_t:
+        assert (want_lab > 0.7).sum() > 0 or n_img == 0
+
+    all_boxes = np.zeros((R, 9), np.float32)
+    all_boxes[:, 0], all_boxes[:, 1:5], all_boxes[:, 7] = c["rois"][:R, 0], c["rois"][:R, 1:], c["rows"][:R, 7]
+    all_boxes[:n_img, 5] = c["rows"][:n_img, 5]
+    m = c["mask"][:R]
+    masks = np.stack((np.float32(1) - m, m), 1)
+    positive = np.concatenate((m[:n_img] > 0.3, m[n_img:] > 0.56))
+    random.seed(5)
+    want = s3.stage3_losses(all_boxes, masks, c["refine"][:R], c["regress"][:R], n_img, positive, tg.reshape(-1, 6))
+    keep = np.zeros(cap, np.uint8)
+    keep[:R] = want["sample_filter"]
+    out = torch.zeros(16, device=DEV)
+    ops.stage3_loss(rois, dev(c["refine"]), dev(c["regress"]), dev(c["mask"]), counts, cap, lab, loc, dev(keep), out,
+                    0.7, 0.75, 6, 0.3, 0.56)
+    got = out.cpu().numpy()
+    for i, k in enumerate(("masks_loss", "conf_loss", "loss_xy", "loss_wh", "category_loss", "loss")):
+        assert abs(got[i] - want[k]) <= 2e-6 * max(1.0, abs(float(want[k]))), (k, got[i], want[k])
+    assert (got[6], got[7], got[8], got[9]) == (want["metric"]["true"], want["metric"]["positive"], want["metric"]["tp"], R)
+

@@ -144,3 +144,45 @@ def test_stage2_matches_reference(golden_dir):
         out = ofus.network_forward_stage2(md, sd, synth.synth_images(2, 160, seed=6), 0.3)
     assert tuple(out.shape) == g["out"].shape and out.shape[0] > 100
     np.testing.assert_allclose(out.numpy(), g["out"], rtol=2e-4, atol=2e-4)
+
+
+def test_stage3_loss_matches_reference(golden_dir):
+    """Labelling + loss branch (my_models.py:545-640): oracle == reference on the fixture generated by
+    tests/golden/make_golden_stage3_loss.py - labels bit-exact, loss / output / attention to fp32 round-off."""
+    import random
+    from millieye_b200.my_models import Network, define_yolo
+    from oracle import stage3_loss as s3
+    g = np.load(os.path.join(golden_dir, "stage3_loss_tiny12_192.npz"))
+    cfg = configs.cfg_path("yolov3-tiny-12")
+    sd = synth.fill_state_dict(Network(define_yolo(cfg), conf_thresh=0.02).state_dict(), seed=6, obj_bias=2.0)
+    imgs, maps = synth.synth_images(4, 192, seed=6), synth.synth_maps(4, 192, seed=6)
+    random.seed(int(g["sampling_seed"]))
+    with torch.no_grad():
+        loss, out, metric, att, aux = ofus.network_forward_train(
+            parse_model_config(cfg), {k: v.float() for k, v in sd.items()}, imgs, maps, synth.synth_radar_boxes(4, seed=5),
+            0.02, g["targets"])
+    assert np.array_equal(s3.targets_to_pixels(g["targets"], 192), g["targets_after"])
+    assert np.array_equal(aux["iou_labels"], g["iou_labels"]) and np.array_equal(aux["target_location"], g["target_location"])
+    assert abs(float(loss) - float(g["loss"])) <= 1e-5 * float(g["loss"])
+    assert (metric["total"], metric["true"], metric["positive"], metric["tp"]) == (int(g["total"]), int(g["true"]),
+                                                                                  int(g["positive"]), float(g["tp"]))
+    assert np.abs(out.numpy() - g["output"]).max() <= 1e-4 and np.abs(att - g["radar_attention"]).max() <= 1e-6
+    for k in ("conf_1_pos", "conf_1_neg", "conf_2_pos", "conf_2_neg"):
+        assert np.allclose(metric["conf"][k], g[k], atol=1e-6)
+
+
+def test_obtain_iou_labels_rules():
+    """Same image AND class, +1 pixel IoU, first maximum, zeros when nothing matches; the multi_boxes=False path keeps
+    indices into the FILTERED target list like the reference (my_models.py:362-366)."""
+    from oracle import stage3_loss as s3
+    t = np.array([[0, 0, 10, 10, 50, 50], [0, 0, 10, 10, 50, 50], [0, 1, 10, 10, 50, 50], [1, 0, 0, 0, 20, 20]], np.float32)
+    b = np.array([[0, 0, 10, 10, 50, 50], [0, 1, 12, 10, 50, 50], [2, 0, 10, 10, 50, 50], [1, 0, 0, 0, 9, 9],
+                  [0, 0, 11, 10, 50, 50]], np.float32)
+    lab, loc = s3.obtain_iou_labels(b, t, True)
+    assert lab[0, 0] == 1.0 and np.array_equal(loc[0], t[0, 2:])
+    assert 0.9 < lab[1, 0] < 1.0 and np.array_equal(loc[1], t[2, 2:])
+    assert lab[2, 0] == 0.0 and not loc[2].any()
+    assert abs(lab[3, 0] - 100.0 / 441.0) < 1e-6
+    lab2, _ = s3.obtain_iou_labels(b, t, False)
+    assert lab2[0, 0] == 1.0 and lab2[4, 0] == 0.0          # target 0 of the filtered list was claimed by box 0
+
