@@ -87,6 +87,14 @@ typedef struct me_conv_desc {
 int me_conv_gemm(const me_conv_desc* d, const void* x, const void* w_packed, const float* bias,
                  const void* residual, void* y, me_stream_t stream);
 
+/* YOLO head: the linear 1x1 head conv (models.py:252, blocks followed by a [yolo] block) with YOLOLayer.forward's
+ * decode (models.py:142-177, see me_yolo_decode) fused into its epilogue: the fp32 logits never go to memory, the
+ * decoded rows are written straight into pred [n][rows_total][5+C] at row_offset.  d->out_f32 must be 1, no
+ * residual, linear activation; d->out_pitch is ignored.  Same results as me_conv_gemm + me_yolo_decode, bit for bit. */
+int me_conv_gemm_yolo(const me_conv_desc* d, const void* x, const void* w_packed, const float* bias, int g,
+                      int num_anchors, int num_classes, const float* host_anchors_wh, float stride, int rows_total,
+                      int row_offset, float* pred, me_stream_t stream);
+
 /* First layer: 3x3 / stride 1 / pad 1 conv straight from the caller's NCHW fp32 image
  * (cin <= 4) to NHWC fp16, BN folded, activation applied.  w_first is fp32 [cout][cin][3][3]
  * already BN-folded (me_fold_first_weights).  models.py:252 for module 0, my_models.py:133. */

@@ -31,6 +31,16 @@ constexpr int kEpiThreads = 128;        // one epilogue group = 4 warps = the fo
 constexpr uint32_t kEpiBarrierId = 1;   // named barrier of group g is kEpiBarrierId + g
 constexpr int kMaxStages = 8;
 
+// YOLO decode fused into the epilogue of a head conv (me_conv_gemm_yolo): out == nullptr means a plain conv.
+struct DecodeParams {
+  float* out;        // [n][rows_total][attrs] fp32
+  int na, attrs;     // anchors of this head, 5 + classes
+  int g, gg;         // grid size, g * g
+  int rows_total, row_offset;
+  float stride;
+  float aw[8], ah[8];  // anchors / stride, rounded to fp32 like models.py:127
+};
+
 struct ConvParams {
   int M;
   int Ho, Wo;
@@ -48,6 +58,7 @@ struct ConvParams {
   const float* bias;
   unsigned long long* debug;  // host-mapped word, written before a watchdog trap
   unsigned long long* trace;  // me_conv_set_trace: 16 clock64 words per CTA (tools/conv_trace.py), else nullptr
+  DecodeParams dec;
 };
 
 // Timed wait for the trace mode: adds the cycles spent in the wait to *acc.
@@ -110,7 +121,12 @@ struct Cfg {
   // A second staging tile costs pipeline stages, so the dispatcher (me_conv_gemm) picks EG per layer.
   static constexpr int EG = EG_;
   static_assert(EG == 1 || EG == 2, "epilogue groups");
-  static constexpr int THREADS = 64 + EG * kEpiThreads;
+  // Eight epilogue warps either way: with one group both warps of a TMEM lane quarter work on the same tile and
+  // split its columns (halves the exposed epilogue of the last tile and the accumulator hold time).
+  static constexpr int THREADS = 64 + 2 * kEpiThreads;
+  static constexpr int GROUP_THREADS = (EG == 2) ? kEpiThreads : 2 * kEpiThreads;
+  static constexpr int WARP_COLS = (EG == 2) ? BN : BN / 2;   // columns one epilogue warp converts per tile
+  static_assert(WARP_COLS % 32 == 0, "an epilogue warp converts whole 32-column chunks");
   static constexpr int SWZ_BITS = (SUB_ROW_BYTES == 128) ? 3 : (SUB_ROW_BYTES == 64) ? 2 : 1;
   static constexpr int TMEM_COLS = (2 * BN <= 32) ? 32 : (2 * BN <= 64) ? 64 : (2 * BN <= 128) ? 128 : (2 * BN <= 256) ? 256 : 512;
   static constexpr int TAIL_BYTES = EG * BN * 4 + 64 * 8 + 16;  // bias (per group) + barriers + tmem ptr
@@ -189,7 +205,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       }
       for (int a = 0; a < 2; ++a) {
         ptx::mbar_init(&tmem_full[a], 1);
-        ptx::mbar_init(&tmem_empty[a], 4);  // one arrive per epilogue warp
+        ptx::mbar_init(&tmem_empty[a], C::GROUP_THREADS / 32);  // one arrive per epilogue warp of the group
       }
       ptx::mbar_init(&res_full[0], 1);
       ptx::mbar_init(&res_full[1], 1);
@@ -302,7 +318,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const int g = (C::EG == 2) ? ((warp - 2) >> 2) : 0;  // epilogue group
     const int q = warp & 3;                              // TMEM lane quarter this warp may read
     const int row = q * 32 + lane;                       // tile row == TMEM lane
-    const int etid = (threadIdx.x - 64) & (kEpiThreads - 1);
+    const int c_base = (C::EG == 2) ? 0 : ((warp - 2) >> 2) * C::WARP_COLS;  // first column of this warp's share
+    const int etid = (threadIdx.x - 64) & (C::GROUP_THREADS - 1);
     const bool leader = (etid == 0);
     const bool tleader = leader && g == 0;               // trace words come from group 0
     uint8_t* stg = staging + g * C::STAGING_BYTES;
@@ -328,8 +345,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       const uint32_t acc_phase = (C::EG == 2) ? (lit & 1) : ((lit >> 1) & 1);
       const long long te0 = (tr && tleader) ? clock64() : 0;
       if (leader && !p.has_res) ptx::tma_store_wait_read0();  // previous store has drained the staging tile
-      for (int i = etid; i < BN; i += kEpiThreads) bias_s[i] = p.bias[n0 + i];
-      ptx::named_bar_sync(bar_id, kEpiThreads);
+      for (int i = etid; i < BN; i += C::GROUP_THREADS) bias_s[i] = p.bias[n0 + i];
+      ptx::named_bar_sync(bar_id, C::GROUP_THREADS);
       const long long te1 = (tr && tleader) ? clock64() : 0;
       mbar_wait(&tmem_full[acc], acc_phase, p.debug, 0x400u + acc);
       ptx::tc_fence_after();
@@ -342,16 +359,16 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         if (lit == 0) t_first_full = te2;
       }
 
-      const uint32_t t_row = tmem_base + acc * BN + (static_cast<uint32_t>(q * 32) << 16);
+      const uint32_t t_row = tmem_base + acc * BN + c_base + (static_cast<uint32_t>(q * 32) << 16);
       if (!(p.dbg & 1)) {  // attribution run: accumulators released unread
-        constexpr int NCH = BN / 32;
+        constexpr int NCH = C::WARP_COLS / 32;
         uint32_t r[2][32];
         ptx::tmem_ld_32x32b_x32(t_row, r[0]);
 #pragma unroll
         for (int ci = 0; ci < NCH; ++ci) {
-          const int c = ci * 32;
+          const int c = c_base + ci * 32;
           ptx::tmem_ld_wait_regs(r[ci & 1]);
-          if (ci + 1 < NCH) ptx::tmem_ld_32x32b_x32(t_row + c + 32, r[(ci + 1) & 1]);  // in flight during the math
+          if (ci + 1 < NCH) ptx::tmem_ld_32x32b_x32(t_row + (ci + 1) * 32, r[(ci + 1) & 1]);  // in flight during the math
           float v[32];
 #pragma unroll
           for (int j4 = 0; j4 < 8; ++j4) {
@@ -409,11 +426,41 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(&tmem_empty[acc]);  // accumulator may be overwritten
       ptx::fence_proxy_async_smem();                       // staging writes -> visible to TMA
-      ptx::named_bar_sync(bar_id, kEpiThreads);
+      ptx::named_bar_sync(bar_id, C::GROUP_THREADS);
       tw.next();
       if (C::EG == 2) tw.next();
+      if constexpr (OUT_F32) {
+        if (p.dec.out != nullptr) {
+          // YOLOLayer.forward (models.py:142-177) on the staged logits: the group's warps walk the tile row by row,
+          // a lane per head channel, so the writes of one row are contiguous over the 5+C attributes of an output
+          // row (anchor-major, then gy, gx).  Same arithmetic as yolo_decode_kernel (simt_ops.cu).
+          const DecodeParams& dp = p.dec;
+          const int head_ch = dp.na * dp.attrs;
+          for (int r = etid >> 5; r < kBM; r += C::GROUP_THREADS / 32) {
+            const int m = m0 + r;
+            if (m >= p.M) break;
+            const int img = m / dp.gg, rem = m - img * dp.gg;
+            const int gy = rem / dp.g, gx = rem - gy * dp.g;
+            float* orow = dp.out + (static_cast<size_t>(img) * dp.rows_total + dp.row_offset + rem) * dp.attrs;
+            for (int c = lane; c < BN; c += 32) {
+              const int col = n0 + c;
+              if (col >= head_ch) break;
+              const int a = col / dp.attrs, k = col - a * dp.attrs;
+              uint32_t off = r * C::SUB_ROW_BYTES + (c % C::SUB_COLS) * 4;
+              off ^= ((off >> 7) & ((1u << C::SWZ_BITS) - 1)) << 4;
+              const float v = *reinterpret_cast<const float*>(stg + (c / C::SUB_COLS) * C::SUB_BYTES + off);
+              float o;
+              if (k < 2) o = (1.f / (1.f + expf(-v)) + static_cast<float>(k == 0 ? gx : gy)) * dp.stride;
+              else if (k < 4) o = (expf(v) * (k == 2 ? dp.aw[a] : dp.ah[a])) * dp.stride;
+              else o = 1.f / (1.f + expf(-v));
+              orow[static_cast<size_t>(a) * dp.gg * dp.attrs + k] = o;
+            }
+          }
+          ptx::named_bar_sync(bar_id, C::GROUP_THREADS);  // the staging tile may be overwritten
+        }
+      }
       if (leader) {
-        if (!(p.dbg & 1)) {
+        if (!(p.dbg & 1) && !(OUT_F32 && p.dec.out != nullptr)) {
 #pragma unroll
           for (int sub = 0; sub < C::NUM_SUB; ++sub)
             ptx::tma_store_2d(&tmC, stg + sub * C::SUB_BYTES, n0 + sub * C::SUB_COLS, m0);
@@ -486,7 +533,7 @@ int ensure_debug_word() {
 
 template <int BN, int BK, bool OUT_F32, bool WS, int EG>
 int launch(const me_conv_desc* d, const void* x, const void* w, const float* bias, const void* residual, void* y,
-           cudaStream_t stream) {
+           cudaStream_t stream, const DecodeParams* dec = nullptr) {
   using C = Cfg<BN, BK, OUT_F32, EG>;
   const int pad = (d->ksize - 1) / 2;
   const int Ho = (d->h + 2 * pad - d->ksize) / d->stride + 1;
@@ -516,6 +563,7 @@ int launch(const me_conv_desc* d, const void* x, const void* w, const float* bia
   if (rc != ME_OK) return rc;
   p.debug = g_debug_dev;
   p.trace = g_trace_dev;
+  if (dec) p.dec = *dec;
   {
     static int dbg = -1;
     if (dbg < 0) {
@@ -642,8 +690,8 @@ int me_debug_status(unsigned long long* host_word) {
   return ME_OK;
 }
 
-int me_conv_gemm(const me_conv_desc* d, const void* x, const void* w_packed, const float* bias, const void* residual,
-                 void* y, me_stream_t stream_) {
+static int conv_dispatch(const me_conv_desc* d, const void* x, const void* w_packed, const float* bias,
+                         const void* residual, void* y, me_stream_t stream_, const me::DecodeParams* dec) {
   using namespace me;
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   ME_REQUIRE(d && x && w_packed && bias && y, "conv: null argument");
@@ -683,7 +731,7 @@ int me_conv_gemm(const me_conv_desc* d, const void* x, const void* w_packed, con
 #define ME_GO(BN, BK, F32, EG)                                                                            \
   do {                                                                                                    \
     if (!F32 && ws_ok(BN, EG)) return launch<BN, BK, false, true, EG>(d, x, w_packed, bias, residual, y, stream); \
-    return launch<BN, BK, F32, false, EG>(d, x, w_packed, bias, residual, y, stream);                     \
+    return launch<BN, BK, F32, false, EG>(d, x, w_packed, bias, residual, y, stream, dec);                \
   } while (0)
   if (bk == 64 && !f32 && cout >= 128) {
     // CTA pairs (256 x BN tiles) halve the shared-memory bytes per flop; worth it once the layer has
@@ -729,6 +777,44 @@ int me_conv_gemm(const me_conv_desc* d, const void* x, const void* w_packed, con
   }
 #undef ME_GO
   return ME_OK;
+}
+
+int me_conv_gemm(const me_conv_desc* d, const void* x, const void* w_packed, const float* bias, const void* residual,
+                 void* y, me_stream_t stream) {
+  return conv_dispatch(d, x, w_packed, bias, residual, y, stream, nullptr);
+}
+
+int me_conv_gemm_yolo(const me_conv_desc* d, const void* x, const void* w_packed, const float* bias, int g,
+                      int num_anchors, int num_classes, const float* host_anchors_wh, float stride, int rows_total,
+                      int row_offset, float* pred, me_stream_t stream) {
+  using namespace me;
+  ME_REQUIRE(d && pred && host_anchors_wh, "conv_yolo: null argument");
+  ME_REQUIRE(d->out_f32 == 1 && d->res_pitch == 0 && d->act == ME_ACT_LINEAR, "conv_yolo: the head conv is linear, fp32, no residual");
+  ME_REQUIRE(num_anchors >= 1 && num_anchors <= 8, "conv_yolo: 1..8 anchors");
+  const int attrs = 5 + num_classes;
+  ME_REQUIRE(d->cout >= num_anchors * attrs, "conv_yolo: cout %d < %d head channels", d->cout, num_anchors * attrs);
+  const int pad = (d->ksize - 1) / 2;
+  ME_REQUIRE((d->h + 2 * pad - d->ksize) / d->stride + 1 == g && (d->w + 2 * pad - d->ksize) / d->stride + 1 == g,
+             "conv_yolo: the conv output is not a %d x %d grid", g, g);
+  ME_REQUIRE(rows_total >= row_offset + num_anchors * g * g, "conv_yolo: rows_total too small");
+  DecodeParams dec{};
+  dec.out = pred;
+  dec.na = num_anchors;
+  dec.attrs = attrs;
+  dec.g = g;
+  dec.gg = g * g;
+  dec.rows_total = rows_total;
+  dec.row_offset = row_offset;
+  dec.stride = stride;
+  for (int a = 0; a < num_anchors; ++a) {
+    // models.py:127 keeps anchors / stride as float32 (FloatTensor of python doubles), :171 multiplies back
+    dec.aw[a] = static_cast<float>(static_cast<double>(host_anchors_wh[2 * a]) / static_cast<double>(stride));
+    dec.ah[a] = static_cast<float>(static_cast<double>(host_anchors_wh[2 * a + 1]) / static_cast<double>(stride));
+  }
+  // the output tensor map is never used for a store in this mode; pred only gives it a valid base address
+  me_conv_desc dd = *d;
+  dd.out_pitch = d->cout;
+  return conv_dispatch(&dd, x, w_packed, bias, nullptr, pred, stream, &dec);
 }
 
 }  // extern "C"

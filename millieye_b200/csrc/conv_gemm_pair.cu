@@ -409,6 +409,14 @@ int launch_pair(const me_conv_desc* d, const void* x, const void* w, const float
 
   int stages = (227 * 1024 - 1024 - C::STAGING_BYTES - C::TAIL_BYTES) / C::STAGE_BYTES;
   if (stages > kMaxStages) stages = kMaxStages;
+  {
+    static int cap = -1;  // ME_PAIR_STAGES: pipeline-depth sensitivity runs
+    if (cap < 0) {
+      const char* e = getenv("ME_PAIR_STAGES");
+      cap = e ? atoi(e) : 0;
+    }
+    if (cap >= 2 && cap < stages) stages = cap;
+  }
   ME_REQUIRE(stages >= 2, "conv(pair): not enough shared memory");
   p.stages = stages;
   const int smem = C::smem_bytes(stages);

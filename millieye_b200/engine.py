@@ -7,6 +7,7 @@ kernels left are conv GEMMs, the 3-channel first conv, max-pool, upsample and th
 and the launch sequence is captured in a CUDA graph that later forwards replay.
 """
 import gc
+import os
 
 import torch
 
@@ -94,6 +95,16 @@ class DarknetPlan:
         self.blocks, self.n, self.size, self.device = blocks, n, size, device
         self.feature_tap = feature_tap
         self.ops = []          # callables fn(b0, nb) enqueueing one kernel each over frames [b0, b0+nb)
+        self.op_kinds = []     # "conv" | "maxpool" | "upsample" | "decode", and the cfg block of every op
+        self.op_blocks = []
+        # Decode kernels form a second launch list (post_ops): in a stream of batches they run with the NMS on the
+        # post-processing stream while the next batch's convolutions run (models.DetectPipeline).
+        self.post_ops = []
+        self.post_blocks = []
+        # ME_FUSE_DECODE=1 runs the YOLO decode in the epilogue of the head conv instead (me_conv_gemm_yolo, bit-identical
+        # results).  Measured slower on B200 (batch 32: conv 2.95 ms vs 2.65 ms + 0.09 ms of decode kernels): the eight
+        # epilogue warps of a 1-CTA/SM GEMM are instruction-bound on the exp/sigmoid of 255 channels, so it is opt-in.
+        self.fuse_decode = os.environ.get("ME_FUSE_DECODE", "0") == "1"
         # Frames are independent, so the batch is run as `splits` sub-batches on parallel streams inside one
         # CUDA graph: while one sub-batch's persistent kernel drains its last (partial) wave of tiles, the
         # other sub-batch's kernel takes over the idle SMs.
@@ -111,6 +122,7 @@ class DarknetPlan:
         self._x_bufs = [torch.zeros((n, in_channels, size, size), dtype=torch.float32, device=device) for _ in range(2)]
         self._slot = 0
         self._graphs = [None, None]
+        self._post_graphs = [None, None]
         self._slot_free = [None, None]   # event: last forward that read the buffer has finished
         self._out_busy = [None, None]    # event: a consumer on another stream is done with this slot's yolo_out
         self._copy_stream = None
@@ -196,6 +208,15 @@ class DarknetPlan:
                 is_head = nxt is not None and nxt["type"] == "yolo"
                 out_idx = i + 1 if fuse_res is not None else i
                 cout = b["filters"]
+                if is_head and self.fuse_decode and b["size"] == 1 and not b["leaky"] and readers[i] == []:
+                    g = s_out
+                    packed = self._pack(i, b)
+                    self._add(lambda b0, nb, sv=src, p=packed, bb=nxt, g=g, st=self.size / g, ro=row_off: ops.conv_gemm_yolo(
+                        sv.at(b0), p, nb, sv.h, sv.w, sv.pitch, self.yolo_out[b0:], g, bb["anchors"], bb["classes"], st,
+                        self.rows_total, ro, cin=sv.real_c if sv.real_c != sv.c else sv.c, cout=p.cout_pad), "conv", i)
+                    nxt["_decoded_by_conv"] = True
+                    views[i] = None
+                    continue
                 if out_idx in target:
                     buf, off = target[out_idx]
                     ov = View(buf, off, cout, s_out, s_out)
@@ -204,6 +225,8 @@ class DarknetPlan:
                     cpad = ops.round_up(cout, 8 if i == 0 else 32)
                     ov = View(self._new(s_out, s_out, cpad, torch.float32 if is_head else torch.float16), 0, cpad,
                               s_out, s_out, real_c=cout)
+                    if is_head:   # head logits live per slot, like the decoded output they are turned into
+                        ov.alt = View(self._new(s_out, s_out, cpad, torch.float32), 0, cpad, s_out, s_out, real_c=cout)
                 self._add_conv(i, b, src, ov, fuse_res, views, is_head)
                 views[i] = ov
                 if fuse_res is not None:
@@ -217,7 +240,7 @@ class DarknetPlan:
                     raise MeError("only 2x2 max-pool is supported")
                 ov = View(self._new(s_out, s_out, ops.round_up(src.c, 8)), 0, src.c, s_out, s_out, real_c=src.real_c)
                 self._add(lambda b0, nb, sv=src, o=ov, st=b["stride"]: ops.maxpool2(
-                    sv.at(b0), o.at(b0), nb, sv.h, sv.w, ops.round_up(sv.c, 8), sv.pitch, o.pitch, st))
+                    sv.at(b0), o.at(b0), nb, sv.h, sv.w, ops.round_up(sv.c, 8), sv.pitch, o.pitch, st), "maxpool", i)
                 views[i] = ov
             elif t == "upsample":
                 if b["stride"] != 2:
@@ -228,7 +251,7 @@ class DarknetPlan:
                 else:
                     ov = View(self._new(s_out, s_out, ops.round_up(src.c, 8)), 0, src.c, s_out, s_out)
                 self._add(lambda b0, nb, sv=src, o=ov: ops.upsample2(sv.at(b0), o.at(b0), nb, sv.h, sv.w, sv.c, sv.pitch,
-                                                                     o.pitch))
+                                                                     o.pitch), "upsample", i)
                 views[i] = ov
             elif t == "route":
                 if len(b["layers"]) == 1:
@@ -239,8 +262,10 @@ class DarknetPlan:
             elif t == "yolo":
                 g = s_out
                 stride = self.size / g
-                self._add(lambda b0, nb, sv=src, bb=b, g=g, st=stride, ro=row_off: ops.yolo_decode(
-                    sv.at(b0), sv.pitch, self.yolo_out[b0:], nb, g, bb["anchors"], bb["classes"], st, self.rows_total, ro))
+                if not b.get("_decoded_by_conv"):
+                    self._add(lambda b0, nb, sv=src, bb=b, g=g, st=stride, ro=row_off: ops.yolo_decode(
+                        self._slot_view(sv).at(b0), sv.pitch, self.yolo_out[b0:], nb, g, bb["anchors"], bb["classes"], st,
+                        self.rows_total, ro), "decode", i, post=True)
                 row_off += len(b["anchors"]) * g * g
                 views[i] = src
             if i == self.feature_tap:
@@ -254,8 +279,26 @@ class DarknetPlan:
         t = self._tensors
         return (t[p + "weight"], t[p + "bias"], t[p + "running_mean"], t[p + "running_var"], 1e-5)
 
-    def _add(self, fn):
+    def _add(self, fn, kind, block, post=False):
+        if post:
+            self.post_ops.append(fn)
+            self.post_blocks.append(block)
+            return
         self.ops.append(fn)
+        self.op_kinds.append(kind)
+        self.op_blocks.append(block)
+
+    def _slot_view(self, v):
+        """The view's buffer of the current slot (only head-logit views have a second one)."""
+        alt = getattr(v, "alt", None)
+        return alt if (alt is not None and self._slot == 1) else v
+
+    def _pack(self, i, b):
+        t = self._tensors
+        packed = ops.pack_conv(t[f"module_list.{i}.conv_{i}.weight"], t.get(f"module_list.{i}.conv_{i}.bias"),
+                               self._bn_of(i) if b["bn"] else None, cout_pad=ops.round_up(b["filters"], 32))
+        self._keep = getattr(self, "_keep", []) + [packed]
+        return packed
 
     def _add_conv(self, i, b, src, ov, fuse_res, views, is_head):
         n = self.n
@@ -269,15 +312,15 @@ class DarknetPlan:
                 raise MeError("first layer must be a 3x3/stride-1 conv over <= 4 input channels")
             first = ops.pack_first_conv(w, bias, bn)
             self._keep = getattr(self, "_keep", []) + [first]
-            self._add(lambda b0, nb, f=first, o=ov, a=act: ops.conv_first(self.x_in[b0:b0 + nb], f, o.at(b0), o.pitch, a))
+            self._add(lambda b0, nb, f=first, o=ov, a=act: ops.conv_first(self.x_in[b0:b0 + nb], f, o.at(b0), o.pitch, a),
+                      "conv", i)
             return
-        packed = ops.pack_conv(w, bias, bn, cout_pad=ops.round_up(b["filters"], 32))
+        packed = self._pack(i, b)
         res_v = views[fuse_res] if fuse_res is not None else None
-        self._keep = getattr(self, "_keep", []) + [packed]
         self._add(lambda b0, nb, sv=src, p=packed, o=ov, st=b["stride"], a=act, rv=res_v, f32=is_head: ops.conv_gemm(
-            sv.at(b0), p, nb, sv.h, sv.w, sv.pitch, o.at(b0), o.pitch, stride=st, act=a,
+            sv.at(b0), p, nb, sv.h, sv.w, sv.pitch, self._slot_view(o).at(b0), o.pitch, stride=st, act=a,
             residual=None if rv is None else rv.at(b0), res_pitch=0 if rv is None else rv.pitch,
-            cin=sv.real_c if sv.real_c != sv.c else sv.c, cout=p.cout_pad, out_f32=f32))
+            cin=sv.real_c if sv.real_c != sv.c else sv.c, cout=p.cout_pad, out_f32=f32), "conv", i)
 
     # ------------------------------------------------------------------ execution
     def enqueue(self, b0=0, nb=None, only=None):
@@ -286,12 +329,17 @@ class DarknetPlan:
             if only is None or i in only:
                 fn(b0, nb)
 
+    def enqueue_post(self):
+        """The decode kernels of the current slot (head logits -> yolo_out)."""
+        for fn in self.post_ops:
+            fn(0, self.n)
+
     def enqueue_split(self, only=None):
         """All sub-batches, each on its own stream, joined back into the current stream.
         `only`: optional set of op indices (profiling a subset of the launch list)."""
         if self.splits == 1:
             self.enqueue(only=only)
-            self.launches = len(self.ops)
+            self.launches = len(self.ops) + len(self.post_ops)
             return
         if self._streams is None:
             self._streams = [torch.cuda.Stream(device=self.device) for _ in range(self.splits - 1)]
@@ -305,7 +353,7 @@ class DarknetPlan:
                 self.enqueue((k + 1) * nb, nb, only)
         for s in self._streams:
             cur.wait_stream(s)
-        self.launches = len(self.ops) * self.splits
+        self.launches = len(self.ops) * self.splits + len(self.post_ops)
 
     @property
     def yolo_out(self):
@@ -322,14 +370,22 @@ class DarknetPlan:
         """Input buffer of the current slot (what the first conv reads)."""
         return self._x_bufs[self._slot]
 
+    def next_input(self):
+        """The (n, C, S, S) fp32 device buffer the NEXT forward reads.  A producer that already works on the device
+        (decoder, augmentation, a previous model) writes the batch straight into it and passes this very tensor to
+        forward_device(): no staging copy is made."""
+        return self._x_bufs[self._slot ^ 1]
+
     def load_input(self, x):
-        """Stages the next batch: switches to the other input buffer and copies x into it.  A pinned host
-        tensor is copied on a separate stream, so the PCIe transfer overlaps the previous forward."""
+        """Stages the next batch: switches to the other input buffer and copies x into it (nothing to copy when x is
+        next_input()).  A pinned host tensor is copied on a separate stream, so the PCIe transfer overlaps the previous
+        forward."""
         self._slot ^= 1
         buf = self._x_bufs[self._slot]
         cur = torch.cuda.current_stream()
         if x.is_cuda:
-            buf.copy_(x, non_blocking=True)
+            if x.data_ptr() != buf.data_ptr() or x.shape != buf.shape or not x.is_contiguous():
+                buf.copy_(x, non_blocking=True)
             return
         if self._copy_stream is None:
             self._copy_stream = torch.cuda.Stream(device=self.device)
@@ -340,8 +396,22 @@ class DarknetPlan:
             buf.copy_(x, non_blocking=True)
         cur.wait_stream(cs)
 
-    def run(self, use_graph=True):
-        """Inputs must already be staged with load_input(). Enqueues (or replays) the whole forward."""
+    def run_decode(self, use_graph=True):
+        """Decode kernels of the current slot on the current stream (after run(decode=False))."""
+        if not self.post_ops:
+            return
+        if not use_graph:
+            self.enqueue_post()
+            return
+        if self._post_graphs[self._slot] is None:
+            self.enqueue_post()
+            torch.cuda.synchronize(self.device)
+            self._post_graphs[self._slot] = capture_graph(self.enqueue_post)
+        self._post_graphs[self._slot].replay()
+
+    def run(self, use_graph=True, decode=True):
+        """Inputs must already be staged with load_input(). Enqueues (or replays) the whole forward; decode=False
+        leaves the head logits undecoded for a later run_decode() (possibly on another stream)."""
         busy = self._out_busy[self._slot]
         if busy is not None:
             torch.cuda.current_stream().wait_event(busy)
@@ -359,3 +429,5 @@ class DarknetPlan:
         if ev is None:
             ev = self._slot_free[self._slot] = torch.cuda.Event()
         ev.record()
+        if decode:
+            self.run_decode(use_graph)

@@ -116,15 +116,16 @@ class Darknet(nn.Module):
             self._plans[key] = plan
         return plan
 
-    def forward_device(self, x):
-        """Runs the forward and returns the plan (outputs stay in the plan's device buffers)."""
+    def forward_device(self, x, decode=True):
+        """Runs the forward and returns the plan (outputs stay in the plan's device buffers).  decode=False stops
+        after the head convs; plan.run_decode() finishes the job (DetectPipeline does that on its second stream)."""
         if x.dim() != 4 or x.shape[2] != x.shape[3]:
             raise MeError(f"expected a square (N,C,S,S) batch, got {tuple(x.shape)}")
         dev = x.device if x.is_cuda else next(self.parameters()).device
         plan = self.plan_for(x.shape[0], x.shape[2], dev)
         with torch.cuda.device(dev):
             plan.load_input(x)   # device->device, or pinned host->device on the copy stream
-            plan.run(self.use_cuda_graph)
+            plan.run(self.use_cuda_graph, decode=decode)
         return plan
 
     def forward(self, x, targets=None):
@@ -223,7 +224,7 @@ class DetectPipeline:
         self._side = None
 
     def submit(self, x, readback=False):
-        plan = self.net.forward_device(x)
+        plan = self.net.forward_device(x, decode=False)
         dev = plan.device
         with torch.cuda.device(dev):
             if self._side is None:
@@ -237,6 +238,7 @@ class DetectPipeline:
                     torch.empty_like(nms.count, device="cpu").pin_memory())
             self._side.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(self._side):
+                plan.run_decode(self.net.use_cuda_graph)
                 ops.filter_nms(plan.yolo_out, self.conf_thresh, self.nms_thresh, self.max_det, xyxy_inplace=True,
                                buffers=rec.nms)
                 rec.det, rec.count = rec.nms.det, rec.nms.count

@@ -12,7 +12,7 @@ from . import _lib
 from ._lib import ME_ACT_LEAKY, ME_ACT_LINEAR, ME_ACT_SIGMOID, ConvDesc, HeadWeights, check, ptr, stream_ptr
 
 __all__ = [
-    "ME_ACT_LINEAR", "ME_ACT_LEAKY", "ME_ACT_SIGMOID", "round_up", "PackedConv", "pack_conv", "conv_gemm",
+    "ME_ACT_LINEAR", "ME_ACT_LEAKY", "ME_ACT_SIGMOID", "round_up", "PackedConv", "pack_conv", "conv_gemm", "conv_gemm_yolo",
     "FirstConv", "pack_first_conv", "conv_first", "maxpool2", "upsample2", "copy_channels", "nhwc_to_nchw_f32",
     "nchw_f32_to_nhwc", "yolo_decode", "filter_nms", "psroi_align", "roi_align", "build_proposals", "fusion_heads",
     "finalize_output",
@@ -72,6 +72,22 @@ def conv_gemm(x, packed, n, h, w, in_pitch, out, out_pitch, stride=1, act=ME_ACT
     check(_lib.lib().me_conv_gemm(byref(d), ptr(x), ptr(packed.w), ptr(packed.bias), ptr(residual), ptr(out),
                                   stream_ptr()), "me_conv_gemm")
     return out
+
+
+def conv_gemm_yolo(x, packed, n, h, w, in_pitch, pred, g, anchors, num_classes, yolo_stride, rows_total, row_offset,
+                   cin=None, cout=None):
+    """Head conv (1x1, linear, bias) with the YOLO decode fused into its epilogue: writes decoded rows into
+    pred (n, rows_total, 5+C) fp32 at row_offset (reference models.py:252 + :142-177)."""
+    _need_cuda(x, pred)
+    assert pred.dtype == torch.float32
+    d = ConvDesc(n=n, h=h, w=w, cin=cin or packed.cin, in_pitch=in_pitch, cout=cout or packed.cout_pad,
+                 out_pitch=cout or packed.cout_pad, ksize=packed.ksize, stride=1, act=ME_ACT_LINEAR, out_f32=1, res_pitch=0)
+    flat = [float(v) for wh in anchors for v in wh]
+    arr = (c_float * len(flat))(*flat)
+    check(_lib.lib().me_conv_gemm_yolo(byref(d), ptr(x), ptr(packed.w), ptr(packed.bias), g, len(anchors), num_classes,
+                                       arr, float(yolo_stride), rows_total, row_offset, ptr(pred), stream_ptr()),
+          "me_conv_gemm_yolo")
+    return pred
 
 
 class FirstConv:

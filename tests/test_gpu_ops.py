@@ -375,3 +375,27 @@ def test_stage3_labels_and_loss_vs_oracle(seed, n_img, n_radar, n_t):
         assert abs(got[i] - want[k]) <= 2e-6 * max(1.0, abs(float(want[k]))), (k, got[i], want[k])
     assert (got[6], got[7], got[8], got[9]) == (want["metric"]["true"], want["metric"]["positive"], want["metric"]["tp"], R)
 
+
+
+# ------------------------------------------------------------------------------- head conv + fused decode
+@pytest.mark.parametrize("n,g,cin,classes,size", [(2, 13, 1024, 80, 416), (3, 26, 256, 12, 416), (2, 52, 256, 80, 416),
+                                                   (5, 10, 512, 12, 320)])
+def test_conv_gemm_yolo_matches_unfused(n, g, cin, classes, size):
+    """me_conv_gemm_yolo (decode in the head conv's epilogue) == me_conv_gemm (fp32 logits) + me_yolo_decode, bit for bit."""
+    torch.manual_seed(g)
+    anchors = [(116, 90), (156, 198), (373, 326)]
+    attrs, cout = 5 + classes, 3 * (5 + classes)
+    cout_pad = ops.round_up(cout, 32)
+    x = (torch.randn(n, g, g, cin, device=DEV) * 0.5).half()
+    packed = ops.pack_conv(torch.randn(cout, cin, 1, 1, device=DEV) / cin ** 0.5, torch.randn(cout, device=DEV) * 0.5, None,
+                           cout_pad=cout_pad)
+    rows_total, row_off = 3 * g * g + 77, 40
+    logits = torch.zeros(n, g, g, cout_pad, device=DEV)
+    ops.conv_gemm(x, packed, n, g, g, cin, logits, cout_pad, act=ops.ME_ACT_LINEAR, out_f32=True)
+    want = torch.full((n, rows_total, attrs), -7.0, device=DEV)
+    ops.yolo_decode(logits, cout_pad, want, n, g, anchors, classes, size / g, rows_total, row_off)
+    got = torch.full((n, rows_total, attrs), -7.0, device=DEV)
+    ops.conv_gemm_yolo(x, packed, n, g, g, cin, got, g, anchors, classes, size / g, rows_total, row_off)
+    torch.cuda.synchronize()
+    assert torch.equal(got, want)
+    assert float(got[:, row_off:row_off + 3 * g * g, 4].min()) >= 0.0          # decoded rows were all written

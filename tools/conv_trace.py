@@ -39,8 +39,7 @@ def main():
     plan.load_input(torch.rand(n, 3, size, size, device=dev))
     plan.enqueue()
     torch.cuda.synchronize()
-    kinds = [(i, b) for i, b in enumerate(plan.blocks) if b["type"] in ("convolutional", "maxpool", "upsample", "yolo")]
-    assert len(kinds) == len(plan.ops)
+    kinds = [(i, plan.blocks[i]) for i in plan.op_blocks]
     trace = torch.zeros(148 * 16, dtype=torch.int64, device=dev)
     lib = _lib.lib()
     only = [int(v) for v in os.environ.get("ONLY_BLOCKS", "").split(",") if v]

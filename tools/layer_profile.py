@@ -31,11 +31,7 @@ def main():
     plan.load_input(torch.rand(n, 3, size, size, device=dev))
     plan.enqueue()
     torch.cuda.synchronize()
-    kinds = []
-    for i, b in enumerate(plan.blocks):
-        if b["type"] in ("convolutional", "maxpool", "upsample", "yolo"):
-            kinds.append((i, b))
-    assert len(kinds) == len(plan.ops)
+    kinds = [(i, plan.blocks[i]) for i in plan.op_blocks]
     total = 0.0
     rows = []
     for (i, b), fn in zip(kinds, plan.ops):
