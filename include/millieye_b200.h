@@ -87,6 +87,15 @@ typedef struct me_conv_desc {
 int me_conv_gemm(const me_conv_desc* d, const void* x, const void* w_packed, const float* bias,
                  const void* residual, void* y, me_stream_t stream);
 
+/* Optional workspace of me_conv_gemm's split-K tail (layers whose last wave of 256 x 256 tiles would leave most SM
+ * pairs idle cut those tiles along K; partial sums and arrival counters live here).  Zero-filled by the caller once,
+ * me_conv_workspace_bytes() long, 256-byte aligned; kernels that may overlap on different streams need different
+ * workspaces (set it before enqueueing on each stream).  NULL (the initial state) disables the split.  The setting is
+ * process-global, like the device; results are deterministic and independent of whether the split is used up to fp32
+ * summation order. */
+size_t me_conv_workspace_bytes(void);
+int me_conv_set_workspace(void* dev_workspace, size_t bytes);
+
 /* YOLO head: the linear 1x1 head conv (models.py:252, blocks followed by a [yolo] block) with YOLOLayer.forward's
  * decode (models.py:142-177, see me_yolo_decode) fused into its epilogue: the fp32 logits never go to memory, the
  * decoded rows are written straight into pred [n][rows_total][5+C] at row_offset.  d->out_f32 must be 1, no

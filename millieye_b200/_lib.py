@@ -56,6 +56,8 @@ SIGNATURES = {
     "me_pack_conv_weights": (c_int, [c_void_p] * 6 + [c_float, c_int, c_int, c_int, c_int, c_void_p, c_void_p,
                                                      c_void_p]),
     "me_conv_gemm": (c_int, [POINTER(ConvDesc), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "me_conv_workspace_bytes": (c_size_t, []),
+    "me_conv_set_workspace": (c_int, [c_void_p, c_size_t]),
     "me_conv_gemm_yolo": (c_int, [POINTER(ConvDesc), c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, POINTER(c_float),
                                   c_float, c_int, c_int, c_void_p, c_void_p]),
     "me_fold_first_weights": (c_int, [c_void_p] * 6 + [c_float, c_int, c_int, c_void_p, c_void_p, c_void_p]),

@@ -152,12 +152,6 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity, unsign
   }
 }
 
-__device__ __forceinline__ float apply_act(float v, int act) {
-  if (act == ME_ACT_LEAKY) return v > 0.f ? v : 0.1f * v;
-  if (act == ME_ACT_SIGMOID) return 1.f / (1.f + __expf(-v));
-  return v;
-}
-
 // WS (weight stationary): the layer's whole weight slab for this CTA's n tile (num_kb x BN x BK) is loaded
 // into shared memory once and the pipeline stages carry A only.  For the thin-channel layers (32..128
 // channels, 208^2..52^2 pixels) re-fetching the weights with every tile doubled the L2 -> SM traffic.

@@ -123,6 +123,7 @@ class DarknetPlan:
         self._slot = 0
         self._graphs = [None, None]
         self._post_graphs = [None, None]
+        self._conv_ws = []
         self._slot_free = [None, None]   # event: last forward that read the buffer has finished
         self._out_busy = [None, None]    # event: a consumer on another stream is done with this slot's yolo_out
         self._copy_stream = None
@@ -325,9 +326,17 @@ class DarknetPlan:
     # ------------------------------------------------------------------ execution
     def enqueue(self, b0=0, nb=None, only=None):
         nb = self.n if nb is None else nb
-        for i, fn in enumerate(self.ops):
-            if only is None or i in only:
-                fn(b0, nb)
+        # one split-K workspace per sub-batch stream: the conv kernels of different sub-batches may overlap
+        k = b0 // nb if nb else 0
+        while len(self._conv_ws) <= k:
+            self._conv_ws.append(ops.conv_workspace(self.device))
+        ops.conv_set_workspace(self._conv_ws[k])
+        try:
+            for i, fn in enumerate(self.ops):
+                if only is None or i in only:
+                    fn(b0, nb)
+        finally:
+            ops.conv_set_workspace(None)
 
     def enqueue_post(self):
         """The decode kernels of the current slot (head logits -> yolo_out)."""

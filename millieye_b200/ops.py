@@ -90,6 +90,20 @@ def conv_gemm_yolo(x, packed, n, h, w, in_pitch, pred, g, anchors, num_classes, 
     return pred
 
 
+def conv_workspace(device):
+    """Zero-filled workspace for the conv kernels' split-K tail (include/millieye_b200.h: me_conv_set_workspace)."""
+    return torch.zeros((_lib.lib().me_conv_workspace_bytes(),), dtype=torch.uint8, device=device)
+
+
+def conv_set_workspace(ws):
+    """Selects the workspace the following me_conv_gemm launches use (None: no split-K tail)."""
+    if ws is None:
+        check(_lib.lib().me_conv_set_workspace(None, 0), "me_conv_set_workspace")
+    else:
+        _need_cuda(ws)
+        check(_lib.lib().me_conv_set_workspace(ptr(ws), ws.numel() * ws.element_size()), "me_conv_set_workspace")
+
+
 class FirstConv:
     def __init__(self, w, bias, cin, cout):
         self.w, self.bias, self.cin, self.cout = w, bias, cin, cout

@@ -18,6 +18,15 @@ DEV = "cuda:0"
 
 
 # ------------------------------------------------------------------------------- conv GEMM
+_WS = []
+
+
+def _conv_ws():
+    if not _WS:
+        _WS.append(ops.conv_workspace(DEV))
+    return _WS[0]
+
+
 def _conv_case(n, h, w, cin, cout, k, s, act, bn=True, res=False, f32=False, seed=0):
     torch.manual_seed(seed)
     x = torch.randn(n, cin, h, w)
@@ -40,8 +49,12 @@ def _conv_case(n, h, w, cin, cout, k, s, act, bn=True, res=False, f32=False, see
     if res:
         ref = ref + resid[..., :cout].float().permute(0, 3, 1, 2)
     out = torch.full((n, ho, wo, cout_pad), float("nan"), dtype=torch.float32 if f32 else torch.float16, device=DEV)
-    ops.conv_gemm(xh.to(DEV), packed, n, h, w, in_pitch, out, cout_pad, stride=s, act=act,
-                  residual=None if resid is None else resid.to(DEV), res_pitch=cout_pad, out_f32=f32)
+    ops.conv_set_workspace(_conv_ws())          # like the engine: lets the pair kernel split the tail tiles along K
+    try:
+        ops.conv_gemm(xh.to(DEV), packed, n, h, w, in_pitch, out, cout_pad, stride=s, act=act,
+                      residual=None if resid is None else resid.to(DEV), res_pitch=cout_pad, out_f32=f32)
+    finally:
+        ops.conv_set_workspace(None)
     torch.cuda.synchronize()
     got = out.float().cpu()[..., :cout].permute(0, 3, 1, 2)
     assert not torch.isnan(got).any()
@@ -76,7 +89,10 @@ CONV_CASES = {
     "3x3_res_thin_multi": dict(n=8, h=104, w=104, cin=32, cout=64, k=3, s=1, act=1, res=True),
     "3x3_res_pair_multi": dict(n=8, h=52, w=52, cin=128, cout=256, k=3, s=1, act=1, res=True),
     "1x1_256_128_multi": dict(n=8, h=52, w=52, cin=256, cout=128, k=1, s=1, act=1),
-    "1x1_512_256_bn256": dict(n=8, h=26, w=26, cin=512, cout=256, k=1, s=1, act=1, res=True),
+    "1x1_512_256_res": dict(n=8, h=26, w=26, cin=512, cout=256, k=1, s=1, act=1, res=True),
+    # 88 pair tiles on 74 pairs: the 14 tail tiles are split along K (4 slices), partial sums reduced by the last arriver
+    "3x3_pair_split_13_res": dict(n=32, h=13, w=13, cin=128, cout=1024, k=3, s=1, act=1, res=True),
+    "3x3_pair_split_13": dict(n=32, h=13, w=13, cin=192, cout=1024, k=3, s=1, act=1),
 }
 
 
@@ -399,3 +415,27 @@ def test_conv_gemm_yolo_matches_unfused(n, g, cin, classes, size):
     torch.cuda.synchronize()
     assert torch.equal(got, want)
     assert float(got[:, row_off:row_off + 3 * g * g, 4].min()) >= 0.0          # decoded rows were all written
+
+
+def test_pair_tail_split_is_deterministic_and_reusable():
+    """The split-K tail of the pair kernel: repeated launches (counters reset by the last arriver) give identical
+    bits, and equal the unsplit kernel to fp32 summation-order round-off."""
+    torch.manual_seed(3)
+    n, g, cin, cout = 32, 13, 256, 1024
+    x = (torch.randn(n, g, g, cin, device=DEV) * 0.5).half()
+    packed = ops.pack_conv(torch.randn(cout, cin, 3, 3, device=DEV) / (cin * 9) ** 0.5, None,
+                           (torch.ones(cout, device=DEV), torch.zeros(cout, device=DEV), torch.zeros(cout, device=DEV),
+                            torch.ones(cout, device=DEV), 1e-5))
+    outs = []
+    for k in range(4):
+        out = torch.zeros(n, g, g, cout, dtype=torch.float16, device=DEV)
+        ops.conv_set_workspace(_conv_ws() if k < 3 else None)      # the last run has no workspace: unsplit kernel
+        try:
+            ops.conv_gemm(x, packed, n, g, g, cin, out, cout)
+        finally:
+            ops.conv_set_workspace(None)
+        outs.append(out)
+    torch.cuda.synchronize()
+    assert torch.equal(outs[0], outs[1]) and torch.equal(outs[0], outs[2])
+    assert float(outs[0].float().abs().max()) > 0.1
+    assert float((outs[0].float() - outs[3].float()).abs().max()) <= 2e-3 * float(outs[3].float().abs().max())

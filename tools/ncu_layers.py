@@ -9,7 +9,7 @@ from collections import OrderedDict
 cfg = sys.argv[2] if len(sys.argv) > 2 else 'yolov3'
 N, S = 32, 416
 lines = [l for l in open(sys.argv[1]) if l.startswith('"')]
-rows = list(csv.DictReader(lines))
+rows = [r for r in csv.DictReader(lines) if r['Metric Name'] == 'gpu__time_duration.sum']
 names = [x['Kernel Name'] for x in rows]; us = [float(x['Metric Value']) / 1000 for x in rows]
 _, blocks = describe_blocks(parse_model_config(configs.cfg_path(cfg)))
 convs = [b for b in blocks if b['type'] == 'convolutional']
@@ -34,7 +34,7 @@ for j, bi in enumerate(ci):
     gf = 2.0 * N * o * o * b['filters'] * b['cin'] * b['size'] ** 2 / 1e9
     gb = (2.0 * N * (i_ * i_ * b['cin'] + o * o * b['filters'] * (2 if res else 1)) + 2.0 * b['filters'] * b['cin'] * b['size'] ** 2) / 1e9
     if bi == 0: gb = (4.0 * N * i_ * i_ * 3 + 2.0 * N * o * o * b['filters']) / 1e9
-    ideal = max(gf / 1361.3 * 1e3, gb / 6550.4 * 1e6)
+    ideal = max(gf / 1404.7 * 1e3, gb / 6535.7 * 1e6)   # MEASURED_PEAKS.json: sustained bf16 TF, copy GB/s
     tot_ideal += ideal
     key = (o, b['size'], b['stride'], b['cin'], b['filters'], res, names[start + j].split('<')[0].split('::')[-1] + '<' + names[start + j].split('<')[1].split('>')[0] + '>')
     e = g.setdefault(key, [0, 0, 0, 0]); e[0] += t; e[1] += 1; e[2] += ideal; e[3] += gf
