@@ -23,6 +23,10 @@ namespace me {
 
 int conv_gemm_pair(int bn, const me_conv_desc* d, const void* x, const void* w, const float* bias, const void* residual,
                    void* y, cudaStream_t stream);  // conv_gemm_pair.cu
+bool conv_thin_enabled();                          // conv_thin.cu
+bool conv_thin_supported(const me_conv_desc* d);
+int conv_thin(const me_conv_desc* d, const void* x, const void* w, const float* bias, const void* residual, void* y,
+              cudaStream_t stream);
 
 namespace {
 
@@ -698,6 +702,8 @@ static int conv_dispatch(const me_conv_desc* d, const void* x, const void* w_pac
   ME_REQUIRE(d->out_pitch >= d->cout && (d->out_pitch * (d->out_f32 ? 4 : 2)) % 16 == 0, "conv: bad out_pitch %d",
              d->out_pitch);
   ME_REQUIRE(d->n > 0 && d->h > 0 && d->w > 0, "conv: empty input");
+  // 3x3 layers over 16 / 32 channels: SIMT im2col producers (TMA delivers their 32- / 64-byte pixel rows too slowly)
+  if (dec == nullptr && conv_thin_enabled() && conv_thin_supported(d)) return conv_thin(d, x, w_packed, bias, residual, y, stream);
   const int bk = me_conv_k_block(d->cin);
   const bool f32 = d->out_f32 != 0;
   const int cout = d->cout;

@@ -67,6 +67,18 @@ __device__ __forceinline__ void named_bar_sync(uint32_t id, uint32_t nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 
+// ---------------------------------------------------------------- cp.async (LDGSTS)
+// 16-byte asynchronous global -> shared copy; !valid copies nothing and zero-fills the 16 bytes (src-size 0).
+__device__ __forceinline__ void cp_async_16(uint32_t dst_smem, const void* src, bool valid) {
+  const uint32_t bytes = valid ? 16u : 0u;
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;" ::"r"(dst_smem), "l"(src), "r"(bytes) : "memory");
+}
+// The mbarrier gets one arrival from this thread once all its earlier cp.async copies have landed (the arrival was
+// counted at mbarrier.init time: .noinc).
+__device__ __forceinline__ void cp_async_mbar_arrive_noinc(uint64_t* bar) {
+  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
 // ---------------------------------------------------------------- TMA
 __device__ __forceinline__ void prefetch_tmap(const CUtensorMap* m) {
   asm volatile("prefetch.tensormap [%0];" ::"l"(reinterpret_cast<uint64_t>(m)) : "memory");

@@ -439,3 +439,19 @@ def test_pair_tail_split_is_deterministic_and_reusable():
     assert torch.equal(outs[0], outs[1]) and torch.equal(outs[0], outs[2])
     assert float(outs[0].float().abs().max()) > 0.1
     assert float((outs[0].float() - outs[3].float()).abs().max()) <= 2e-3 * float(outs[3].float().abs().max())
+
+
+@pytest.mark.parametrize("name", ["3x3_bk32", "3x3_s2_32_64", "3x3_res_thin_multi", "3x3_bk16"])
+def test_conv_thin_kernel_all_shapes(name):
+    """The cp.async-fed thin kernel also serves 32-channel inputs under ME_CONV_THIN=2 (off by default: no faster than
+    the TMA kernel there); run the conv cases that qualify in a child process with it forced on."""
+    import subprocess
+    import sys
+    here = os.path.abspath(__file__)
+    code = ("import sys, importlib.util; sys.path.insert(0, %r); "
+            "spec = importlib.util.spec_from_file_location('gpu_ops_cases', %r); t = importlib.util.module_from_spec(spec); "
+            "spec.loader.exec_module(t); t._conv_case(**t.CONV_CASES[%r]); print('THIN-OK')"
+            % (os.path.dirname(os.path.dirname(here)), here, name))
+    env = dict(os.environ, ME_CONV_THIN="2")
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, timeout=300)
+    assert "THIN-OK" in r.stdout, r.stderr[-2000:]

@@ -43,6 +43,8 @@ CASES = {
     "e53_208_3x3_32_64_res": dict(n=32, h=208, w=208, cin=32, cout=64, k=3, s=1, act=1, bn=True, res=True, time=True, noref=True),
     "e53_208_1x1_64_32": dict(n=32, h=208, w=208, cin=64, cout=32, k=1, s=1, act=1, bn=True, time=True, noref=True),
     "e53_104_3x3_s2_64_128": dict(n=32, h=208, w=208, cin=64, cout=128, k=3, s=2, act=1, bn=True, time=True, noref=True),
+    "t12_208_3x3_16_32": dict(n=32, h=208, w=208, cin=16, cout=32, k=3, s=1, act=1, bn=True, time=True, noref=True),
+    "t12_104_3x3_32_64": dict(n=32, h=104, w=104, cin=32, cout=64, k=3, s=1, act=1, bn=True, time=True, noref=True),
     "d53_26_3x3_s2_256_512": dict(n=32, h=52, w=52, cin=256, cout=512, k=3, s=2, act=1, bn=True, time=True, spot=True),
 }
 
