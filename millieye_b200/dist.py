@@ -58,3 +58,38 @@ def gather_rows(rows, frames_per_rank, cap, group=None):
     bufs = [torch.empty_like(payload) for _ in range(world)]
     dist.all_gather(bufs, payload, group=group)
     return torch.cat([b[:int(c.item())] for b, c in zip(bufs, ks)], 0)
+
+
+def all_reduce_sum_(t, group=None):
+    """In-place sum over ranks (no-op for a single process).  The stage-3 losses are sums over proposals
+    (reduction='sum', reference my_models.py:296-313,614-633) and the metric entries are counts, so the whole-batch
+    values of a sharded step are the element-wise sums of the ranks' me_stage3_loss vectors."""
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+    return t
+
+
+def all_reduce_gradients(params, group=None, average=True):
+    """One flat bucket for every gradient of `params` (the stage-3 trainable set is 112 845 fp32 values, SURVEY.md
+    F8: latency-bound, so a single all-reduce): flatten, all-reduce, scatter back.  Parameters without a gradient
+    (F7: unused heads, or no image proposals on this rank) take part with zeros so that every rank reduces the same
+    bucket layout.  Returns the number of reduced elements."""
+    params = [p for p in params if p.requires_grad]
+    if not params:
+        return 0
+    world = dist.get_world_size(group) if dist.is_available() and dist.is_initialized() else 1
+    flat = torch.cat([(p.grad if p.grad is not None else torch.zeros_like(p)).reshape(-1).to(torch.float32) for p in params])
+    if world > 1:
+        dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+        if average:
+            flat /= world
+    off = 0
+    for p in params:
+        n = p.numel()
+        g = flat[off:off + n].view_as(p).to(p.dtype)
+        if p.grad is None:
+            p.grad = g.clone()
+        else:
+            p.grad.copy_(g)
+        off += n
+    return off

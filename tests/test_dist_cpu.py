@@ -8,7 +8,8 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from millieye_b200.dist import gather_detections, gather_rows, shard_batch, shard_bounds, shard_rows_by_frame
+from millieye_b200.dist import (all_reduce_gradients, all_reduce_sum_, gather_detections, gather_rows, shard_batch, shard_bounds,
+                                shard_rows_by_frame)
 
 
 def _free_port():
@@ -69,3 +70,44 @@ def test_sharded_gather_equals_single_process():
         lo, hi = shard_bounds(total, world, rank)
         assert all(0 <= v < hi - lo for v in local_radar[:, 0].tolist())
     assert results[0][4][:, 1].tolist() == [1.0, 2.0] and results[1][4][:, 1].tolist() == [3.0]
+
+
+def _reduce_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        torch.manual_seed(0)
+        lin = torch.nn.Linear(5, 3)
+        unused = torch.nn.Linear(2, 2)                     # never gets a gradient
+        x = torch.full((4, 5), float(rank + 1))
+        lin(x).sum().backward()
+        if rank == 0:
+            unused.weight.grad = torch.ones_like(unused.weight)   # only one rank has a gradient for it
+        n = all_reduce_gradients(list(lin.parameters()) + list(unused.parameters()))
+        loss_vec = all_reduce_sum_(torch.arange(10, dtype=torch.float32) * (rank + 1))
+        q.put((rank, n, lin.weight.grad.clone(), unused.weight.grad.clone(), unused.bias.grad.clone(), loss_vec))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.timeout(120)
+def test_gradient_bucket_and_loss_reduction():
+    """Single-bucket gradient all-reduce (mean over ranks, missing gradients count as zeros) and the sum-reduction of
+    the stage-3 loss vector, world size 2 on gloo."""
+    world = 2
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_reduce_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    results = sorted([q.get(timeout=90) for _ in range(world)], key=lambda t: t[0])
+    for p in procs:
+        p.join(timeout=30)
+    for rank, n, wgrad, ugrad, ubias, loss_vec in results:
+        assert n == 15 + 3 + 4 + 2
+        assert torch.allclose(wgrad, torch.full((3, 5), 4 * 1.5))          # mean of 4*1 and 4*2 per weight
+        assert torch.allclose(ugrad, torch.full((2, 2), 0.5)) and torch.equal(ubias, torch.zeros(2))
+        assert torch.equal(loss_vec, torch.arange(10, dtype=torch.float32) * 3)
+    assert torch.equal(results[0][2], results[1][2])
+
