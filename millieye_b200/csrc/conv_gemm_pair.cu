@@ -48,7 +48,7 @@ struct PairParams {
   int has_res;
   int im2col;
   int stages;
-  int dbg;  // ME_CONV_DBG bit mask for attribution runs: 1 skip epilogue, 2 skip operand loads, 4 skip MMAs
+  int dbg;  // ME_CONV_DBG bit mask for attribution runs: 1 skip epilogue, 2 skip operand loads, 4 skip MMAs, 32 / 64 skip B / A loads
   const float* bias;
   unsigned long long* debug;
   unsigned long long* trace;  // see conv_gemm.cu
@@ -221,14 +221,19 @@ conv_gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
           if (p.dbg & 2) {  // attribution run: no operand traffic, the barrier protocol stays intact
             if (leader) ptx::mbar_arrive(&full_bar[stage]);
           } else {
-            if (leader) ptx::mbar_arrive_expect_tx(&full_bar[stage], 2 * C::STAGE_BYTES);  // both CTAs' bytes
-            if (p.im2col) {
-              const int r = tap / 3, s = tap - r * 3;
-              ptx::tma_load_im2col_4d_pair(&tmA, full_leader, sa, cb * kBK, cw, ch, cn, (uint16_t)s, (uint16_t)r);
-            } else {
-              ptx::tma_load_2d_pair(&tmA, full_leader, sa, cb * kBK, m0);
+            // attribution bits 32 / 64: no weight (B) / no activation (A) traffic; the stage keeps stale bytes
+            const bool load_a = !(p.dbg & 64), load_b = !(p.dbg & 32);
+            if (leader)
+              ptx::mbar_arrive_expect_tx(&full_bar[stage], 2 * ((load_a ? C::A_BYTES : 0) + (load_b ? C::B_BYTES : 0)));
+            if (load_a) {
+              if (p.im2col) {
+                const int r = tap / 3, s = tap - r * 3;
+                ptx::tma_load_im2col_4d_pair(&tmA, full_leader, sa, cb * kBK, cw, ch, cn, (uint16_t)s, (uint16_t)r);
+              } else {
+                ptx::tma_load_2d_pair(&tmA, full_leader, sa, cb * kBK, m0);
+              }
             }
-            ptx::tma_load_2d_pair(&tmB, full_leader, sb, kb * kBK, nb);
+            if (load_b) ptx::tma_load_2d_pair(&tmB, full_leader, sb, kb * kBK, nb);
           }
           if (++cb == p.kb_per_tap) { cb = 0; ++tap; }
           if (++stage == (uint32_t)p.stages) { stage = 0; phase ^= 1; }
