@@ -58,6 +58,7 @@ struct ConvParams {
   int stages;
   int bres_bytes;  // weight-stationary mode: bytes of the resident weight slab (num_kb * B_BYTES)
   int kps;         // K blocks per pipeline stage (one mbarrier round trip)
+  int prefetch_kb; // weight K blocks prefetched into L2 before griddepcontrol.wait
   int dbg;         // ME_CONV_DBG attribution mask: 1 skip epilogue, 2 skip operand loads, 4 skip MMAs, 16 no stage commits
   const float* bias;
   unsigned long long* debug;  // host-mapped word, written before a watchdog trap
@@ -219,6 +220,13 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
   if (tr && threadIdx.x == 0) tr[1] = clock64();
+  // The weights do not depend on the previous layer: pull this CTA's first weight tiles into L2 while the previous
+  // kernel drains (ME_CONV_PREFETCH=0 disables; p.prefetch_kb = 0).
+  if (warp == 0 && p.prefetch_kb > 0 && ptx::elect_one()) {
+    TileWalk<WS> tw0(p.tiles_m, p.tiles_n);
+    if (tw0.valid())
+      for (int kb = 0; kb < p.prefetch_kb; ++kb) ptx::tma_prefetch_2d(&tmB, kb * BK, tw0.tn * BN);
+  }
   ptx::pdl_wait();  // inputs written by the previous kernel are complete and visible from here on
   if (tr && threadIdx.x == 0) tr[2] = clock64();
 
@@ -579,6 +587,14 @@ int launch(const me_conv_desc* d, const void* x, const void* w, const float* bia
   if (stages > kMaxStages) stages = kMaxStages;
   ME_REQUIRE(stages >= 2, "conv: not enough shared memory for a 2-stage pipeline");
   p.stages = stages;
+  {
+    static int pf = -1;
+    if (pf < 0) {
+      const char* e = getenv("ME_CONV_PREFETCH");
+      pf = (e && e[0] == '0') ? 0 : 1;
+    }
+    p.prefetch_kb = pf ? (p.num_kb < stages * p.kps ? p.num_kb : stages * p.kps) : 0;
+  }
   const int smem = 1024 + p.bres_bytes + stages * p.kps * STAGE + C::EPI_BYTES;
 
   CUtensorMap tmA, tmB, tmC, tmR;

@@ -48,6 +48,7 @@ struct PairParams {
   int has_res;
   int im2col;
   int stages;
+  int prefetch_kb;  // weight K blocks prefetched into L2 before griddepcontrol.wait
   int dbg;  // ME_CONV_DBG bit mask for attribution runs: 1 skip epilogue, 2 skip operand loads, 4 skip MMAs, 32 / 64 skip B / A loads
   const float* bias;
   unsigned long long* debug;
@@ -190,6 +191,12 @@ conv_gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
   if (tr && threadIdx.x == 0) tr[1] = clock64();
+  // weights of the first stages -> L2 while the previous layer drains (see conv_gemm.cu)
+  if (warp == 0 && p.prefetch_kb > 0 && pair < p.tiles_m * p.tiles_n && ptx::elect_one()) {
+    const int tn0 = pair % p.tiles_n;
+    for (int kb = 0; kb < p.prefetch_kb; ++kb)
+      ptx::tma_prefetch_2d(&tmB, kb * kBK, tn0 * BN + static_cast<int>(rank) * (BN / 2));
+  }
   ptx::pdl_wait();
   if (tr && threadIdx.x == 0) tr[2] = clock64();
 
@@ -575,6 +582,14 @@ int launch_pair(const me_conv_desc* d, const void* x, const void* w, const float
   }
   ME_REQUIRE(stages >= 2, "conv(pair): not enough shared memory");
   p.stages = stages;
+  {
+    static int pf = -1;
+    if (pf < 0) {
+      const char* e = getenv("ME_CONV_PREFETCH");
+      pf = (e && e[0] == '0') ? 0 : 1;
+    }
+    p.prefetch_kb = pf ? (p.num_kb < stages ? p.num_kb : stages) : 0;
+  }
   const int smem = C::smem_bytes(stages);
 
   CUtensorMap tmA, tmB, tmC, tmR;
