@@ -18,6 +18,11 @@ module3_our_dataset/):
                     restated in numpy with the semantics probed in SURVEY.md §8a A10/A11
   fusion.py         my_models.py:433-539 (Network.forward, inference branch) and the heads
                     :47-77, :130-157, :176-210, :213-284, :378-391
+  stage3_loss.py    my_models.py:545-640 (labelling + loss branch: obtain_iou_labels :317-375, FocalLoss :287-314,
+                    regression_loss :394-408, sampling, metric)
+  stage3_train.py   one train-mode forward + backward of the fusion heads as train.py:169-186 runs it (torch autograd):
+                    the checker of the backward pass the product does not have yet
+  radar.py          utils/datasets.py:56-106 (radar heat-map) and data_collection/utils/utils.py:81-120 (projection)
   synth.py          deterministic synthetic weights (numpy RandomState) shared by the golden
                     generator and the tests
 

@@ -186,3 +186,36 @@ def test_obtain_iou_labels_rules():
     lab2, _ = s3.obtain_iou_labels(b, t, False)
     assert lab2[0, 0] == 1.0 and lab2[4, 0] == 0.0          # target 0 of the filtered list was claimed by box 0
 
+
+
+def test_stage3_train_step_matches_reference(golden_dir):
+    """Oracle of the (not yet built) stage-3 backward pass: one train-mode forward + backward (train.py:169-186) gives
+    the reference's loss, the gradient of every head parameter and the BatchNorm running statistics after the step
+    (fixture from tests/golden/make_golden_stage3_grads.py; the three large matrices are sub-sampled there)."""
+    import random
+    from millieye_b200.my_models import Network, define_yolo
+    from oracle import stage3_train as st
+    g = np.load(os.path.join(golden_dir, "stage3_grads_tiny12_192.npz"))
+    gl = np.load(os.path.join(golden_dir, "stage3_loss_tiny12_192.npz"))
+    cfg = configs.cfg_path("yolov3-tiny-12")
+    sd = synth.fill_state_dict(Network(define_yolo(cfg), conf_thresh=0.02).state_dict(), seed=6, obj_bias=2.0)
+    random.seed(int(gl["sampling_seed"]))
+    res = st.train_step(parse_model_config(cfg), {k: v.float() if v.is_floating_point() else v for k, v in sd.items()},
+                        synth.synth_images(4, 192, seed=6), synth.synth_maps(4, 192, seed=6),
+                        synth.synth_radar_boxes(4, seed=5), 0.02, gl["targets"])
+    assert abs(res["loss"] - float(g["loss"])) <= 1e-5 * float(g["loss"])
+    assert (res["n_all"], res["true"]) == (int(g["total"]), int(g["true"]))
+    names = [str(n) for n in g["names"]]
+    assert sorted(res["grads"]) == sorted(names)                      # the same parameters receive a gradient (SURVEY F7)
+    for name in names:
+        got = res["grads"][name].numpy()
+        if "grad/" + name in g.files:
+            ref = g["grad/" + name]
+            assert np.abs(got - ref).max() <= 1e-5 * max(1e-12, np.abs(ref).max()), name
+        else:
+            ref, sums = g["gsample/" + name], g["gsum/" + name]
+            assert np.abs(got.reshape(-1)[::37] - ref).max() <= 1e-5 * max(1e-12, np.abs(ref).max()), name
+            assert abs(got.astype(np.float64).sum() - sums[0]) <= 1e-5 * sums[1], name
+    for k in g.files:
+        if k.startswith("buf/"):
+            assert np.abs(res["buffers"][k[4:]].numpy() - g[k]).max() <= 1e-6, k
