@@ -220,3 +220,25 @@ def test_stage3_train_step_matches_reference(golden_dir):
     for k in g.files:
         if k.startswith("buf/"):
             assert np.abs(res["buffers"][k[4:]].numpy() - g[k]).max() <= 1e-6, k
+
+
+def test_yolo_loss_matches_reference(golden_dir):
+    """Oracle of Darknet.forward(x, targets) (the product raises for it): total loss and every entry of
+    the per-layer metrics dictionaries equal the reference's on the fixture of tests/golden/make_golden_yolo_loss.py,
+    which includes two targets that land in the same cell with the same anchor (the last one wins)."""
+    from millieye_b200.models import Darknet
+    from oracle import yolo_loss as yl
+    g = np.load(os.path.join(golden_dir, "yolo_loss_tiny12_160.npz"))
+    cfg = configs.cfg_path("yolov3-tiny-12")
+    sd = synth.fill_state_dict(Darknet(cfg).state_dict(), seed=8, obj_bias=-1.0)
+    with torch.no_grad():
+        loss, feat, yolo, metrics = yl.darknet_loss(parse_model_config(cfg), {k: v.float() if v.is_floating_point() else v
+                                                                              for k, v in sd.items()},
+                                                    synth.synth_images(3, 160, seed=8), torch.from_numpy(g["targets"]))
+    assert abs(float(loss) - float(g["loss"])) <= 1e-5 * float(g["loss"])
+    keys = [str(k) for k in g["metric_keys"]]
+    assert len(metrics) == 2
+    for li, m in enumerate(metrics):
+        for k, r in zip(keys, g[f"metrics{li}"]):
+            assert abs(m[k] - r) <= 1e-5 * max(1.0, abs(r)), (li, k)
+    assert np.abs(yolo.numpy() - g["yolo"]).max() <= 1e-4 and np.abs(feat.numpy() - g["featuremap"]).max() <= 1e-5
