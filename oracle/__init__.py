@@ -22,6 +22,9 @@ module3_our_dataset/):
                     regression_loss :394-408, sampling, metric)
   stage3_train.py   one train-mode forward + backward of the fusion heads as train.py:169-186 runs it (torch autograd):
                     the checker of the backward pass the product does not have yet
+  stage3_backward.py the same step's backward derived by hand, op by op (BatchNorm on batch statistics, conv wgrad /
+                    dgrad, RoIAlign adjoint, heads, losses) - the arithmetic the next round's kernels implement;
+                    checked against stage3_train.py
   yolo_loss.py      yolov3/models.py:180-232 + utils/utils.py:381-440 (YOLO training loss of Darknet.forward(x, targets);
                     checker only - the product does not implement that branch)
   radar.py          utils/datasets.py:56-106 (radar heat-map) and data_collection/utils/utils.py:81-120 (projection)

@@ -242,3 +242,31 @@ def test_yolo_loss_matches_reference(golden_dir):
         for k, r in zip(keys, g[f"metrics{li}"]):
             assert abs(m[k] - r) <= 1e-5 * max(1.0, abs(r)), (li, k)
     assert np.abs(yolo.numpy().reshape(-1)[::97] - g["yolo_sample"]).max() <= 1e-4 and feat.shape == (3, 256, 10, 10)
+
+
+def test_manual_backward_matches_autograd(golden_dir):
+    """oracle/stage3_backward.py (hand-derived backward of the parameters train.py updates: BatchNorm on batch
+    statistics, 3x3 conv wgrad / dgrad by im2col, the RoIAlign adjoint, the radar_net and ensemble heads, focal + BCE
+    loss) against torch.autograd on the same step: every one of the 24 gradients to 1e-4 (or 1e-6 absolute for the
+    conv biases in front of a BatchNorm, whose gradient is zero)."""
+    import random
+    from millieye_b200.my_models import Network, define_yolo
+    from oracle import stage3_backward as sb
+    from oracle import stage3_train as st
+    gl = np.load(os.path.join(golden_dir, "stage3_loss_tiny12_192.npz"))
+    cfg = configs.cfg_path("yolov3-tiny-12")
+    sd = synth.fill_state_dict(Network(define_yolo(cfg), conf_thresh=0.02).state_dict(), seed=6, obj_bias=2.0)
+    sdf = {k: v.float() if v.is_floating_point() else v for k, v in sd.items()}
+    maps = synth.synth_maps(4, 192, seed=6)
+    random.seed(int(gl["sampling_seed"]))
+    res = st.train_step(parse_model_config(cfg), sdf, synth.synth_images(4, 192, seed=6), maps,
+                        synth.synth_radar_boxes(4, seed=5), 0.02, gl["targets"])
+    with torch.no_grad():
+        cache = sb.forward_train(sdf, maps, res["box_locations"], res["n_img"], res["yolo_vec"], res["cls"],
+                                 torch.from_numpy(res["pos"]), torch.from_numpy(res["sample_filter"]))
+        grads = sb.backward(cache)
+    assert abs(cache["loss"] - res["loss"]) <= 1e-5 * res["loss"]
+    assert len(grads) == 24
+    for k, v in grads.items():
+        ref = res["grads"][k]
+        assert float((v - ref).abs().max()) <= 1e-6 + 1e-4 * float(ref.abs().max()), k
