@@ -137,3 +137,74 @@ def test_shard_bounds():
     rows = torch.tensor([[0, 1.0], [3, 2.0], [4, 3.0], [7, 4.0]])
     got = shard_rows_by_frame(rows, 8, 2, 1)
     assert got.tolist() == [[0, 3.0], [3, 4.0]]
+
+
+def test_plan_launch_list_on_cpu(monkeypatch):
+    """DarknetPlan's wiring without a GPU: the library calls are replaced by recorders and the plan is built on CPU
+    tensors, so the launch list of Darknet-53 can be checked for what the kernels rely on - residuals fused into the
+    producing conv and pointing at the shortcut source, route concats written in place through pitch / channel offset,
+    fp32 linear head convs, decode kernels on the post-processing list with the reference's row offsets (models.py:266)."""
+    import torch
+    from millieye_b200 import engine, ops
+    from millieye_b200._lib import ME_ACT_LEAKY, ME_ACT_LINEAR
+    calls = []
+
+    def fake_pack(weight, conv_bias=None, bn=None, cout_pad=None):
+        cout, cin, k, _ = weight.shape
+        pad = cout_pad or ops.round_up(cout, 32)
+        return ops.PackedConv(torch.zeros(1), torch.zeros(1), cin, cout, pad, k)
+
+    monkeypatch.setattr(ops, "pack_conv", fake_pack)
+    monkeypatch.setattr(ops, "pack_first_conv", lambda w, b=None, bn=None: ops.FirstConv.__new__(ops.FirstConv))
+    monkeypatch.setattr(ops, "conv_workspace", lambda dev: torch.zeros(1))
+    monkeypatch.setattr(ops, "conv_set_workspace", lambda ws: None)
+    monkeypatch.setattr(ops, "conv_first", lambda x, f, out, pitch, act: calls.append(("first", out.data_ptr(), pitch, act)))
+    monkeypatch.setattr(ops, "conv_gemm", lambda x, p, n, h, w, in_pitch, out, out_pitch, **kw: calls.append(
+        ("conv", x.data_ptr(), out.data_ptr(), h, in_pitch, out_pitch, kw)))
+    monkeypatch.setattr(ops, "upsample2", lambda x, y, n, h, w, c, ip, op_: calls.append(("up", x.data_ptr(), y.data_ptr(), c, ip, op_)))
+    monkeypatch.setattr(ops, "yolo_decode", lambda logits, pitch, out, n, g, anchors, nc, stride, rows, off: calls.append(
+        ("decode", logits.data_ptr(), g, rows, off, stride)))
+    monkeypatch.delenv("ME_FUSE_DECODE", raising=False)
+
+    net = __import__("millieye_b200.models", fromlist=["Darknet"]).Darknet(configs.cfg_path("yolov3"))
+    tensors = {k: v.detach().float() for k, v in net.state_dict().items() if v.is_floating_point()}
+    plan = engine.DarknetPlan(net._blocks, tensors, 1, 64, torch.device("cpu"), None)
+    assert plan.op_kinds.count("conv") == 75 and plan.op_kinds.count("upsample") == 2 and len(plan.post_ops) == 3
+    assert plan.rows_total == 3 * (2 * 2 + 4 * 4 + 8 * 8)
+    plan.enqueue()
+    plan.enqueue_post()
+    convs = [c for c in calls if c[0] == "conv"]
+    assert len(convs) == 74 and calls[0][0] == "first"
+    out_of = {}                      # output pointer of the conv that produces each cfg block's tensor
+    conv_blocks = [b for b, k in zip(plan.op_blocks, plan.op_kinds) if k == "conv"]
+    for blk, c in zip(conv_blocks[1:], convs):
+        out_of[blk] = c[2]
+    out_of[0] = calls[0][1]
+    n_res = 0
+    for blk, c in zip(conv_blocks[1:], convs):
+        kw = c[6]
+        nxt = plan.blocks[blk + 1] if blk + 1 < len(plan.blocks) else {"type": ""}
+        if nxt["type"] == "shortcut":            # the add is fused: residual = output of block `from` (an alias chain)
+            n_res += 1
+            src = nxt["src"]
+            while plan.blocks[src]["type"] == "shortcut":
+                src -= 1                          # a shortcut's tensor is the tensor of the conv in front of it
+            assert kw["residual"] is not None and kw["residual"].data_ptr() == out_of[src]
+            assert kw["res_pitch"] >= kw["cout"] and c[5] >= kw["cout"]   # (the output may sit in a wider concat buffer)
+        else:
+            assert kw.get("residual") is None
+        if nxt["type"] == "yolo":
+            assert kw["out_f32"] and kw["act"] == ME_ACT_LINEAR and kw["cout"] == 256
+        else:
+            assert not kw["out_f32"]
+    assert n_res == 23
+    # route -1,61 (block 86): the upsample of block 85 and the tensor of block 61 share one 768-channel buffer
+    ups = [c for c in calls if c[0] == "up"]
+    assert ups[0][5] == 768 and ups[1][5] == 384                     # upsample writes with the concat buffer's pitch
+    conv60 = convs[conv_blocks[1:].index(60)]
+    assert conv60[5] == 768 and conv60[2] == ups[0][2] + 2 * 256      # 256 fp16 channels after the upsampled slice
+    conv87 = convs[conv_blocks[1:].index(87)]
+    assert conv87[4] == 768 and conv87[1] == ups[0][2]                # the conv after the route reads the whole buffer
+    dec = [c for c in calls if c[0] == "decode"]
+    assert [(d[2], d[4]) for d in dec] == [(2, 0), (4, 12), (8, 60)] and all(d[3] == plan.rows_total for d in dec)
+    assert [d[5] for d in dec] == [32.0, 16.0, 8.0]
