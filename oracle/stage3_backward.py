@@ -2,8 +2,11 @@
 have to implement.  Test infrastructure only (see oracle/__init__.py); no autograd is used here, and the result is
 checked against oracle/stage3_train.py (torch.autograd, itself pinned bit for bit by the reference's gradients).
 
-Scope: the parameters train.py actually updates in stage 3 (reference module3_our_dataset/train.py:100-149 freezes the
-R-CNN part: img_cnn_layers and refinement_head.net0-2): radar_cnn_layers (three 3x3 conv + BatchNorm + LeakyReLU, one
+Scope: every parameter that receives a gradient.  With --pretrained_module2 train.py freezes the R-CNN part
+(img_cnn_layers and refinement_head.net0-2, reference module3_our_dataset/train.py:117-149) and only the radar / fusion
+set below is updated; without it ("train module2 + module3 from scratch", :111-115) the image path trains too
+(forward_train(..., feat=...) / backward(..., image_path=True): 1x1 conv + BatchNorm + LeakyReLU, the PS-RoIAlign
+adjoint, FC 490->256, FC 256->13 + sigmoid).  Radar / fusion set: radar_cnn_layers (three 3x3 conv + BatchNorm + LeakyReLU, one
 1x1 conv + sigmoid; my_models.py:130-157), refinement_head.radar_net (7x7 conv on the 7x7 crop = a 490->10 linear map,
 BatchNorm over the proposals, LeakyReLU, 1x1 conv, sigmoid; :246-251, 268-276) and ensemble_head (:176-210), for the loss
 of :610-635 (FocalLoss on the image proposals' masks + confidence BCE / 6).  All BatchNorms run on batch statistics.
@@ -101,14 +104,77 @@ def roi_align_backward(grad_out, rois, n, channels, height, width, scale, pooled
     return g.astype(np.float32)
 
 
+def psroi_align_backward(grad_out, rois, n, height, width, scale, pooled=7):
+    """Adjoint of torchvision ps_roi_align (sampling_ratio=-1): output (c, ph, pw) only reads feature channel
+    (c*P + ph)*P + pw inside bin (ph, pw); start = coord*scale - 0.5, size not clamped, count = gh*gw.
+    grad_out (R, C_out, P, P) numpy -> (N, C_out*P*P, H, W)."""
+    c_out = grad_out.shape[1]
+    g = np.zeros((n, c_out * pooled * pooled, height, width), dtype=np.float64)
+    f32 = np.float32
+    ch = (np.arange(c_out)[:, None, None] * pooled + np.arange(pooled)[None, :, None]) * pooled + np.arange(pooled)[None, None, :]
+    for r in range(len(rois)):
+        b = int(rois[r, 0])
+        sw, sh = f32(rois[r, 1]) * f32(scale) - f32(0.5), f32(rois[r, 2]) * f32(scale) - f32(0.5)
+        ew, eh = f32(rois[r, 3]) * f32(scale) - f32(0.5), f32(rois[r, 4]) * f32(scale) - f32(0.5)
+        rw, rh = f32(ew - sw), f32(eh - sh)
+        bin_h, bin_w = f32(rh / f32(pooled)), f32(rw / f32(pooled))
+        gh, gw = int(np.ceil(rh / f32(pooled))), int(np.ceil(rw / f32(pooled)))
+        if gh <= 0 or gw <= 0:
+            continue
+        count = gh * gw
+        for ph in range(pooled):
+            ys = (f32(ph) * bin_h + sh) + (np.arange(gh, dtype=f32) + f32(0.5)) * bin_h / f32(gh)
+            for pw in range(pooled):
+                xs = (f32(pw) * bin_w + sw) + (np.arange(gw, dtype=f32) + f32(0.5)) * bin_w / f32(gw)
+                go = grad_out[r, :, ph, pw].astype(np.float64) / count                 # (C_out,)
+                chans = ch[:, ph, pw]
+                for y in ys:
+                    for x in xs:
+                        if y < -1.0 or y > height or x < -1.0 or x > width:
+                            continue
+                        yy, xx = max(y, f32(0)), max(x, f32(0))
+                        yl, xl = int(yy), int(xx)
+                        if yl >= height - 1:
+                            yl = yh = height - 1
+                            yy = f32(yl)
+                        else:
+                            yh = yl + 1
+                        if xl >= width - 1:
+                            xl = xh = width - 1
+                            xx = f32(xl)
+                        else:
+                            xh = xl + 1
+                        ly, lx = float(yy - yl), float(xx - xl)
+                        hy, hx = 1.0 - ly, 1.0 - lx
+                        g[b, chans, yl, xl] += go * hy * hx
+                        g[b, chans, yl, xh] += go * hy * lx
+                        g[b, chans, yh, xl] += go * ly * hx
+                        g[b, chans, yh, xh] += go * ly * lx
+    return g.astype(np.float32)
+
+
 # ------------------------------------------------------------------------------------------------ forward (train mode)
-def forward_train(sd, maps, box_locations, n_img, yolo_vec, cls_img_path, pos, sample_filter, alpha=0.75, lambda_conf=6.0):
+def forward_train(sd, maps, box_locations, n_img, yolo_vec, cls_img_path, pos, sample_filter, alpha=0.75, lambda_conf=6.0,
+                  feat=None):
     """Radar branch + heads in training mode, keeping what the backward needs.
     sd: fp32 tensors by reference key; maps (N,3,g,g); box_locations (R,5) pixels; cls_img_path (R,13): sigmoid output of
-    refinement_head.net2 (the frozen image path; column 0 enters the confidence); pos / sample_filter: bool (R,)."""
-    from torchvision.ops import roi_align
+    refinement_head.net2 (column 0 enters the confidence) - taken as given (frozen image path) unless `feat`
+    (N,256,g,g), the detector's feature map, is passed: then the image path is run here too and its intermediates are
+    kept for backward(image_path=True); pos / sample_filter: bool (R,)."""
+    from torchvision.ops import ps_roi_align, roi_align
     c = dict(sd=sd, maps=maps, rois=box_locations, n_img=n_img, yolo_vec=yolo_vec, pos=pos, sel=sample_filter, alpha=alpha,
              lam=lambda_conf)
+    if feat is not None:
+        zi = F.conv2d(feat, sd["img_cnn_layers.net.conv_0.weight"], sd["img_cnn_layers.net.conv_0.bias"])
+        yi, xhi, istdi = bn_forward(zi, sd["img_cnn_layers.net.batch_norm_0.weight"], sd["img_cnn_layers.net.batch_norm_0.bias"],
+                                    (0, 2, 3))
+        ai = F.leaky_relu(yi, SLOPE)
+        x_img = ps_roi_align(ai, box_locations, (7, 7), spatial_scale=1. / 16).flatten(1)
+        tp = x_img @ sd["refinement_head.net0.0.weight"].t() + sd["refinement_head.net0.0.bias"]
+        t = F.leaky_relu(tp, SLOPE)
+        cls_img_path = torch.sigmoid(t @ sd["refinement_head.net2.0.weight"].t() + sd["refinement_head.net2.0.bias"])
+        c.update(feat=feat, yi=yi, xhi=xhi, istdi=istdi, x_img=x_img, tp=tp, t=t, map_hw=tuple(ai.shape))
+    c["cls"] = cls_img_path
     a = maps
     c["a0"] = a
     for i, name in enumerate(("conv1", "conv2", "conv3"), 1):
@@ -147,7 +213,7 @@ def forward_train(sd, maps, box_locations, n_img, yolo_vec, cls_img_path, pos, s
 
 
 # ------------------------------------------------------------------------------------------------ backward
-def backward(c):
+def backward(c, image_path=False):
     sd, n_img, pos, sel = c["sd"], c["n_img"], c["pos"], c["sel"]
     grads = {}
     conf = c["conf"][:, 0]
@@ -207,4 +273,27 @@ def backward(c):
         grads[f"{q}{name}.1.weight"], grads[f"{q}{name}.1.bias"] = dg, dbeta
         dw, db, da = conv3x3_backward(dz, c[f"a{i - 1}"], sd[f"{q}{name}.0.weight"], need_input_grad=i > 1)
         grads[f"{q}{name}.0.weight"], grads[f"{q}{name}.0.bias"] = dw, db
+    if not image_path:
+        return grads
+    # ---- image path: conf = sigmoid(rc + cls[:, 0]) and, for image proposals, u[:, 1, 0] = cls[:, 1]
+    cls = c["cls"]
+    dcls = torch.zeros_like(cls)
+    dcls[:, 0] = drc                                                                # same pre-activation as rc
+    dcls[:n_img, 1] = du[:, 1, 0]
+    dz2 = dcls * cls * (1 - cls)
+    r = "refinement_head."
+    grads[r + "net2.0.weight"] = dz2.t() @ c["t"]
+    grads[r + "net2.0.bias"] = dz2.sum(0)
+    dtp = leaky_backward(dz2 @ sd[r + "net2.0.weight"], c["tp"])
+    grads[r + "net0.0.weight"] = dtp.t() @ c["x_img"]
+    grads[r + "net0.0.bias"] = dtp.sum(0)
+    dx_img = (dtp @ sd[r + "net0.0.weight"]).view(R, 10, 7, 7)
+    n, _, hh, ww = c["map_hw"]
+    dai = torch.from_numpy(psroi_align_backward(dx_img.numpy(), c["rois"].numpy(), n, hh, ww, 1. / 16))
+    dyi = leaky_backward(dai, c["yi"])
+    i = "img_cnn_layers.net."
+    dzi, dg, dbeta = bn_backward(dyi, c["xhi"], c["istdi"], sd[i + "batch_norm_0.weight"], (0, 2, 3))
+    grads[i + "batch_norm_0.weight"], grads[i + "batch_norm_0.bias"] = dg, dbeta
+    grads[i + "conv_0.weight"] = torch.einsum("nohw,nchw->oc", dzi, c["feat"]).view_as(sd[i + "conv_0.weight"])
+    grads[i + "conv_0.bias"] = dzi.sum((0, 2, 3))
     return grads

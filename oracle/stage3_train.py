@@ -115,4 +115,4 @@ def train_step(module_defs, sd, images, maps, radar_boxes, conf_thresh, targets,
     grads = {k: v.grad for k, v in params.items() if v.grad is not None}
     return dict(loss=float(loss.item()), grads=grads, buffers=buffers, n_img=n_img, n_all=len(all_boxes), reg=reg.detach(),
                 sample_filter=sample_filter, true=int(pos.sum()), pos=pos, box_locations=box_locations.detach(),
-                yolo_vec=yolo_vec.detach(), cls=cls.detach())
+                yolo_vec=yolo_vec.detach(), cls=cls.detach(), feat=feat.detach())

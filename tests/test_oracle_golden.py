@@ -247,8 +247,9 @@ def test_yolo_loss_matches_reference(golden_dir):
 def test_manual_backward_matches_autograd(golden_dir):
     """oracle/stage3_backward.py (hand-derived backward of the parameters train.py updates: BatchNorm on batch
     statistics, 3x3 conv wgrad / dgrad by im2col, the RoIAlign adjoint, the radar_net and ensemble heads, focal + BCE
-    loss) against torch.autograd on the same step: every one of the 24 gradients to 1e-4 (or 1e-6 absolute for the
-    conv biases in front of a BatchNorm, whose gradient is zero)."""
+    loss; with the image path also the PS-RoIAlign adjoint, FC 490->256 / 256->13 and the 1x1 conv + BatchNorm) against
+    torch.autograd on the same step: every one of the 24 / 32 gradients to 1e-4 (or 1e-6 absolute for the conv biases in
+    front of a BatchNorm, whose gradient is zero)."""
     import random
     from millieye_b200.my_models import Network, define_yolo
     from oracle import stage3_backward as sb
@@ -264,9 +265,13 @@ def test_manual_backward_matches_autograd(golden_dir):
     with torch.no_grad():
         cache = sb.forward_train(sdf, maps, res["box_locations"], res["n_img"], res["yolo_vec"], res["cls"],
                                  torch.from_numpy(res["pos"]), torch.from_numpy(res["sample_filter"]))
-        grads = sb.backward(cache)
-    assert abs(cache["loss"] - res["loss"]) <= 1e-5 * res["loss"]
-    assert len(grads) == 24
-    for k, v in grads.items():
-        ref = res["grads"][k]
-        assert float((v - ref).abs().max()) <= 1e-6 + 1e-4 * float(ref.abs().max()), k
+        grads = sb.backward(cache)                       # the set train.py updates with --pretrained_module2
+        full = sb.forward_train(sdf, maps, res["box_locations"], res["n_img"], res["yolo_vec"], None,
+                                torch.from_numpy(res["pos"]), torch.from_numpy(res["sample_filter"]), feat=res["feat"])
+        grads_all = sb.backward(full, image_path=True)   # training from scratch: the image path too
+    assert abs(cache["loss"] - res["loss"]) <= 1e-5 * res["loss"] and abs(full["loss"] - res["loss"]) <= 1e-5 * res["loss"]
+    assert len(grads) == 24 and sorted(grads_all) == sorted(res["grads"]) and len(grads_all) == 32
+    for got in (grads, grads_all):
+        for k, v in got.items():
+            ref = res["grads"][k]
+            assert float((v - ref).abs().max()) <= 1e-6 + 1e-4 * float(ref.abs().max()), k
