@@ -43,7 +43,9 @@ def _worker(rank, world, port, total, q):
         grows = gather_rows(rows, total // world, cap=64)
         radar = torch.tensor([[0.0, 1], [1, 2], [total - 1, 3]])
         local_radar = shard_rows_by_frame(radar, total, world, rank)
-        q.put((rank, gdet, gcnt, grows, local_radar))
+        # numpy arrays are pickled by value; a torch tensor in an mp.Queue is a shared-memory handle that dies with
+        # the worker, and a worker that exits before the parent unpickles gives a sporadic FileNotFoundError
+        q.put((rank, gdet.numpy(), gcnt.numpy(), grows.numpy(), local_radar.numpy()))
     finally:
         dist.destroy_process_group()
 
@@ -58,6 +60,7 @@ def test_sharded_gather_equals_single_process():
     for p in procs:
         p.start()
     results = sorted([q.get(timeout=90) for _ in range(world)], key=lambda t: t[0])
+    results = [(r[0],) + tuple(torch.from_numpy(a) for a in r[1:]) for r in results]
     for p in procs:
         p.join(30)
         assert p.exitcode == 0
@@ -85,7 +88,7 @@ def _reduce_worker(rank, world, port, q):
             unused.weight.grad = torch.ones_like(unused.weight)   # only one rank has a gradient for it
         n = all_reduce_gradients(list(lin.parameters()) + list(unused.parameters()))
         loss_vec = all_reduce_sum_(torch.arange(10, dtype=torch.float32) * (rank + 1))
-        q.put((rank, n, lin.weight.grad.clone(), unused.weight.grad.clone(), unused.bias.grad.clone(), loss_vec))
+        q.put((rank, n, lin.weight.grad.numpy(), unused.weight.grad.numpy(), unused.bias.grad.numpy(), loss_vec.numpy()))
     finally:
         dist.destroy_process_group()
 
@@ -102,6 +105,7 @@ def test_gradient_bucket_and_loss_reduction():
     for p in procs:
         p.start()
     results = sorted([q.get(timeout=90) for _ in range(world)], key=lambda t: t[0])
+    results = [r[:2] + tuple(torch.from_numpy(a) for a in r[2:]) for r in results]
     for p in procs:
         p.join(timeout=30)
     for rank, n, wgrad, ugrad, ubias, loss_vec in results:
