@@ -318,12 +318,14 @@ def run_gpu(args):
                          ms_per_step=ms_e2e / args.steps),
                 gpu_launches=int(launches_per_step * args.steps),
                 roofline=dict(bound="tensor", achieved=achieved, peak=pk["tflops"], unit="TFLOP/s", frac=achieved / pk["tflops"],
-                              traffic=measured_traffic(), peak_source=pk["src"],
+                              traffic=(measured_traffic() or {}).get("dram_bytes_per_step"), traffic_detail=measured_traffic(),
+                              peak_source=pk["src"],
                               kernel="conv_gemm_kernel / conv_gemm_pair_kernel / conv_first_tc_kernel (tcgen05 implicit GEMM)",
                               launches=n_conv, conv_ms_per_step=conv_ms,
-                              note="achieved = 65.864 GFLOP/frame x 32 frames / device time of the step's conv launches "
-                                   "(74 tcgen05 GEMMs + the tensor-core first conv per sub-batch; the three head convs carry "
-                                   "the fused YOLO decode in their epilogue), CUDA events around graph replays"),
+                              note="achieved = 65.864 GFLOP/frame x 32 frames / device time of the step's 75 conv launches "
+                                   "(74 tcgen05 GEMMs + the tensor-core first conv), CUDA events around replays of a graph "
+                                   "holding only those launches; traffic = DRAM bytes (read + write) of the same 75 launches "
+                                   "per step from the committed ncu capture"),
                 cpu_baseline=cpu)
     emit(line)
     if world > 1:
