@@ -96,6 +96,33 @@ int me_conv_gemm(const me_conv_desc* d, const void* x, const void* w_packed, con
 size_t me_conv_workspace_bytes(void);
 int me_conv_set_workspace(void* dev_workspace, size_t bytes);
 
+/* ---- a run of conv layers as one persistent kernel --------------------------------------------------------------
+ * Darknet.forward walks its module list one layer at a time (yolov3/models.py:247-262); launched that way a third of
+ * the conv time of Darknet-53 was launch gaps, pipeline fill / drain and partial last waves.  me_conv_chain_* runs a
+ * list of layers - each described exactly like a me_conv_gemm call - as ONE persistent kernel of CTA pairs in which a
+ * 256 x BN tile of layer l starts as soon as the tiles of the layers it reads (dep_layer: producer of x, res_layer:
+ * producer of residual; -1 = complete before the launch) have been stored.  Results are those of the per-layer calls.
+ *   eligible:  1x1 / 3x3 stride 1 / 3x3 stride 2, cin % 64 == 0, cout % 128 == 0, fp16 output.
+ *   build:     fills a caller-owned HOST blob (me_conv_chain_blob_bytes long, 128-byte aligned) with the layer table
+ *              (tensor maps), the per-pair work lists and the counter area; the caller copies it to a 256-byte aligned
+ *              DEVICE buffer of the same size once.
+ *   run:       enqueues the counter reset + the kernel on `stream` (graph capturable, no allocation, re-entrant per
+ *              device blob).  Layers must appear in execution order. */
+typedef struct me_chain_layer {
+  me_conv_desc d;
+  const void* x;
+  const void* w_packed;
+  const float* bias;
+  const void* residual;
+  void* y;
+  int dep_layer;
+  int res_layer;
+} me_chain_layer;
+int me_conv_chain_eligible(const me_conv_desc* d);
+size_t me_conv_chain_blob_bytes(const me_chain_layer* layers, int n_layers);
+int me_conv_chain_build(const me_chain_layer* layers, int n_layers, void* host_blob, size_t blob_bytes);
+int me_conv_chain_run(const void* host_blob, void* dev_blob, me_stream_t stream);
+
 /* YOLO head: the linear 1x1 head conv (models.py:252, blocks followed by a [yolo] block) with YOLOLayer.forward's
  * decode (models.py:142-177, see me_yolo_decode) fused into its epilogue: the fp32 logits never go to memory, the
  * decoded rows are written straight into pred [n][rows_total][5+C] at row_offset.  d->out_f32 must be 1, no

@@ -24,6 +24,11 @@ class ConvDesc(Structure):
         "res_pitch")]
 
 
+class ChainLayer(Structure):
+    _fields_ = [("d", ConvDesc), ("x", c_void_p), ("w_packed", c_void_p), ("bias", c_void_p), ("residual", c_void_p),
+                ("y", c_void_p), ("dep_layer", c_int), ("res_layer", c_int)]
+
+
 class HeadWeights(Structure):
     _fields_ = [(n, c_void_p) for n in (
         "net1_w", "net1_b", "net2_w", "net2_b", "radar_w", "radar_b", "radar2_w", "radar2_b",
@@ -56,6 +61,10 @@ SIGNATURES = {
     "me_pack_conv_weights": (c_int, [c_void_p] * 6 + [c_float, c_int, c_int, c_int, c_int, c_void_p, c_void_p,
                                                      c_void_p]),
     "me_conv_gemm": (c_int, [POINTER(ConvDesc), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "me_conv_chain_eligible": (c_int, [POINTER(ConvDesc)]),
+    "me_conv_chain_blob_bytes": (c_size_t, [POINTER(ChainLayer), c_int]),
+    "me_conv_chain_build": (c_int, [POINTER(ChainLayer), c_int, c_void_p, c_size_t]),
+    "me_conv_chain_run": (c_int, [c_void_p, c_void_p, c_void_p]),
     "me_conv_workspace_bytes": (c_size_t, []),
     "me_conv_set_workspace": (c_int, [c_void_p, c_size_t]),
     "me_conv_gemm_yolo": (c_int, [POINTER(ConvDesc), c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, POINTER(c_float),

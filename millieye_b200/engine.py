@@ -124,6 +124,10 @@ class DarknetPlan:
         self._graphs = [None, None]
         self._post_graphs = [None, None]
         self._conv_ws = []
+        self._conv_meta = {}   # op index -> conv launch description
+        self.chains = []       # ops.ConvChain objects (kept alive; the op list holds their run())
+        # ME_CONV_CHAIN=0: one kernel per conv layer (per-layer tools: conv_trace.py, ncu_layers.py)
+        self.use_chains = os.environ.get("ME_CONV_CHAIN", "1") != "0" and torch.device(device).type == "cuda"
         self._slot_free = [None, None]   # event: last forward that read the buffer has finished
         self._out_busy = [None, None]    # event: a consumer on another stream is done with this slot's yolo_out
         self._copy_stream = None
@@ -272,8 +276,84 @@ class DarknetPlan:
             if i == self.feature_tap:
                 self.feature_view = views[i]
         self.views = views
+        if self.use_chains and self.splits == 1:
+            self._form_chains()
         if self.feature_tap is not None and self.feature_view is not None and self.feature_view.buf.dtype != torch.float16:
             raise MeError("feature tap must be an fp16 activation")
+
+    def _form_chains(self):
+        """Groups runs of consecutive chain-eligible conv launches into one persistent kernel each (ops.ConvChain).
+
+        Head convs (their output only feeds the decode kernels) are moved to the end of the launch list first, so
+        the runs they used to interrupt join up: Darknet-53 becomes 9 per-layer launches, three chains (52^2..13^2
+        trunk + first head trunk, 26^2 head trunk, 52^2 head trunk) separated by the two upsamples, and the three
+        head convs."""
+        n_ops = len(self.ops)
+        order = [k for k in range(n_ops) if not self._conv_meta.get(k, {}).get("leaf")] + \
+                [k for k in range(n_ops) if self._conv_meta.get(k, {}).get("leaf")]
+        # producer op of every conv output view: buffer -> [(channel offset, channels, op)]
+        written = {}
+        for k in order:
+            m = self._conv_meta.get(k)
+            if m is not None:
+                o = m["out"]
+                written.setdefault(id(o.buf), []).append((o.off, o.c, k))
+
+        def producers(view):
+            if view is None:
+                return []
+            return [k for (off, c, k) in written.get(id(view.buf), []) if off < view.off + view.c and view.off < off + c]
+
+        def describe(k):
+            m = self._conv_meta[k]
+            sv, o, rv = m["src"], m["out"], m["res"]
+            return ops.conv_desc(m["packed"], self.n, sv.h, sv.w, sv.pitch, o.pitch, stride=m["stride"], act=m["act"],
+                                 res_pitch=0 if rv is None else rv.pitch, cin=m["cin"], cout=m["cout"], out_f32=m["f32"])
+
+        new_ops, new_kinds, new_blocks = [], [], []
+        run = []   # op indices of the chain being collected
+
+        def flush():
+            if len(run) >= 2:
+                pos = {k: j for j, k in enumerate(run)}
+                layers = []
+                for k in run:
+                    m = self._conv_meta[k]
+                    dep = [pos[q] for q in producers(m["src"]) if q in pos]
+                    res = [pos[q] for q in producers(m["res"]) if q in pos]
+                    layers.append(dict(desc=describe(k), x=m["src"].t, packed=m["packed"], y=m["out"].t,
+                                       residual=None if m["res"] is None else m["res"].t,
+                                       dep=dep[0] if dep else -1, res=res[0] if res else -1))
+                chain = ops.ConvChain(layers, self.device)
+                self.chains.append(chain)
+                new_ops.append(lambda b0, nb, c=chain: c.run())
+                new_kinds.append("conv")
+                new_blocks.append([self.op_blocks[k] for k in run])
+            else:
+                for k in run:
+                    new_ops.append(self.ops[k])
+                    new_kinds.append(self.op_kinds[k])
+                    new_blocks.append(self.op_blocks[k])
+            run.clear()
+
+        for k in order:
+            m = self._conv_meta.get(k)
+            ok = m is not None and not m["f32"] and ops.conv_chain_eligible(describe(k))
+            if ok:
+                in_run = set(run)
+                # at most one producer inside the run for the input and for the residual (a concat of two in-run
+                # layers would need two dependencies)
+                if len([q for q in producers(m["src"]) if q in in_run]) > 1 or \
+                        len([q for q in producers(m["res"]) if q in in_run]) > 1:
+                    flush()
+                run.append(k)
+            else:
+                flush()
+                new_ops.append(self.ops[k])
+                new_kinds.append(self.op_kinds[k])
+                new_blocks.append(self.op_blocks[k])
+        flush()
+        self.ops, self.op_kinds, self.op_blocks = new_ops, new_kinds, new_blocks
 
     def _bn_of(self, i):
         p = f"module_list.{i}.batch_norm_{i}."
@@ -318,6 +398,10 @@ class DarknetPlan:
             return
         packed = self._pack(i, b)
         res_v = views[fuse_res] if fuse_res is not None else None
+        # what the chain builder (_form_chains) needs to describe this launch to me_conv_chain_build
+        self._conv_meta[len(self.ops)] = dict(src=src, packed=packed, out=ov, stride=b["stride"], act=act, res=res_v,
+                                              cin=src.real_c if src.real_c != src.c else src.c, cout=packed.cout_pad,
+                                              f32=is_head, leaf=is_head)
         self._add(lambda b0, nb, sv=src, p=packed, o=ov, st=b["stride"], a=act, rv=res_v, f32=is_head: ops.conv_gemm(
             sv.at(b0), p, nb, sv.h, sv.w, sv.pitch, self._slot_view(o).at(b0), o.pitch, stride=st, act=a,
             residual=None if rv is None else rv.at(b0), res_pitch=0 if rv is None else rv.pitch,

@@ -13,7 +13,7 @@ from ._lib import ME_ACT_LEAKY, ME_ACT_LINEAR, ME_ACT_SIGMOID, ConvDesc, HeadWei
 
 __all__ = [
     "ME_ACT_LINEAR", "ME_ACT_LEAKY", "ME_ACT_SIGMOID", "round_up", "PackedConv", "pack_conv", "conv_gemm", "conv_gemm_yolo",
-    "FirstConv", "pack_first_conv", "conv_first", "maxpool2", "upsample2", "copy_channels", "nhwc_to_nchw_f32",
+    "conv_desc", "conv_chain_eligible", "ConvChain", "FirstConv", "pack_first_conv", "conv_first", "maxpool2", "upsample2", "copy_channels", "nhwc_to_nchw_f32",
     "nchw_f32_to_nhwc", "yolo_decode", "filter_nms", "psroi_align", "roi_align", "build_proposals", "fusion_heads",
     "finalize_output",
 ]
@@ -88,6 +88,55 @@ def conv_gemm_yolo(x, packed, n, h, w, in_pitch, pred, g, anchors, num_classes, 
                                        arr, float(yolo_stride), rows_total, row_offset, ptr(pred), stream_ptr()),
           "me_conv_gemm_yolo")
     return pred
+
+
+def conv_desc(packed, n, h, w, in_pitch, out_pitch, stride=1, act=ME_ACT_LEAKY, res_pitch=0, cin=None, cout=None,
+              out_f32=False):
+    return ConvDesc(n=n, h=h, w=w, cin=cin or packed.cin, in_pitch=in_pitch, cout=cout or packed.cout_pad,
+                    out_pitch=out_pitch, ksize=packed.ksize, stride=stride, act=act, out_f32=1 if out_f32 else 0,
+                    res_pitch=res_pitch)
+
+
+def conv_chain_eligible(desc):
+    return bool(_lib.lib().me_conv_chain_eligible(byref(desc)))
+
+
+class ConvChain:
+    """A run of conv layers executed as one persistent kernel (include/millieye_b200.h: me_conv_chain_*).
+
+    layers: list of dicts with desc (ConvDesc), x, packed (PackedConv), y, residual (tensor or None), dep, res (index of
+    the layer in this list that produces x / residual, or -1 when it is complete before the launch)."""
+
+    def __init__(self, layers, device):
+        L = _lib.lib()
+        n = len(layers)
+        arr = (_lib.ChainLayer * n)()
+        self._keep = layers
+        for a, l in zip(arr, layers):
+            _need_cuda(l["x"], l["y"], l.get("residual"))
+            a.d = l["desc"]
+            a.x = l["x"].data_ptr()
+            a.w_packed = l["packed"].w.data_ptr()
+            a.bias = l["packed"].bias.data_ptr()
+            a.residual = l["residual"].data_ptr() if l.get("residual") is not None else None
+            a.y = l["y"].data_ptr()
+            a.dep_layer = l.get("dep", -1)
+            a.res_layer = l.get("res", -1)
+        with torch.cuda.device(device):
+            nbytes = L.me_conv_chain_blob_bytes(arr, n)
+            if nbytes == 0:
+                raise _lib.MeError("me_conv_chain_blob_bytes failed")
+            raw = torch.zeros((nbytes + 128,), dtype=torch.uint8)
+            shift = (-raw.data_ptr()) % 128
+            self.host = raw[shift:shift + nbytes]
+            check(L.me_conv_chain_build(arr, n, ctypes.c_void_p(self.host.data_ptr()), nbytes), "me_conv_chain_build")
+            self.dev = torch.empty((nbytes,), dtype=torch.uint8, device=device)
+            self.dev.copy_(self.host)
+        self.n_layers = n
+
+    def run(self):
+        check(_lib.lib().me_conv_chain_run(ctypes.c_void_p(self.host.data_ptr()), ptr(self.dev), stream_ptr()),
+              "me_conv_chain_run")
 
 
 def conv_workspace(device):

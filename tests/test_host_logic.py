@@ -208,3 +208,61 @@ def test_plan_launch_list_on_cpu(monkeypatch):
     dec = [c for c in calls if c[0] == "decode"]
     assert [(d[2], d[4]) for d in dec] == [(2, 0), (4, 12), (8, 60)] and all(d[3] == plan.rows_total for d in dec)
     assert [d[5] for d in dec] == [32.0, 16.0, 8.0]
+
+
+def test_chain_formation_on_cpu(monkeypatch):
+    """DarknetPlan._form_chains without a GPU: Darknet-53's launch list becomes 8 per-layer launches, three chains
+    (the trunk from the last 104^2 layer down plus the first head trunk, the 26^2 head trunk, the 52^2 head trunk) separated
+    by the two upsamples, and the three fp32 head convs at the end; every chain layer names the layer that produces
+    its input / residual, or -1 when that tensor is complete before the chain starts."""
+    import torch
+    from millieye_b200 import engine, ops
+
+    def fake_pack(weight, conv_bias=None, bn=None, cout_pad=None):
+        cout, cin, k, _ = weight.shape
+        return ops.PackedConv(torch.zeros(1), torch.zeros(1), cin, cout, cout_pad or ops.round_up(cout, 32), k)
+
+    chains = []
+
+    class FakeChain:
+        def __init__(self, layers, device):
+            self.layers = layers
+            chains.append(self)
+
+        def run(self):
+            pass
+
+    def eligible(d):
+        return d.ksize in (1, 3) and d.cin % 64 == 0 and d.cout % 128 == 0 and not d.out_f32
+
+    monkeypatch.setattr(ops, "pack_conv", fake_pack)
+    monkeypatch.setattr(ops, "pack_first_conv", lambda w, b=None, bn=None: ops.FirstConv.__new__(ops.FirstConv))
+    monkeypatch.setattr(ops, "ConvChain", FakeChain)
+    monkeypatch.setattr(ops, "conv_chain_eligible", eligible)
+    net = __import__("millieye_b200.models", fromlist=["Darknet"]).Darknet(configs.cfg_path("yolov3"))
+    tensors = {k: v.detach().float() for k, v in net.state_dict().items() if v.is_floating_point()}
+    plan = engine.DarknetPlan(net._blocks, tensors, 1, 64, torch.device("cpu"), None)
+    assert not plan.use_chains and len(plan.ops) == 77          # no GPU: one launch per layer
+    plan._form_chains()
+    kinds = plan.op_kinds
+    assert kinds.count("upsample") == 2 and len(chains) == 3
+    sizes = [len(c.layers) for c in chains]
+    assert sum(sizes) + 8 + 3 == 75                              # every conv is launched exactly once
+    assert sizes == [51, 7, 6]
+    # launch order: 8 early layers, chain, upsample, chain, upsample, chain, 3 heads
+    assert [isinstance(b, list) for b in plan.op_blocks] == [False] * 8 + [True, False, True, False, True] + [False] * 3
+    assert kinds[-3:] == ["conv"] * 3 and [plan.blocks[b + 1]["type"] for b in plan.op_blocks[-3:]] == ["yolo"] * 3
+    for c in chains:
+        for j, l in enumerate(c.layers):
+            assert l["dep"] < j and l["res"] < j
+            if l["dep"] >= 0:                                    # the producer writes exactly what this layer reads
+                assert c.layers[l["dep"]]["y"].data_ptr() == l["x"].data_ptr()
+            if l["residual"] is not None and l["res"] >= 0:
+                assert c.layers[l["res"]]["y"].data_ptr() == l["residual"].data_ptr()
+    first = chains[0].layers
+    assert first[0]["dep"] == -1 and first[0]["res"] == -1 and first[0]["residual"] is not None   # 104^2 3x3 64->128 + shortcut
+    assert first[1]["desc"].stride == 2 and first[1]["desc"].cout == 256
+    assert [l["dep"] for l in first[1:50]] == list(range(49))    # a straight line down to the last 13^2 trunk conv
+    assert first[50]["dep"] == 48 and first[50]["desc"].cout == 256   # route -4: the 1x1 in front of the upsample
+    assert sum(1 for l in first if l["residual"] is not None) == 21   # 1 + 8 + 8 + 4 residual blocks
+    assert all(l["dep"] == -1 for l in (chains[1].layers[0], chains[2].layers[0]))   # they read concat buffers
