@@ -56,12 +56,15 @@ def emit(line):
 
 
 def peaks():
+    """Roofline denominators: the driver-measured MEASURED_PEAKS.json (burst = cuBLAS bf16 timed alone, sustained = the
+    same GEMM looped for seconds under the power cap), else the profiling recipe's fallback."""
     path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(path):
         with open(path) as fh:
             p = json.load(fh)
-        return dict(hbm_gbs=p["hbm_gbs"], tflops=p.get("bf16_tflops_sustained", p["bf16_tflops"]), src="measured (sustained)")
-    return dict(hbm_gbs=6650.0, tflops=1400.0, src="fallback")
+        return dict(hbm_gbs=p["hbm_gbs"], burst=p["bf16_tflops"], sustained=p.get("bf16_tflops_sustained", p["bf16_tflops"]),
+                    src="measured")
+    return dict(hbm_gbs=6650.0, burst=1590.0, sustained=1400.0, src="fallback")
 
 
 def measured_traffic():
@@ -132,8 +135,29 @@ def build_models(device):
     return net, sd
 
 
+def reference_step_fn(threads, batch):
+    """The UNMODIFIED reference (baseline/_ref, staged by baseline/stage_reference.py) on the same step: its own
+    Darknet.forward + non_max_suppression_cpp, same weights recipe and input distribution as the GPU arm."""
+    from baseline import ref_runner
+    from millieye_b200 import configs
+    from millieye_b200.models import Darknet
+    from oracle import synth
+    sd = synth.fill_state_dict(Darknet(configs.cfg_path(CFG)).state_dict(), seed=0, conv_gain=0.6, **WEIGHTS)
+    x = synth.synth_images(batch, SIZE, seed=0)
+    return ref_runner.darknet53_step_fn(sd, x, CONF_THRESH, threads)
+
+
+def reference_available():
+    try:
+        from baseline import ref_runner
+        return ref_runner.available()
+    except Exception:  # noqa: BLE001
+        return False
+
+
 def cpu_forward_fn(threads):
-    """The reference's CPU path for the same step (oracle port: torch CPU fp32 ops + torchvision NMS)."""
+    """The reference's CPU path for the same step (oracle port: torch CPU fp32 ops + torchvision NMS); only used when
+    the verbatim reference is not staged under baseline/_ref."""
     from millieye_b200 import configs
     from millieye_b200.models import Darknet
     from oracle import boxes as obox
@@ -157,23 +181,92 @@ def run_reference(args):
     if rank != 0:
         return
     threads = os.cpu_count() or 1
-    step = cpu_forward_fn(threads)
-    for _ in range(min(args.warmup, 2)):
+    use_ref = reference_available() and not os.environ.get("ME_BENCH_PORT")
+    if use_ref:
+        # the reference itself at the full batch: one step = 32 frames, like the GPU arm
+        batch, kind = BATCH, "reference"
+        step = reference_step_fn(threads, batch)
+        what = "the unmodified reference (baseline/_ref): Darknet.forward + non_max_suppression_cpp"
+    else:
+        batch, kind = CPU_BATCH, "port"
+        step = cpu_forward_fn(threads)
+        what = "oracle port (baseline/_ref not staged)"
+    warm = min(args.warmup, 1 if use_ref else 2)
+    for _ in range(warm):
         step()
     t0 = time.perf_counter()
     for _ in range(args.steps):
         step()
     dt = time.perf_counter() - t0
-    fps = CPU_BATCH * args.steps / dt
-    sample = (f"Darknet-53 forward + decode + NMS, fp32, batch {CPU_BATCH} per step (bounded sample of the batch-{BATCH} "
-              f"workload), torch CPU ops on {threads} threads")
+    fps = batch * args.steps / dt
+    sample = (f"{what}; Darknet-53 forward + decode + NMS, fp32, batch {batch} per step, {args.steps} steps, torch CPU ops "
+              f"on {threads} threads")
     line = dict(impl="reference", metric=METRIC, value=fps, unit="frames/s", n_gpus=args.gpus, steps=args.steps,
-                warmup=min(args.warmup, 2), ms_per_step=dt / args.steps * 1e3, higher_is_better=True, scaling="weak",
+                warmup=warm, ms_per_step=dt / args.steps * 1e3, higher_is_better=True, scaling="weak",
                 vs_baseline=None, dtype="f32", data="synthetic",
-                config=dict(workload=f"Darknet-53 YOLOv3 inference, batch {BATCH}, {SIZE}x{SIZE}", cpu_sample_batch=CPU_BATCH),
-                cpu_baseline=dict(value=fps, unit="frames/s", cores=threads, kind="port", sample=sample),
+                config=dict(workload=f"Darknet-53 YOLOv3 inference (forward + decode + conf filter + NMS), batch {BATCH} per "
+                                     f"step, {SIZE}x{SIZE}", cpu_sample_batch=batch, same_config=batch == BATCH,
+                            conf_thresh=CONF_THRESH),
+                cpu_baseline=dict(value=fps, unit="frames/s", cores=threads, kind=kind, sample=sample),
                 e2e=dict(value=fps, unit="frames/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0))
     emit(line)
+
+
+def check_parity(host_batch, rec, frames):
+    """Detections of the first `frames` frames of a timed batch (as read back by the e2e arm) against the CPU oracle on
+    the same images and weights: survivors are matched row by row (same class, IoU >= 0.9 with an unused oracle row);
+    reports how many rows match and the box / score errors over the matched rows (north_star: 1e-3 relative)."""
+    import numpy as np
+    from millieye_b200 import configs
+    from millieye_b200.models import Darknet
+    from oracle import boxes as obox
+    from oracle import darknet as odark
+    from oracle import synth
+    from oracle.parse_config import parse_model_config
+    try:
+        md = parse_model_config(configs.cfg_path(CFG))
+        sd = synth.fill_state_dict(Darknet(configs.cfg_path(CFG)).state_dict(), seed=0, conv_gain=0.6, **WEIGHTS)
+        x = host_batch[:frames].clone()
+        with torch.no_grad():
+            _, y = odark.darknet_forward(md, sd, x)
+        ref = obox.non_max_suppression_cpp(y.clone().numpy(), CONF_THRESH, use_torchvision=True)
+        det = rec.host_det.numpy()
+        cnt = rec.host_cnt.numpy()
+        rows_ref = rows_gpu = matched = exact_order = 0
+        box_err = score_err = 0.0
+        for f in range(frames):
+            r = ref[f] if ref[f] is not None else np.zeros((0, det.shape[2]), np.float32)
+            r = np.asarray(r)
+            g = det[f, :cnt[f]]
+            rows_ref += len(r)
+            rows_gpu += len(g)
+            used = np.zeros(len(r), bool)
+            for i, row in enumerate(g):
+                best, bj = 0.0, -1
+                for j, rr in enumerate(r):
+                    if used[j] or rr[6] != row[6]:
+                        continue
+                    ix = max(0.0, min(row[2], rr[2]) - max(row[0], rr[0]))
+                    iy = max(0.0, min(row[3], rr[3]) - max(row[1], rr[1]))
+                    inter = ix * iy
+                    u = (row[2] - row[0]) * (row[3] - row[1]) + (rr[2] - rr[0]) * (rr[3] - rr[1]) - inter
+                    iou = inter / u if u > 0 else 0.0
+                    if iou > best:
+                        best, bj = iou, j
+                if bj >= 0 and best >= 0.9:
+                    used[bj] = True
+                    matched += 1
+                    exact_order += int(bj == i)
+                    rr = r[bj]
+                    scale = max(abs(rr[2] - rr[0]), abs(rr[3] - rr[1]), 1.0)
+                    box_err = max(box_err, float(np.abs(row[:4] - rr[:4]).max() / scale))
+                    score_err = max(score_err, float(np.abs(row[4:6] - rr[4:6]).max()))
+        return dict(checked=True, frames=frames, rows_oracle=rows_ref, rows_gpu=rows_gpu, rows_matched=matched,
+                    rows_same_rank=exact_order, max_box_err_rel=box_err, max_score_err_abs=score_err,
+                    tolerance=1e-3, within_tolerance=bool(matched == rows_ref == rows_gpu and box_err <= 1e-3 and score_err <= 1e-3),
+                    how="oracle (CPU fp32 restatement of the reference) on the same images / weights; rows matched by class and IoU >= 0.9")
+    except Exception as e:  # noqa: BLE001
+        return dict(checked=False, error=str(e)[:200])
 
 
 def run_gpu(args):
@@ -252,8 +345,12 @@ def run_gpu(args):
     rec = last["rec"].wait()
     counts = rec.host_cnt.tolist()
 
-    # conv-only time: the same launch list without decode / NMS, for the tensor roofline
-    conv_ms = None
+    # conv-only time: the same launch list without decode / NMS, for the tensor roofline.  Two measurements:
+    #  burst     - a few replays (tens of ms, boost clock): compared with the burst peak (a kernel timed alone)
+    #  sustained - replays for >= 2 s with their own clock record: compared with the sustained peak (cuBLAS looped for
+    #              seconds under the power cap), so the denominator matches how the numerator was taken
+    conv_ms = conv_ms_long = None
+    clocks_long = None
     if rank == 0:
         conv_ops = {i for i, b in enumerate(_op_kinds(plan)) if b == "conv"}
         torch.cuda.synchronize()
@@ -270,6 +367,23 @@ def run_gpu(args):
         torch.cuda.synchronize()
         conv_ms = e0.elapsed_time(e1) / reps
         n_conv = len(conv_ops) * plan.splits
+        if not args.no_sustained:
+            reps_long = max(reps, int(2200.0 / conv_ms) + 1)
+            s2 = ClockSampler(local)
+            s2.start()
+            e0.record()
+            for _ in range(reps_long):
+                g.replay()
+            e1.record()
+            torch.cuda.synchronize()
+            clocks_long = s2.stop()
+            clocks_long["seconds"] = e0.elapsed_time(e1) * 1e-3
+            conv_ms_long = e0.elapsed_time(e1) / reps_long
+
+    # parity of what was timed: the detections of the last e2e batch's first frames against the CPU oracle
+    parity = None
+    if rank == 0 and not args.no_parity:
+        parity = check_parity(host[(args.steps - 1) % n_inputs], rec, 4)
 
     if world > 1:
         dist.barrier()
@@ -282,24 +396,48 @@ def run_gpu(args):
     flops_frame = odark.conv_flops(parse_model_config(configs.cfg_path(CFG)), SIZE)
     fps = world * BATCH * args.steps / ms_dev * 1e3
     fps_e2e = world * BATCH * args.steps / ms_e2e * 1e3
-    achieved = flops_frame * BATCH / (conv_ms * 1e-3) / 1e12
+    achieved_burst = flops_frame * BATCH / (conv_ms * 1e-3) / 1e12
+    achieved_long = flops_frame * BATCH / (conv_ms_long * 1e-3) / 1e12 if conv_ms_long else None
     h2d = BATCH * 3 * SIZE * SIZE * 4
     d2h = rec.host_det.numel() * 4 + rec.host_cnt.numel() * 4
 
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
         threads = os.cpu_count() or 1
-        cstep = cpu_forward_fn(threads)
+        use_ref = reference_available() and not os.environ.get("ME_BENCH_PORT")
+        cb = BATCH if use_ref else CPU_BATCH
+        cstep = reference_step_fn(threads, cb) if use_ref else cpu_forward_fn(threads)
         cstep()
         t0 = time.perf_counter()
         it = 0
-        while it < 2 or (time.perf_counter() - t0 < 10.0 and it < 50):
+        while it < 2 or (time.perf_counter() - t0 < 12.0 and it < 50):
             cstep()
             it += 1
         dt = time.perf_counter() - t0
-        cpu = dict(value=CPU_BATCH * it / dt, unit="frames/s", cores=threads, kind="port",
-                   sample=f"{it} x Darknet-53 forward+decode+NMS at batch {CPU_BATCH}, fp32, torch CPU ops, {threads} threads, "
-                          f"{dt:.1f} s")
+        cpu = dict(value=cb * it / dt, unit="frames/s", cores=threads, kind="reference" if use_ref else "port",
+                   sample=f"{it} x Darknet-53 forward+decode+NMS at batch {cb}, fp32, "
+                          + ("the unmodified reference (baseline/_ref)" if use_ref else "oracle port")
+                          + f", torch CPU ops, {threads} threads, {dt:.1f} s")
+
+    # Headline fraction: the >= 2 s replay against the sustained peak when it was taken (same regime on both sides),
+    # else the short replay against the burst peak; both pairs are always reported.
+    if achieved_long is not None:
+        achieved, peak, basis = achieved_long, pk["sustained"], "sustained (>= 2 s replay vs sustained peak)"
+    else:
+        achieved, peak, basis = achieved_burst, pk["burst"], "burst (short replay vs burst peak)"
+    roofline = dict(bound="tensor", achieved=achieved, peak=peak, unit="TFLOP/s", frac=achieved / peak, basis=basis,
+                    achieved_burst=achieved_burst, peak_burst=pk["burst"], frac_burst=achieved_burst / pk["burst"],
+                    achieved_sustained=achieved_long, peak_sustained=pk["sustained"],
+                    frac_sustained=(achieved_long / pk["sustained"]) if achieved_long else None,
+                    clocks_sustained=clocks_long,
+                    traffic=(measured_traffic() or {}).get("dram_bytes_per_step"), traffic_detail=measured_traffic(),
+                    peak_source=pk["src"],
+                    kernel="conv_chain_kernel / conv_gemm_kernel / conv_gemm_pair_kernel / conv_first_tc_kernel (tcgen05 implicit GEMM)",
+                    launches=n_conv, conv_ms_per_step=conv_ms, conv_ms_per_step_sustained=conv_ms_long,
+                    note="achieved = 65.864 GFLOP/frame x 32 frames / device time of the step's conv launches (all 75 conv "
+                         "layers: per-layer tcgen05 GEMMs, the tensor-core first conv and the persistent multi-layer chain "
+                         "kernels), CUDA events around replays of a graph holding only those launches; traffic = DRAM bytes "
+                         "(read + write) of the conv launches per step from the committed ncu capture")
 
     line = dict(metric=METRIC, value=fps, unit="frames/s", n_gpus=world, steps=args.steps, warmup=max(args.warmup, 3),
                 ms_per_step=ms_dev / args.steps, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f16",
@@ -317,15 +455,7 @@ def run_gpu(args):
                 e2e=dict(value=fps_e2e, unit="frames/s", h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h,
                          ms_per_step=ms_e2e / args.steps),
                 gpu_launches=int(launches_per_step * args.steps),
-                roofline=dict(bound="tensor", achieved=achieved, peak=pk["tflops"], unit="TFLOP/s", frac=achieved / pk["tflops"],
-                              traffic=(measured_traffic() or {}).get("dram_bytes_per_step"), traffic_detail=measured_traffic(),
-                              peak_source=pk["src"],
-                              kernel="conv_gemm_kernel / conv_gemm_pair_kernel / conv_first_tc_kernel (tcgen05 implicit GEMM)",
-                              launches=n_conv, conv_ms_per_step=conv_ms,
-                              note="achieved = 65.864 GFLOP/frame x 32 frames / device time of the step's 75 conv launches "
-                                   "(74 tcgen05 GEMMs + the tensor-core first conv), CUDA events around replays of a graph "
-                                   "holding only those launches; traffic = DRAM bytes (read + write) of the same 75 launches "
-                                   "per step from the committed ncu capture"),
+                roofline=roofline, parity_checked=bool(parity and parity.get("checked")), parity=parity,
                 cpu_baseline=cpu)
     emit(line)
     if world > 1:
@@ -344,6 +474,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-sustained", action="store_true", help="skip the >= 2 s conv-only replay")
+    ap.add_argument("--no-parity", action="store_true", help="skip the oracle check of the timed detections")
     args = ap.parse_args()
     quiet_stdout()
     if args.impl == "reference":

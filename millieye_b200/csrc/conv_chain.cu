@@ -447,10 +447,15 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) conv_ch
           ptx::tma_store_wait_read0();    // the staging tile has been read
         }
         const int next = __ldg(wl + i + 1);
-        if (next >= 0) hand_over(next);
+        // The next tile's residual may be (or depend on) the tile just stored: publish first in that case, or the
+        // wait inside hand_over() would wait for this very thread.  Otherwise the staging tile is handed over first
+        // and the wait for the store's completion stays off the epilogue's critical path.
+        const bool next_waits = next >= 0 && p.layers[next >> kItemShift].has_res && p.layers[next >> kItemShift].res_base >= 0;
+        if (next >= 0 && !next_waits) hand_over(next);
         ptx::tma_store_wait_all0();       // the tile is in memory
         fence_proxy_async_all();
         publish_counter(p.counters + L->ctr_base + tm);
+        if (next_waits) hand_over(next);
       }
     }
     __syncwarp();
