@@ -32,6 +32,7 @@
 namespace me {
 
 unsigned long long* conv_debug_word();   // conv_gemm.cu
+unsigned long long* conv_trace_buffer();
 int conv_ensure_debug_word();
 bool conv_pdl_enabled();
 
@@ -88,7 +89,20 @@ struct ChainParams {
   int stages;
   int* counters;
   unsigned long long* debug;
+  unsigned long long* trace;   // me_conv_set_trace: 16 words per CTA (tools/chain_trace.py), else nullptr
 };
+
+// wait with the cycles spent in it added to `acc` when tracing
+#define ME_CHAIN_TRACED(acc, stmt)        \
+  do {                                    \
+    if (tr) {                             \
+      const long long t_ = clock64();     \
+      stmt;                               \
+      (acc) += clock64() - t_;            \
+    } else {                              \
+      stmt;                               \
+    }                                     \
+  } while (0)
 
 __device__ __forceinline__ void watchdog_trap(unsigned long long* dbg, uint32_t tag, uint32_t aux) {
   if (dbg) {
@@ -171,6 +185,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) conv_ch
   const bool leader = rank == 0;
   const int pair = static_cast<int>(ptx::cluster_id_x());
   const int* wl = p.work + static_cast<size_t>(pair) * p.work_stride;
+  unsigned long long* tr = p.trace ? p.trace + 16ull * blockIdx.x : nullptr;
+  if (tr && threadIdx.x == 0) tr[0] = clock64();
 
   ptx::pdl_launch_dependents();
   if (warp == 1) {
@@ -200,11 +216,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) conv_ch
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
   ptx::pdl_wait();
+  if (tr && threadIdx.x == 0) tr[1] = clock64();
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer (both CTAs)
     if (ptx::elect_one()) {
       uint32_t stage = 0, phase = 0;
+      long long w_dep = 0, w_empty = 0;
       int cur = -1;
       const ChainLayer* L = nullptr;
       for (int i = 0;; ++i) {
@@ -235,7 +253,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) conv_ch
         bool deps_ok = L->dep_kind < 0;
         int tap = 0, cb = 0;
         for (int kb = 0; kb < num_kb; ++kb) {
-          mbar_wait(&empty_bar[stage], phase ^ 1, p.debug, 0x100u + stage);
+          ME_CHAIN_TRACED(w_empty, mbar_wait(&empty_bar[stage], phase ^ 1, p.debug, 0x100u + stage));
           uint8_t* sa = stage_base + stage * kStageBytes;
           uint8_t* sb = sa + kABytes;
           const uint32_t full_leader = ptx::mapa(ptx::smem_u32(&full_bar[stage]), 0);
@@ -248,7 +266,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) conv_ch
             int lo, hi;
             dep_rows(*L, m0, m1, &lo, &hi);
             for (int t = lo / (2 * kBM); t <= hi / (2 * kBM); ++t)
-              wait_counter(p.counters + L->dep_base + t, L->dep_target, p.debug, 0x700u);
+              ME_CHAIN_TRACED(w_dep, wait_counter(p.counters + L->dep_base + t, L->dep_target, p.debug, 0x700u));
             fence_proxy_async_all();
             deps_ok = true;
           }
@@ -262,6 +280,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) conv_ch
           if (++stage == (uint32_t)p.stages) { stage = 0; phase ^= 1; }
         }
       }
+      if (tr) { tr[2] = w_dep; tr[3] = w_empty; tr[4] = clock64(); }
     }
     __syncwarp();
   } else if (warp == 1) {
@@ -270,6 +289,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) conv_ch
       uint32_t stage = 0, phase = 0;
       int cur = -1, num_kb = 0;
       uint32_t idesc = 0;
+      long long w_full = 0, w_acc = 0, t_first = 0;
+      int n_items = 0;
       for (int it = 0;; ++it) {
         const int item = __ldg(wl + it);
         if (item < 0) break;
@@ -281,11 +302,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) conv_ch
         }
         const int acc = it & 1;
         const uint32_t acc_phase = (it >> 1) & 1;
-        mbar_wait(&tmem_empty[acc], acc_phase ^ 1, p.debug, 0x200u + acc);
+        ME_CHAIN_TRACED(w_acc, mbar_wait(&tmem_empty[acc], acc_phase ^ 1, p.debug, 0x200u + acc));
         ptx::tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * kAccStride;
+        ++n_items;
         for (int kb = 0; kb < num_kb; ++kb) {
-          mbar_wait(&full_bar[stage], phase, p.debug, 0x300u + stage);
+          ME_CHAIN_TRACED(w_full, mbar_wait(&full_bar[stage], phase, p.debug, 0x300u + stage));
+          if (tr && t_first == 0) { t_first = clock64(); w_full = 0; }
           ptx::tc_fence_after();
           const uint32_t a_addr = ptx::smem_u32(stage_base + stage * kStageBytes);
           const uint32_t b_addr = a_addr + kABytes;
@@ -300,6 +323,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) conv_ch
         }
         ptx::umma_commit_pair(&tmem_full[acc], 0b11);       // accumulator ready in both CTAs
       }
+      if (tr) { tr[5] = w_full; tr[6] = w_acc; tr[7] = t_first; tr[8] = clock64(); tr[14] = n_items; }
     }
     __syncwarp();
   } else if (warp < 2 + kEpiThreads / 32) {
@@ -310,6 +334,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) conv_ch
     const int etid = threadIdx.x - 64;
     int cur = -1, bn = 0, tiles_n = 1, act = 0, has_res = 0;
     const float* bias = nullptr;
+    const bool eleader = threadIdx.x == 64;
+    long long w_tfull = 0, w_stg = 0;
+    if (!eleader) tr = nullptr;
     for (int it = 0;; ++it) {
       const int item = __ldg(wl + it);
       if (item < 0) break;
@@ -330,9 +357,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) conv_ch
       ptx::named_bar_sync(kEpiBarrierId, kEpiThreads);   // everybody is done with the previous tile's bias
       for (int k = etid; k < bn; k += kEpiThreads) s_bias[k] = __ldg(bias + n0 + k);
       ptx::named_bar_sync(kEpiBarrierId, kEpiThreads);
-      mbar_wait(&tmem_full[acc], acc_phase, p.debug, 0x400u + acc);
+      ME_CHAIN_TRACED(w_tfull, mbar_wait(&tmem_full[acc], acc_phase, p.debug, 0x400u + acc));
       ptx::tc_fence_after();
-      mbar_wait(stg_ready, it & 1, p.debug, 0x500u);
+      ME_CHAIN_TRACED(w_stg, mbar_wait(stg_ready, it & 1, p.debug, 0x500u));
 
       const int c_base = half * (bn / 2);
       const int nch = bn / 64;   // 32-column chunks per warp: 2 or 4
@@ -397,6 +424,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) conv_ch
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(&stg_full[it & 1]);
     }
+    if (tr) { tr[9] = w_tfull; tr[10] = w_stg; tr[12] = clock64(); }
   } else {
     // ------------------------------------------------------------------ store warps (alternating tiles)
     const int w = warp - (2 + kEpiThreads / 32);
@@ -464,6 +492,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) conv_ch
   ptx::tc_fence_before();
   ptx::cluster_sync();  // the peer may still be reading our barriers / issuing MMAs on our TMEM
   ptx::tc_fence_after();
+  if (p.trace && threadIdx.x == 0) p.trace[16ull * blockIdx.x + 13] = clock64();
   if (warp == 1) ptx::tmem_dealloc_pair(tmem_base, kTmemCols);
 }
 
@@ -720,6 +749,7 @@ int me_conv_chain_run(const void* host_blob, void* dev_blob, me_stream_t stream_
   p.stages = H->stages;
   p.counters = reinterpret_cast<int*>(dbase + H->counters_off);
   p.debug = conv_debug_word();
+  p.trace = conv_trace_buffer();
   int dev = 0;
   ME_CUDA(cudaGetDevice(&dev));
   static bool attr_set[64] = {false};

@@ -27,37 +27,75 @@ def shard_rows_by_frame(rows, total, world_size, rank):
     return out
 
 
-def gather_detections(det, count, group=None):
-    """det (n_local, max_det, cols), count (n_local,) int32 -> the same for the whole batch on every rank.
-    Shards must have equal n_local (pad the batch otherwise); one all_gather per tensor."""
+_GATHER_OUT = {}      # (device, dtype, numel, world) -> pre-allocated all_gather output
+_SHAPE_CHECKED = set()
+
+
+def _check_equal_shards(n_local, group):
+    """all_gather_into_tensor needs the same shard shape on every rank; checked once per (group, n_local)."""
+    key = (id(group), n_local)
+    if key in _SHAPE_CHECKED:
+        return
+    world = dist.get_world_size(group)
+    dev = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend(group) == "nccl" else torch.device("cpu")
+    mine = torch.tensor([n_local], dtype=torch.int64, device=dev)
+    every = torch.zeros((world,), dtype=torch.int64, device=dev)
+    dist.all_gather_into_tensor(every, mine, group=group)
+    if not bool((every == n_local).all()):
+        raise ValueError(f"gather_detections: shards hold {every.tolist()} frames; pad the batch so that every rank "
+                         "runs the same number of frames")
+    _SHAPE_CHECKED.add(key)
+
+
+def gather_detections(det, count, group=None, packed=None):
+    """det (n_local, max_det, cols) fp32, count (n_local,) int32 -> the same for the whole batch on every rank, with
+    ONE collective: counts travel in the same buffer as the rows (bit-cast to fp32) and the output is a
+    pre-allocated tensor (all_gather_into_tensor; no list form, no cat).  `packed`: the flat fp32 buffer det and count
+    are views of (ops.NmsBuffers.flat) - without it the two are packed with one copy.  Every rank must hold the same
+    n_local (checked once per shape); the returned tensors are views of a buffer that the next call overwrites."""
     world = dist.get_world_size(group)
     if world == 1:
         return det, count
-    dets = [torch.empty_like(det) for _ in range(world)]
-    counts = [torch.empty_like(count) for _ in range(world)]
-    dist.all_gather(dets, det.contiguous(), group=group)
-    dist.all_gather(counts, count.contiguous(), group=group)
-    return torch.cat(dets, 0), torch.cat(counts, 0)
+    n, max_det, cols = det.shape
+    _check_equal_shards(n, group)
+    body = n * max_det * cols
+    if packed is None or packed.numel() != body + n or packed.data_ptr() != det.data_ptr():
+        packed = torch.cat((det.reshape(-1), count.view(torch.float32).reshape(-1)))
+    key = (packed.device, packed.numel(), world, id(group))
+    out = _GATHER_OUT.get(key)
+    if out is None:
+        # flat (concatenation along dim 0): the layout both NCCL and gloo accept for all_gather_into_tensor
+        out = _GATHER_OUT[key] = torch.empty((world * packed.numel(),), dtype=torch.float32, device=packed.device)
+    dist.all_gather_into_tensor(out, packed.reshape(-1), group=group)
+    out2 = out.view(world, packed.numel())
+    # one strided copy per tensor (the rows of the ranks are not adjacent in the gathered buffer)
+    gdet = out2[:, :body].reshape(world * n, max_det, cols)
+    gcount = out2[:, body:].view(torch.int32).reshape(world * n)
+    return gdet, gcount
 
 
-def gather_rows(rows, frames_per_rank, cap, group=None):
+def gather_rows(rows, total_frames, cap, group=None):
     """Variable-length (k, cols) result rows whose column 0 is a local frame index -> all ranks' rows with
-    global frame indices, in rank order.  Two-phase: counts, then payload padded to `cap` rows."""
+    global frame indices, in rank order.  `total_frames` is the size of the whole batch: this rank's first global
+    frame is shard_bounds(total_frames, world, rank)[0], also for uneven shards.  Two-phase: counts, then payload
+    padded to `cap` rows."""
     world = dist.get_world_size(group)
     rank = dist.get_rank(group)
     if world == 1:
         return rows
     k = torch.tensor([rows.shape[0]], dtype=torch.int64, device=rows.device)
-    ks = [torch.zeros_like(k) for _ in range(world)]
-    dist.all_gather(ks, k, group=group)
-    if int(max(v.item() for v in ks)) > cap:
+    ks = torch.zeros((world,), dtype=torch.int64, device=rows.device)
+    dist.all_gather_into_tensor(ks, k, group=group)
+    ks = ks.tolist()
+    if max(ks) > cap:
         raise ValueError("gather_rows: cap too small for the largest shard result")
     payload = torch.zeros((cap, rows.shape[1]), dtype=rows.dtype, device=rows.device)
     payload[:rows.shape[0]] = rows
-    payload[:rows.shape[0], 0] += rank * frames_per_rank
-    bufs = [torch.empty_like(payload) for _ in range(world)]
-    dist.all_gather(bufs, payload, group=group)
-    return torch.cat([b[:int(c.item())] for b, c in zip(bufs, ks)], 0)
+    payload[:rows.shape[0], 0] += shard_bounds(total_frames, world, rank)[0]
+    bufs = torch.empty((world * payload.numel(),), dtype=rows.dtype, device=rows.device)
+    dist.all_gather_into_tensor(bufs, payload.reshape(-1), group=group)
+    bufs = bufs.view(world, cap, rows.shape[1])
+    return torch.cat([bufs[r, :ks[r]] for r in range(world)], 0)
 
 
 def all_reduce_sum_(t, group=None):
@@ -69,11 +107,16 @@ def all_reduce_sum_(t, group=None):
     return t
 
 
-def all_reduce_gradients(params, group=None, average=True):
+def all_reduce_gradients(params, group=None, average=False):
     """One flat bucket for every gradient of `params` (the stage-3 trainable set is 112 845 fp32 values, SURVEY.md
     F8: latency-bound, so a single all-reduce): flatten, all-reduce, scatter back.  Parameters without a gradient
     (F7: unused heads, or no image proposals on this rank) take part with zeros so that every rank reduces the same
-    bucket layout.  Returns the number of reduced elements."""
+    bucket layout.  Returns the number of reduced elements.
+
+    The gradients are SUMMED by default: the stage-3 losses are sums over proposals (reduction='sum', reference
+    my_models.py:296-313,614-633; all_reduce_sum_ adds the ranks' loss vectors the same way), so the sum over ranks of
+    the shard gradients is the gradient of the whole-batch step a single process would take.  average=True divides by
+    the world size (the DistributedDataParallel convention for mean-reduced losses)."""
     params = [p for p in params if p.requires_grad]
     if not params:
         return 0

@@ -336,9 +336,13 @@ class DarknetPlan:
                     new_blocks.append(self.op_blocks[k])
             run.clear()
 
+        # ME_CHAIN_CUT=b1,b2,...: start a new chain in front of these cfg blocks (stage-level timing, tools/chain_trace.py)
+        cuts = {int(v) for v in os.environ.get("ME_CHAIN_CUT", "").split(",") if v}
         for k in order:
             m = self._conv_meta.get(k)
             ok = m is not None and not m["f32"] and ops.conv_chain_eligible(describe(k))
+            if ok and self.op_blocks[k] in cuts:
+                flush()
             if ok:
                 in_run = set(run)
                 # at most one producer inside the run for the input and for the residual (a concat of two in-run
