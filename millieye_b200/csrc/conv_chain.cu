@@ -335,6 +335,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) conv_ch
     int cur = -1, bn = 0, tiles_n = 1, act = 0, has_res = 0;
     const float* bias = nullptr;
     const bool eleader = threadIdx.x == 64;
+    int bias_layer = -1, bias_tn = -1;
     long long w_tfull = 0, w_stg = 0;
     if (!eleader) tr = nullptr;
     for (int it = 0;; ++it) {
@@ -354,9 +355,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) conv_ch
       const int n0 = tn * bn;
       const int acc = it & 1;
       const uint32_t acc_phase = (it >> 1) & 1;
-      ptx::named_bar_sync(kEpiBarrierId, kEpiThreads);   // everybody is done with the previous tile's bias
-      for (int k = etid; k < bn; k += kEpiThreads) s_bias[k] = __ldg(bias + n0 + k);
-      ptx::named_bar_sync(kEpiBarrierId, kEpiThreads);
+      if (item >> kItemShift != bias_layer || tn != bias_tn) {   // same layer and n tile as the last one: bias is in place
+        bias_layer = item >> kItemShift;
+        bias_tn = tn;
+        ptx::named_bar_sync(kEpiBarrierId, kEpiThreads);   // everybody is done with the previous tile's bias
+        for (int k = etid; k < bn; k += kEpiThreads) s_bias[k] = __ldg(bias + n0 + k);
+        ptx::named_bar_sync(kEpiBarrierId, kEpiThreads);
+      }
       ME_CHAIN_TRACED(w_tfull, mbar_wait(&tmem_full[acc], acc_phase, p.debug, 0x400u + acc));
       ptx::tc_fence_after();
       ME_CHAIN_TRACED(w_stg, mbar_wait(stg_ready, it & 1, p.debug, 0x500u));

@@ -47,12 +47,13 @@ def _check_equal_shards(n_local, group):
     _SHAPE_CHECKED.add(key)
 
 
-def gather_detections(det, count, group=None, packed=None):
+def gather_detections(det, count, group=None, packed=None, out=None):
     """det (n_local, max_det, cols) fp32, count (n_local,) int32 -> the same for the whole batch on every rank, with
     ONE collective: counts travel in the same buffer as the rows (bit-cast to fp32) and the output is a
     pre-allocated tensor (all_gather_into_tensor; no list form, no cat).  `packed`: the flat fp32 buffer det and count
     are views of (ops.NmsBuffers.flat) - without it the two are packed with one copy.  Every rank must hold the same
-    n_local (checked once per shape); the returned tensors are views of a buffer that the next call overwrites."""
+    n_local (checked once per shape).  The returned tensors are views of `out` (flat fp32, world * (det.numel() +
+    n_local) elements, owned by the caller) or, without it, of a cached buffer that the next call overwrites."""
     world = dist.get_world_size(group)
     if world == 1:
         return det, count
@@ -62,7 +63,8 @@ def gather_detections(det, count, group=None, packed=None):
     if packed is None or packed.numel() != body + n or packed.data_ptr() != det.data_ptr():
         packed = torch.cat((det.reshape(-1), count.view(torch.float32).reshape(-1)))
     key = (packed.device, packed.numel(), world, id(group))
-    out = _GATHER_OUT.get(key)
+    if out is None:
+        out = _GATHER_OUT.get(key)
     if out is None:
         # flat (concatenation along dim 0): the layout both NCCL and gloo accept for all_gather_into_tensor
         out = _GATHER_OUT[key] = torch.empty((world * packed.numel(),), dtype=torch.float32, device=packed.device)

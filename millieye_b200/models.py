@@ -206,22 +206,52 @@ class DetectPipeline:
     streams of batches (run_sp.py:213-214 / run_mp.py:314-320 call the two back to back for every frame): the
     confidence filter + NMS, the optional all-gather over ranks and the device->host read of batch i run on a second
     CUDA stream while the main stream already executes the convolutions of batch i+1.  Every submit() returns the
-    record of its batch; record.wait() blocks the host until that batch's detections are complete."""
+    record of its batch; record.wait() blocks the host until that batch's detections are complete.
+
+    Records live in a ring of `depth` (default 4) per plan: a record's buffers are reused by the depth-th submit after
+    it, and that submit first waits (on the host) until the record has completed, so a caller may keep up to `depth`
+    batches in flight; a record must be consumed before `depth` further submits are made."""
 
     class Record:
-        def __init__(self, nms, host_det, host_cnt):
-            self.nms, self.host_det, self.host_cnt = nms, host_det, host_cnt
+        def __init__(self, nms):
+            self.nms = nms
             self.det, self.count = nms.det, nms.count
+            self.host_flat = torch.empty_like(nms.flat, device="cpu").pin_memory()
+            body = nms.det.numel()
+            self.host_det = self.host_flat[:body].view(nms.det.shape)
+            self.host_cnt = self.host_flat[body:].view(torch.int32)
+            self.host_all = None          # gathered detections of every rank (gather=True, readback=True)
+            self.gather_out = None
             self.done = torch.cuda.Event()
+            self.pending = False
 
         def wait(self):
             self.done.synchronize()
+            self.pending = False
             return self
 
-    def __init__(self, net, conf_thresh, nms_thresh=0.5, max_det=200, gather=False):
+    def __init__(self, net, conf_thresh, nms_thresh=0.5, max_det=200, gather=False, depth=4):
         self.net, self.conf_thresh, self.nms_thresh, self.max_det, self.gather = net, conf_thresh, nms_thresh, max_det, gather
-        self._records = {}
+        self.depth = max(2, int(depth))
+        self._rings = {}     # plan -> [records], round robin
+        self._next = {}
         self._side = None
+
+    def _record(self, plan, dev):
+        # plans are rebuilt when weights / devices change: drop the rings of plans the net no longer holds
+        live = {id(p) for p in self.net._plans.values()}
+        for key in [k for k in self._rings if k not in live]:
+            del self._rings[key], self._next[key]
+        ring = self._rings.setdefault(id(plan), [])
+        k = self._next.get(id(plan), 0)
+        self._next[id(plan)] = (k + 1) % self.depth
+        if len(ring) <= k:
+            ring.append(DetectPipeline.Record(ops.NmsBuffers(plan.n, plan.rows_total, plan.attrs - 5, self.max_det, dev)))
+        rec = ring[k]
+        if rec.pending:
+            rec.done.synchronize()   # its previous occupant is still in flight: wait before its buffers are reused
+        rec.pending = True
+        return rec
 
     def submit(self, x, readback=False):
         plan = self.net.forward_device(x, decode=False)
@@ -229,13 +259,7 @@ class DetectPipeline:
         with torch.cuda.device(dev):
             if self._side is None:
                 self._side = torch.cuda.Stream(device=dev)
-            key = (id(plan), plan._slot)
-            rec = self._records.get(key)
-            if rec is None:
-                nms = ops.NmsBuffers(plan.n, plan.rows_total, plan.attrs - 5, self.max_det, dev)
-                rec = self._records[key] = DetectPipeline.Record(
-                    nms, torch.empty_like(nms.det, device="cpu").pin_memory(),
-                    torch.empty_like(nms.count, device="cpu").pin_memory())
+            rec = self._record(plan, dev)
             self._side.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(self._side):
                 plan.run_decode(self.net.use_cuda_graph)
@@ -244,11 +268,20 @@ class DetectPipeline:
                 rec.det, rec.count = rec.nms.det, rec.nms.count
                 if self.gather:
                     from .dist import gather_detections
-                    rec.det, rec.count = gather_detections(rec.nms.det, rec.nms.count)
+                    import torch.distributed as tdist
+                    if rec.gather_out is None:     # the record owns its gather output: nothing is copied or concatenated
+                        rec.gather_out = torch.empty((tdist.get_world_size() * rec.nms.flat.numel(),), dtype=torch.float32,
+                                                     device=dev)
+                    rec.det, rec.count = gather_detections(rec.nms.det, rec.nms.count, packed=rec.nms.flat,
+                                                           out=rec.gather_out)
                 if readback:
-                    rec.host_det.copy_(rec.nms.det, non_blocking=True)
-                    rec.host_cnt.copy_(rec.nms.count, non_blocking=True)
+                    rec.host_flat.copy_(rec.nms.flat, non_blocking=True)      # this rank's shard: one copy
+                    if self.gather:
+                        if rec.host_all is None:
+                            rec.host_all = (torch.empty_like(rec.det, device="cpu").pin_memory(),
+                                            torch.empty_like(rec.count, device="cpu").pin_memory())
+                        rec.host_all[0].copy_(rec.det, non_blocking=True)      # and the whole batch
+                        rec.host_all[1].copy_(rec.count, non_blocking=True)
                 rec.done.record()
             plan.hold_output(rec.done)
         return rec
-

@@ -247,8 +247,12 @@ class NmsBuffers:
     def __init__(self, n, rows, num_classes, max_det, device):
         L = _lib.lib()
         self.n, self.rows, self.nc, self.max_det = n, rows, num_classes, max_det
-        self.det = torch.zeros((n, max_det, 7 + num_classes), dtype=torch.float32, device=device)
-        self.count = torch.zeros((n,), dtype=torch.int32, device=device)
+        # det and count are views of ONE flat fp32 buffer (counts bit-cast): the multi-GPU gather sends it as it is
+        # (dist.gather_detections, a single all_gather_into_tensor) and the host read-back is one copy
+        cols = 7 + num_classes
+        self.flat = torch.zeros((n * max_det * cols + n,), dtype=torch.float32, device=device)
+        self.det = self.flat[:n * max_det * cols].view(n, max_det, cols)
+        self.count = self.flat[n * max_det * cols:].view(torch.int32)
         self.index = torch.zeros((n, max_det), dtype=torch.int32, device=device)
         self.ws_bytes = L.me_filter_nms_workspace(n, rows, num_classes)
         self.ws = torch.empty((self.ws_bytes,), dtype=torch.uint8, device=device)
