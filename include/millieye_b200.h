@@ -303,6 +303,58 @@ typedef struct me_radar_cfg {
 int me_radar_maps(const float* points, const int* counts, int n, int cap, const me_radar_cfg* cfg,
                   float* maps_out, float* uvzv_out, int* kept_out, me_stream_t stream);
 
+/* ---- stage-3 training step (train.py:169-191, my_models.py:545-640 + autograd) -----------
+ * fp32 building blocks of the train-mode forward and the hand-derived backward of the heads that train
+ * (img_cnn_layers, radar_cnn_layers, refinement_head, ensemble_head); the frozen detector stays on the tensor-core
+ * engine.  Matrices are row-major [rows][channels]; every call is stream-ordered and allocation-free.
+ * Host side: millieye_b200/stage3_train.py; derivation: oracle/stage3_backward.py. */
+/* C[i][j] = sum_k A(i,k) * B(k,j) (+ bias[j], then ME_ACT_*), A(i,k) = A[i*sai + k*sak], B(k,j) = B[k*sbk + j*sbj];
+ * accumulate != 0: C += product.  Covers x W^T (nn.Linear / 1x1 conv / im2col conv forward), dZ W (input gradient)
+ * and dZ^T x (weight gradient) of my_models.py:62,133-150,238-251 by the choice of strides. */
+int me_gemm_f32(int M, int N, int K, const float* A, long long sai, long long sak, const float* B, long long sbk,
+                long long sbj, float* C, long long ldc, const float* bias, int act, int accumulate, me_stream_t stream);
+/* out[c] = sum_r X[r][c] * (Y ? Y[r][c] : 1), double accumulation (bias gradients, BatchNorm dgamma / dbeta). */
+int me_colsum_f32(const float* X, const float* Y, long long rows, int cols, long long ldx, long long ldy, float* out,
+                  me_stream_t stream);
+/* fp16 rows with a pitch (the detector's NHWC feature map) -> dense fp32 rows; NCHW fp32 -> rows [n*hw][c]. */
+int me_half_rows_to_float(const void* x, long long rows, int cols, int pitch, float* y, me_stream_t stream);
+int me_nchw_to_rows_f32(const float* x, int n, int c, int hw, float* y, me_stream_t stream);
+/* 3x3 / stride 1 / pad 1 im2col on rows: cols[p][ci*9 + tap] (the k order of an OIHW weight row), and its adjoint in
+ * gather form (deterministic). */
+int me_im2col3_f32(const float* x, int n, int h, int w, int c, float* cols, me_stream_t stream);
+int me_col2im3_f32(const float* dcols, int n, int h, int w, int c, float* dx, me_stream_t stream);
+/* nn.BatchNorm2d / BatchNorm1d in training mode + LeakyReLU(0.1) (my_models.py:63-75,136-150,248-249): batch mean and
+ * biased variance per channel (double accumulation), running statistics updated in place with `momentum` (unbiased
+ * variance; NULL: no update), x_hat and the activation a written out; mean_ws / inv_std: [cols] scratch kept for the
+ * backward.  bwd: da_inout holds dL/da on entry (overwritten with dL/dy), dz gets dL/dz; dgamma / dbeta out. */
+int me_bn_train_fwd(const float* z, long long rows, int cols, const float* gamma, const float* beta, float eps,
+                    float momentum, float* running_mean, float* running_var, float* mean_ws, float* inv_std,
+                    float* xhat, float* a, me_stream_t stream);
+int me_bn_train_bwd(float* da_inout, const float* a, const float* xhat, long long rows, int cols, const float* gamma,
+                    const float* inv_std, float* dgamma, float* dbeta, float* dz, me_stream_t stream);
+int me_leaky_bwd_f32(float* d_inout, const float* a, long long total, me_stream_t stream);
+int me_sigmoid_bwd_f32(float* d_inout, const float* s, long long total, me_stream_t stream);
+/* torchvision roi_align (aligned=False) / ps_roi_align (sampling_ratio=-1, see me_roi_align / me_psroi_align) on an fp32
+ * map [n][h][w][chan_total]; out / grad_out [num_rois][channels*pooled*pooled] in (c, ph, pw) order.  backward != 0:
+ * the adjoint - grad_out is scattered into dfeat (zero-filled by the caller) with atomicAdd. */
+int me_roi_align_f32(int position_sensitive, int backward, const float* feat, float* dfeat, int n, int h, int w,
+                     int chan_total, int channels, int pooled, float scale, const float* rois, int num_rois, float* out,
+                     const float* grad_out, me_stream_t stream);
+/* Per-proposal tail of refinement_head + ensemble_head in fp32 (my_models.py:268-284, 202-210, 513-514) and the
+ * backward of  FocalLoss(masks of the sampled image proposals) + BCE(conf of the sample) / lambda  (:610-635) down to
+ * the pre-activations: d_o [n_img][2], hl [n_img][64], dhp [2 n_img][32], u [2 n_img][2] (operands of the ensemble
+ * head's weight-gradient products), dr2 [n_all] (radar_net's last pre-activation), dz2 [n_all][13] (net2's). */
+int me_stage3_tail_fwd(const float* r2, const float* cls, int cls_pitch, const float* img_boxes, int n_img, int n_all,
+                       const float* fc1_w, const float* fc1_b, const float* fc2_w, const float* fc2_b, float* rc,
+                       float* refine, float* mask, float* p, me_stream_t stream);
+int me_stage3_tail_bwd(const float* rc, const float* refine, const float* cls, int cls_pitch, const float* p,
+                       const float* img_boxes, int n_img, int n_all, const unsigned char* pos, const unsigned char* sel,
+                       float alpha, float lambda_conf, const float* fc1_w, const float* fc1_b, const float* fc2_w, float* d_o,
+                       float* hl, float* dhp, float* u, float* dr2, float* dz2, me_stream_t stream);
+/* torch.optim.Adam step (train.py:158; no weight decay / amsgrad) over flat fp32 buffers; step counts from 1. */
+int me_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, long long n, float lr, float beta1,
+                 float beta2, float eps, int step, me_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -97,6 +97,23 @@ SIGNATURES = {
     "me_stage3_labels": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_void_p]),
     "me_stage3_loss": (c_int, [c_void_p] * 5 + [c_int, c_void_p, c_void_p, c_void_p, POINTER(Stage3LossCfg), c_void_p,
                                c_void_p]),
+    "me_gemm_f32": (c_int, [c_int, c_int, c_int, c_void_p, c_longlong, c_longlong, c_void_p, c_longlong, c_longlong, c_void_p,
+                            c_longlong, c_void_p, c_int, c_int, c_void_p]),
+    "me_colsum_f32": (c_int, [c_void_p, c_void_p, c_longlong, c_int, c_longlong, c_longlong, c_void_p, c_void_p]),
+    "me_half_rows_to_float": (c_int, [c_void_p, c_longlong, c_int, c_int, c_void_p, c_void_p]),
+    "me_nchw_to_rows_f32": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "me_im2col3_f32": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "me_col2im3_f32": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
+    "me_bn_train_fwd": (c_int, [c_void_p, c_longlong, c_int, c_void_p, c_void_p, c_float, c_float] + [c_void_p] * 7),
+    "me_bn_train_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_longlong, c_int] + [c_void_p] * 6),
+    "me_leaky_bwd_f32": (c_int, [c_void_p, c_void_p, c_longlong, c_void_p]),
+    "me_sigmoid_bwd_f32": (c_int, [c_void_p, c_void_p, c_longlong, c_void_p]),
+    "me_roi_align_f32": (c_int, [c_int, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_float, c_void_p,
+                                 c_int, c_void_p, c_void_p, c_void_p]),
+    "me_stage3_tail_fwd": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_int, c_int] + [c_void_p] * 9),
+    "me_stage3_tail_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int, c_int, c_void_p, c_void_p,
+                                   c_float, c_float] + [c_void_p] * 10),
+    "me_adam_step": (c_int, [c_void_p] * 4 + [c_longlong, c_float, c_float, c_float, c_float, c_int, c_void_p]),
     "me_finalize_output": (c_int, [c_void_p] * 6 + [c_int, c_int, c_float, c_float, c_int, c_void_p, c_void_p, c_void_p,
                                                     c_size_t, c_void_p]),
 }

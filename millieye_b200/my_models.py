@@ -241,6 +241,15 @@ class Network(nn.Module):
     def _invalidate(self):
         self._plans = {}
 
+    def train(self, mode=True):
+        """nn.Module.train; leaving training mode drops the inference plans, whose packed fp16 weights and folded
+        BatchNorm statistics were taken before the training steps changed them."""
+        was_training = any(m.training for m in (self.img_cnn_layers, self.radar_cnn_layers, self.refinement_head))
+        super().train(mode)
+        if was_training and not mode:
+            self._invalidate()
+        return self
+
     def load_state_dict(self, *args, **kwargs):
         self._invalidate()
         return super().load_state_dict(*args, **kwargs)
@@ -268,14 +277,13 @@ class Network(nn.Module):
         """Same contract as reference my_models.py:433-452.  images (N,3,S,S) fp32 0..1; maps (N,3,S/16,S/16);
         radar_boxes_location (n,5) [frame, x1,y1,x2,y2] in 0..1 - scaled by S IN PLACE like the reference (:491);
         model_mode 0 fusion / 1 YOLO only / 2 radar only.  Returns output (K,8) on the device."""
-        if targets is not None:
-            if model_mode != 0:
-                raise MeError("targets are only used with model_mode 0 (reference my_models.py:476-480 returns / "
-                              "changes thresholds before the loss branch in the other modes)")
-            if any(m.training for m in (self.img_cnn_layers, self.radar_cnn_layers, self.refinement_head)):
-                raise MeError("Network.forward(targets=...) runs the labelling + loss branch (my_models.py:545-640) with "
-                              "running BatchNorm statistics: call .eval() first.  Batch-statistics BatchNorm and the "
-                              "backward pass of the fusion heads are not built (DESIGN.md, out of scope this round)")
+        heads_training = any(m.training for m in (self.img_cnn_layers, self.radar_cnn_layers, self.refinement_head))
+        if targets is not None and model_mode != 0:
+            raise MeError("targets are only used with model_mode 0 (reference my_models.py:476-480 returns / "
+                          "changes thresholds before the loss branch in the other modes)")
+        if heads_training and (targets is None or model_mode != 0):
+            raise MeError("in train() mode the heads run on batch statistics, which only the training step "
+                          "(forward(images, maps, radar_boxes, 0, targets), train.py:185) defines; call .eval() for inference")
         base = self.base_detector
         plan_b = base.forward_device(images)
         dev = plan_b.device
@@ -292,6 +300,8 @@ class Network(nn.Module):
             if n_radar > 0:
                 radar_boxes_location[:, 1:] *= images.shape[-1]          # reference side effect (:491)
                 plan.radar_dev[:n_radar].copy_(radar_boxes_location, non_blocking=True)
+            if heads_training:
+                return self._train_branch(plan, images, maps, n_radar, targets)
             plan.maps_in.copy_(maps, non_blocking=True)
             plan.score_maps()
             plan.proposals(self.conf_thresh, self.class_idx, n_radar)
@@ -303,7 +313,7 @@ class Network(nn.Module):
                 return output
             return self._loss_branch(plan, images.shape[3], targets, output)
 
-    def _loss_branch(self, plan, img_size, targets, output):
+    def _loss_branch(self, plan, img_size, targets, output, radar_score_rows=None):
         """Reference my_models.py:545-640 on the forward's device buffers: labels (me_stage3_labels), balanced
         sampling with python's `random` on the host like the reference (:600), losses + counters (me_stage3_loss).
         `targets` (m,6) [image, class, cx, cy, w, h] in 0..1 is rewritten IN PLACE to pixel x1y1x2y2 as the reference
@@ -345,6 +355,83 @@ class Network(nn.Module):
                       conf=confs)
         self.last_losses = dict(masks_loss=float(vals[0]), conf_loss=float(vals[1]), loss_xy=float(vals[2]),
                                 loss_wh=float(vals[3]), category_loss=float(vals[4]))
+        self._last_sample = (pos, keep)
         g = plan.g
-        radar_attention = plan.radar_score[..., 0].to(torch.float32).reshape(plan.n, 1, g, g)
+        if radar_score_rows is not None:     # train branch: fp32 rows [n*g*g, 10]
+            radar_attention = radar_score_rows[:, 0].reshape(plan.n, 1, g, g).clone()
+        else:
+            radar_attention = plan.radar_score[..., 0].to(torch.float32).reshape(plan.n, 1, g, g)
         return plan.loss_out[5].clone(), output, metric, radar_attention
+
+    # ------------------------------------------------------------------ training step (train.py:169-191)
+    def _head_tensors(self):
+        params = {k: v.data for k, v in self.named_parameters() if not k.startswith("base_detector.")}
+        buffers = {k: v for k, v in self.named_buffers() if not k.startswith("base_detector.") and "running_" in k}
+        return params, buffers
+
+    def _train_branch(self, plan, images, maps, n_radar, targets):
+        """model.train() forward with targets: the frozen detector's proposals, then the heads in fp32 on batch
+        statistics (stage3_train.HeadTrainer), labels / balanced sample / losses like the eval branch, and a loss tensor
+        whose backward() runs the hand-derived backward kernels and fills .grad of every head parameter that requires
+        one - so `loss.backward(); optimizer.step()` of train.py:186-190 work unchanged."""
+        from . import stage3_train as st
+        dev = plan.device
+        if getattr(self, "_trainer", None) is None or self._trainer.device != dev:
+            self._trainer = st.HeadTrainer(dev)
+        tr = self._trainer
+        n, g = plan.n, plan.g
+        P = n * g * g
+        plan.proposals(self.conf_thresh, self.class_idx, n_radar)
+        n_img, n_all = (int(v) for v in plan.counts.tolist())
+        fv = plan.base.feature_view
+        feat_rows = st.half_rows_to_float(fv.t, P, 256, fv.pitch, tr._buf("feat_rows", (P, 256)))
+        maps_rows = st.nchw_to_rows(maps.to(device=dev, dtype=torch.float32).contiguous(), tr._buf("maps_rows", (P, 3)))
+        params, buffers = self._head_tensors()
+        for k, v in params.items():
+            if v.dtype != torch.float32 or not v.is_contiguous():
+                raise MeError(f"training needs contiguous fp32 parameters ({k} is {v.dtype})")
+        cache = tr.forward(params, buffers, feat_rows, maps_rows, n, g, plan.rois, plan.img_boxes, n_img, n_all,
+                           regress_out=plan.regress, refine_out=plan.refine, mask_out=plan.mask)
+        for m in (self.img_cnn_layers, self.radar_cnn_layers, self.refinement_head):
+            for mod in m.modules():
+                if isinstance(mod, (nn.BatchNorm2d, nn.BatchNorm1d)) and mod.num_batches_tracked is not None:
+                    mod.num_batches_tracked += 1
+        ops.finalize_output(plan.img_boxes, plan.rois, plan.refine, plan.regress, plan.mask, plan.counts, plan.cap,
+                            float(self.refine_threshold_img), float(self.refine_threshold_radar), True, plan.out, plan.out_count,
+                            plan.final_ws)
+        self.refinement_head.count += 1
+        k = int(plan.out_count.item())
+        output = plan.out[:k].clone()
+        loss_val, output, metric, radar_attention = self._loss_branch(plan, images.shape[3], targets, output,
+                                                                      radar_score_rows=cache["s"])
+        pos, keep = self._last_sample
+        pos_d = tr._bufs["pos"] = torch.from_numpy(pos.astype("uint8")).to(dev) if n_all else torch.zeros(1, dtype=torch.uint8, device=dev)
+        sel_d = tr._bufs["sel"] = torch.from_numpy(keep.astype("uint8")).to(dev) if n_all else torch.zeros(1, dtype=torch.uint8, device=dev)
+        named = dict(self.named_parameters())
+        image_path = all(named[k].requires_grad for k in st.IMAGE_PATH)
+        names = [k for k in st.TRAINABLE if named[k].requires_grad and (image_path or k not in st.IMAGE_PATH)]
+        self._train_state = dict(cache=cache, params=params, pos=pos_d, sel=sel_d, image_path=image_path, names=names)
+        loss = _Stage3Loss.apply(loss_val, self, *[named[k] for k in names])
+        return loss, output, metric, radar_attention
+
+    def backward_into(self, grads_out=None):
+        """The backward of the last training forward, without autograd: gradients are written into `grads_out`
+        ({name: tensor}, e.g. Stage3Optimizer.grads - overwritten, not accumulated) and returned."""
+        s = self._train_state
+        return self._trainer.backward(s["params"], s["cache"], s["pos"], s["sel"], self.alpha, self.loss_lambda[0],
+                                      image_path=s["image_path"], out=grads_out)
+
+
+class _Stage3Loss(torch.autograd.Function):
+    """loss tensor of the training forward; backward() = HeadTrainer.backward (csrc/train_ops.cu)."""
+
+    @staticmethod
+    def forward(ctx, loss_val, model, *params):
+        ctx.model = model
+        ctx.names = list(model._train_state["names"])
+        return loss_val.clone()
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        grads = ctx.model.backward_into(None)
+        return (None, None) + tuple(grads[k] * grad_out for k in ctx.names)

@@ -191,9 +191,9 @@ def test_fusion_empty_and_errors():
     assert out.shape == (0, 8)                        # empty proposals give a (0,8) tensor, never raise
     out = model(imgs, maps, torch.zeros((0, 5), device=DEV), 0)
     assert out.shape[1] == 8
-    with pytest.raises(MeError):      # batch-statistics BatchNorm / backward are not built: train() mode must not pass silently
+    with pytest.raises(MeError):      # train() mode is only defined for the training step (with targets): no silent inference
         model.train()
-        model(imgs, maps, torch.zeros((0, 5), device=DEV), 0, targets=torch.zeros(1, 6))
+        model(imgs, maps, torch.zeros((0, 5), device=DEV), 0)
     model.eval()
     loss, out, metric, att = model(imgs, maps, torch.zeros((0, 5), device=DEV), 0, targets=torch.zeros(0, 6))
     assert float(loss) == 0.0 and out.shape[1] == 8 and att.shape == (2, 1, 6, 6) and metric["true"] == 0
