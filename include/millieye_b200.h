@@ -323,15 +323,29 @@ int me_nchw_to_rows_f32(const float* x, int n, int c, int hw, float* y, me_strea
  * gather form (deterministic). */
 int me_im2col3_f32(const float* x, int n, int h, int w, int c, float* cols, me_stream_t stream);
 int me_col2im3_f32(const float* dcols, int n, int h, int w, int c, float* dx, me_stream_t stream);
-/* nn.BatchNorm2d / BatchNorm1d in training mode + LeakyReLU(0.1) (my_models.py:63-75,136-150,248-249): batch mean and
- * biased variance per channel (double accumulation), running statistics updated in place with `momentum` (unbiased
- * variance; NULL: no update), x_hat and the activation a written out; mean_ws / inv_std: [cols] scratch kept for the
- * backward.  bwd: da_inout holds dL/da on entry (overwritten with dL/dy), dz gets dL/dz; dgamma / dbeta out. */
+/* nn.BatchNorm2d / BatchNorm1d in training mode + LeakyReLU(0.1) (my_models.py:63-75,136-150,248-249), in steps so that
+ * the ranks of a sharded batch can add their partial sums in between (synchronised BatchNorm: the sharded step then
+ * equals the reference's single-process step on the whole batch):
+ *   partial_stats: sums[0..cols) = sum z, sums[cols..2cols) = sum z^2 (double), sums[2 cols] = rows   (2 cols + 1 doubles)
+ *   finalize:      batch mean / biased variance -> mean_out, inv_std; running statistics updated in place with
+ *                  `momentum` (unbiased variance; NULL: no update); the row count is read from sums[2 cols]
+ *   apply:         x_hat = (z - mean) * inv_std, a = leaky(gamma * x_hat + beta)
+ *   train_fwd:     the three in a row (single process).
+ *   bwd_sums:      da_inout holds dL/da on entry and dL/dy on return; dgamma = sum dy * x_hat, dbeta = sum dy (this rank)
+ *   bwd_apply:     dz = inv_std * gamma * (dy - dbeta_total / N - x_hat * dgamma_total / N), N = *total_rows (device). */
+int me_bn_partial_stats(const float* z, long long rows, int cols, double* sums, me_stream_t stream);
+int me_bn_finalize(const double* sums, int cols, float eps, float momentum, float* running_mean, float* running_var,
+                   float* mean_out, float* inv_std, me_stream_t stream);
+int me_bn_apply(const float* z, long long rows, int cols, const float* mean, const float* inv_std, const float* gamma,
+                const float* beta, float* xhat, float* a, me_stream_t stream);
 int me_bn_train_fwd(const float* z, long long rows, int cols, const float* gamma, const float* beta, float eps,
-                    float momentum, float* running_mean, float* running_var, float* mean_ws, float* inv_std,
+                    float momentum, float* running_mean, float* running_var, double* sums_ws, float* mean_ws, float* inv_std,
                     float* xhat, float* a, me_stream_t stream);
-int me_bn_train_bwd(float* da_inout, const float* a, const float* xhat, long long rows, int cols, const float* gamma,
-                    const float* inv_std, float* dgamma, float* dbeta, float* dz, me_stream_t stream);
+int me_bn_bwd_sums(float* da_inout, const float* a, const float* xhat, long long rows, int cols, float* dgamma, float* dbeta,
+                   me_stream_t stream);
+int me_bn_bwd_apply(const float* dy, const float* xhat, long long rows, int cols, const float* gamma, const float* inv_std,
+                    const float* dgamma_total, const float* dbeta_total, const double* total_rows, float* dz,
+                    me_stream_t stream);
 int me_leaky_bwd_f32(float* d_inout, const float* a, long long total, me_stream_t stream);
 int me_sigmoid_bwd_f32(float* d_inout, const float* s, long long total, me_stream_t stream);
 /* torchvision roi_align (aligned=False) / ps_roi_align (sampling_ratio=-1, see me_roi_align / me_psroi_align) on an fp32

@@ -104,8 +104,12 @@ SIGNATURES = {
     "me_nchw_to_rows_f32": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_void_p]),
     "me_im2col3_f32": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
     "me_col2im3_f32": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_void_p]),
-    "me_bn_train_fwd": (c_int, [c_void_p, c_longlong, c_int, c_void_p, c_void_p, c_float, c_float] + [c_void_p] * 7),
-    "me_bn_train_bwd": (c_int, [c_void_p, c_void_p, c_void_p, c_longlong, c_int] + [c_void_p] * 6),
+    "me_bn_partial_stats": (c_int, [c_void_p, c_longlong, c_int, c_void_p, c_void_p]),
+    "me_bn_finalize": (c_int, [c_void_p, c_int, c_float, c_float] + [c_void_p] * 5),
+    "me_bn_apply": (c_int, [c_void_p, c_longlong, c_int] + [c_void_p] * 7),
+    "me_bn_train_fwd": (c_int, [c_void_p, c_longlong, c_int, c_void_p, c_void_p, c_float, c_float] + [c_void_p] * 8),
+    "me_bn_bwd_sums": (c_int, [c_void_p, c_void_p, c_void_p, c_longlong, c_int, c_void_p, c_void_p, c_void_p]),
+    "me_bn_bwd_apply": (c_int, [c_void_p, c_void_p, c_longlong, c_int] + [c_void_p] * 7),
     "me_leaky_bwd_f32": (c_int, [c_void_p, c_void_p, c_longlong, c_void_p]),
     "me_sigmoid_bwd_f32": (c_int, [c_void_p, c_void_p, c_longlong, c_void_p]),
     "me_roi_align_f32": (c_int, [c_int, c_int, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_float, c_void_p,

@@ -33,7 +33,10 @@ int fail(int code, const char* fmt, ...);
 static inline int ceil_div(int a, int b) { return (a + b - 1) / b; }
 static inline int round_up(int a, int b) { return ceil_div(a, b) * b; }
 
-int sm_count();
+int sm_count();   // of the current device (cached per device ordinal)
+// true the first time it is called with `seen` on the current device: per-device one-time setup such as
+// cudaFuncSetAttribute(MaxDynamicSharedMemorySize), which belongs to the device's copy of the function
+bool first_use_on_device(bool (&seen)[64]);
 
 // ---- tensor-map encoders (driver entry points fetched at run time; no link-time libcuda) ----
 // 2D row-major [rows][cols] view with `pitch_elems` elements between rows.

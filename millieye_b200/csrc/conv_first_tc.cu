@@ -293,11 +293,9 @@ int launch_first(const float* x, const __half* wk, const float* bias, __half* y,
                  int out_pitch, int act, int tiles, int grid, cudaStream_t stream) {
   using F = FCfg<VEC>;
   auto kern = conv_first_tc_kernel<COUT, VEC>;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static bool attr_seen[64] = {false};   // per instantiation and per device
+  if (first_use_on_device(attr_seen))
     ME_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, F::SMEM));
-    attr_set = true;
-  }
   static int dbg = -1;
   if (dbg < 0) {
     const char* e = getenv("ME_FIRST_DBG");

@@ -622,11 +622,9 @@ int launch(const me_conv_desc* d, const void* x, const void* w, const float* bia
   }
 
   auto kern = conv_gemm_kernel<BN, BK, OUT_F32, WS, EG>;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static bool attr_seen[64] = {false};   // per instantiation and per device
+  if (first_use_on_device(attr_seen))
     ME_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    attr_set = true;
-  }
   const int total = p.tiles_m * p.tiles_n;
   int grid = sm_count();
   if (grid <= 0) grid = 148;

@@ -616,11 +616,9 @@ int launch_pair(const me_conv_desc* d, const void* x, const void* w, const float
   }
 
   auto kern = conv_gemm_pair_kernel<BN>;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static bool attr_seen[64] = {false};   // per instantiation and per device
+  if (first_use_on_device(attr_seen))
     ME_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    attr_set = true;
-  }
   const int total = p.tiles_m * p.tiles_n;
   int sms = sm_count();
   if (sms <= 0) sms = 148;

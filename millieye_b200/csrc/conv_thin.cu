@@ -353,11 +353,9 @@ int launch_thin(const me_conv_desc* d, const void* x, const void* w, const float
     tmR = tmC;
   }
   auto kern = conv_thin_kernel<CIN, COUT>;
-  static bool attr_set = false;
-  if (!attr_set) {
+  static bool attr_seen[64] = {false};   // per instantiation and per device
+  if (first_use_on_device(attr_seen))
     ME_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
-    attr_set = true;
-  }
   int grid = sm_count();
   if (grid <= 0) grid = 148;
   if (grid > p.tiles) grid = p.tiles;

@@ -114,7 +114,8 @@ __device__ __forceinline__ unsigned int score_desc_bits(float s) {
 // greedy suppression, stopping once max_det boxes are kept.
 __global__ void __launch_bounds__(kSelThreads, 1)
 nms_select_kernel(const float* __restrict__ pred, int rows, int nc, float conf_thresh, float nms_thresh_f, int max_det,
-                  float* __restrict__ det, int* __restrict__ det_count, int* __restrict__ det_index, void* ws) {
+                  float* __restrict__ det, int* __restrict__ det_count, int* __restrict__ det_index, void* ws,
+                  int keys_in_smem) {
   extern __shared__ unsigned long long s_dyn[];
   __shared__ int s_scan[kSelThreads / 32];
   __shared__ int s_k;
@@ -129,8 +130,9 @@ nms_select_kernel(const float* __restrict__ pred, int rows, int nc, float conf_t
   const int attrs = 5 + nc;
   const int det_cols = 7 + nc;
   const int pow2 = next_pow2(rows);
-  unsigned long long* keys = (pow2 <= kMaxSmemKeys) ? s_dyn : L.keys;
-  unsigned char* supp = reinterpret_cast<unsigned char*>(s_dyn + (pow2 <= kMaxSmemKeys ? pow2 : 0));
+  // the host decides from the whole shared-memory budget whether the sort keys fit next to the fixed staging areas
+  unsigned long long* keys = keys_in_smem ? s_dyn : L.keys;
+  unsigned char* supp = reinterpret_cast<unsigned char*>(s_dyn + (keys_in_smem ? pow2 : 0));
   // staging area for the sorted boxes: the greedy loop reads box i once per survivor, and a global/L2 round trip
   // per survivor (~0.7 us x up to 200) was most of this kernel's 84 us
   float* sm_box = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(supp) + rows + 15) & ~uintptr_t(15));
@@ -400,19 +402,27 @@ int me_filter_nms(float* pred, int n, int rows, int num_classes, float conf_thre
                                                                    xyxy_inplace, workspace);
   ME_LAUNCH_CHECK();
   const int pow2 = next_pow2(rows);
-  const size_t smem = (pow2 <= kMaxSmemKeys ? static_cast<size_t>(pow2) * 8 : 0) + static_cast<size_t>(rows) + 32 +
-                      static_cast<size_t>(kSmemBoxes) * 24 + static_cast<size_t>(kMatrixK) * (kMatrixK / 32) * 4;
+  // Sort keys live in shared memory when they fit NEXT TO the box stage and the suppression matrix (the whole budget,
+  // not just pow2 <= kMaxSmemKeys: 12 257..16 384 rows - YOLOv3 at 448 / 480 / 512 - need 128 KB of keys plus 80 KB of
+  // fixed areas and used to fail the limit below); otherwise the kernel sorts in the global workspace.
+  constexpr size_t kSmemLimit = 220 * 1024;
+  const size_t fixed = static_cast<size_t>(rows) + 32 + static_cast<size_t>(kSmemBoxes) * 24 +
+                       static_cast<size_t>(kMatrixK) * (kMatrixK / 32) * 4;
+  const int keys_in_smem = (pow2 <= kMaxSmemKeys && static_cast<size_t>(pow2) * 8 + fixed <= kSmemLimit) ? 1 : 0;
+  const size_t smem = (keys_in_smem ? static_cast<size_t>(pow2) * 8 : 0) + fixed;
   // (double)ovr > nms_thresh for a float ovr  <=>  ovr > the largest float that is <= nms_thresh
   float thresh_f = static_cast<float>(nms_thresh);
   if (static_cast<double>(thresh_f) > nms_thresh) thresh_f = nextafterf(thresh_f, -INFINITY);
-  static bool attr_set = false;
-  if (!attr_set) {
-    ME_CUDA(cudaFuncSetAttribute(nms_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 220 * 1024));
-    attr_set = true;
+  int dev = 0;
+  ME_CUDA(cudaGetDevice(&dev));
+  static bool attr_set[64] = {false};   // per device: the attribute belongs to the device's copy of the function
+  if (dev < 0 || dev >= 64 || !attr_set[dev]) {
+    ME_CUDA(cudaFuncSetAttribute(nms_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kSmemLimit)));
+    if (dev >= 0 && dev < 64) attr_set[dev] = true;
   }
-  ME_REQUIRE(smem <= 220 * 1024, "filter_nms: %d rows need %zu B of shared memory", rows, smem);
+  ME_REQUIRE(smem <= kSmemLimit, "filter_nms: %d rows need %zu B of shared memory", rows, smem);
   nms_select_kernel<<<n, kSelThreads, smem, stream>>>(pred, rows, num_classes, conf_thresh, thresh_f, max_det, det,
-                                                      det_count, det_index, workspace);
+                                                      det_count, det_index, workspace, keys_in_smem);
   ME_LAUNCH_CHECK();
   return ME_OK;
 }

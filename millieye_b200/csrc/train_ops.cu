@@ -167,44 +167,59 @@ __global__ void col2im3_kernel(const float* __restrict__ dcols, int n, int h, in
 }
 
 // ------------------------------------------------------------------------------------------------ BatchNorm (batch statistics)
-// Per channel over `rows` rows: mean, biased variance (double), running statistics updated like nn.BatchNorm2d in
-// training mode (momentum m, unbiased variance into running_var), inv_std out.
+// Batch statistics in two steps so that the ranks of a sharded batch can add their partial sums in between
+// (synchronised BatchNorm: the step then equals the reference's single-process step on the whole batch):
+//   partial : sums[c] = sum_r z[r][c], sums[cols + c] = sum_r z[r][c]^2 (double), sums[2 cols] = rows
+//   finalize: mean, biased variance -> inv_std; running statistics updated like nn.BatchNorm2d in training mode
+//             (momentum m, unbiased variance into running_var).  The row count is read from device memory.
 __global__ void __launch_bounds__(256)
-bn_stats_kernel(const float* __restrict__ z, long long rows, int cols, float eps, float momentum,
-                float* __restrict__ running_mean, float* __restrict__ running_var, float* __restrict__ mean_out,
-                float* __restrict__ inv_std) {
+bn_partial_kernel(const float* __restrict__ z, long long rows, int cols, double* __restrict__ sums) {
   __shared__ double s1[8][33], s2[8][33];
   const int c = blockIdx.x * 32 + (threadIdx.x & 31);
   const int lr = threadIdx.x >> 5;
-  double a = 0.0;
-  if (c < cols)
-    for (long long r = lr; r < rows; r += 8) a += static_cast<double>(z[r * cols + c]);
-  s1[lr][threadIdx.x & 31] = a;
-  __syncthreads();
-  double mean = 0.0;
-#pragma unroll
-  for (int k = 0; k < 8; ++k) mean += s1[k][threadIdx.x & 31];
-  mean /= static_cast<double>(rows);
-  double v = 0.0;
+  double a = 0.0, b = 0.0;
   if (c < cols)
     for (long long r = lr; r < rows; r += 8) {
-      const double d = static_cast<double>(z[r * cols + c]) - mean;
-      v += d * d;
+      const double v = static_cast<double>(z[r * cols + c]);
+      a += v;
+      b += v * v;
     }
-  s2[lr][threadIdx.x & 31] = v;
+  s1[lr][threadIdx.x & 31] = a;
+  s2[lr][threadIdx.x & 31] = b;
   __syncthreads();
   if (lr == 0 && c < cols) {
-    double var = 0.0;
+    double t1 = 0.0, t2 = 0.0;
 #pragma unroll
-    for (int k = 0; k < 8; ++k) var += s2[k][threadIdx.x & 31];
-    const double biased = var / static_cast<double>(rows);
-    const double unbiased = rows > 1 ? var / static_cast<double>(rows - 1) : biased;
-    mean_out[c] = static_cast<float>(mean);
-    inv_std[c] = static_cast<float>(1.0 / sqrt(biased + static_cast<double>(eps)));
-    if (running_mean) {
-      running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * static_cast<float>(mean);
-      running_var[c] = (1.f - momentum) * running_var[c] + momentum * static_cast<float>(unbiased);
+    for (int k = 0; k < 8; ++k) {
+      t1 += s1[k][threadIdx.x & 31];
+      t2 += s2[k][threadIdx.x & 31];
     }
+    sums[c] = t1;
+    sums[cols + c] = t2;
+  }
+  if (blockIdx.x == 0 && threadIdx.x == 0) sums[2 * cols] = static_cast<double>(rows);
+}
+
+__global__ void bn_finalize_kernel(const double* __restrict__ sums, int cols, float eps, float momentum,
+                                   float* __restrict__ running_mean, float* __restrict__ running_var,
+                                   float* __restrict__ mean_out, float* __restrict__ inv_std) {
+  const int c = blockIdx.x * blockDim.x + threadIdx.x;
+  if (c >= cols) return;
+  const double rows = sums[2 * cols];
+  if (rows < 1.0) {   // no rows anywhere (no proposals in the whole batch): nothing to normalise, statistics untouched
+    mean_out[c] = 0.f;
+    inv_std[c] = rsqrtf(eps);
+    return;
+  }
+  const double mean = sums[c] / rows;
+  double biased = sums[cols + c] / rows - mean * mean;
+  if (biased < 0.0) biased = 0.0;
+  const double unbiased = rows > 1.0 ? biased * rows / (rows - 1.0) : biased;
+  mean_out[c] = static_cast<float>(mean);
+  inv_std[c] = static_cast<float>(1.0 / sqrt(biased + static_cast<double>(eps)));
+  if (running_mean) {
+    running_mean[c] = (1.f - momentum) * running_mean[c] + momentum * static_cast<float>(mean);
+    running_var[c] = (1.f - momentum) * running_var[c] + momentum * static_cast<float>(unbiased);
   }
 }
 
@@ -231,9 +246,10 @@ __global__ void leaky_bwd_kernel(float* __restrict__ da, const float* __restrict
 __global__ void bn_bwd_apply_kernel(const float* __restrict__ dy, const float* __restrict__ xhat, long long rows, int cols,
                                     const float* __restrict__ gamma, const float* __restrict__ inv_std,
                                     const float* __restrict__ dgamma, const float* __restrict__ dbeta,
-                                    float* __restrict__ dz) {
+                                    const double* __restrict__ total_rows, float* __restrict__ dz) {
   const long long total = rows * cols;
-  const float inv_rows = 1.f / static_cast<float>(rows);
+  // dgamma / dbeta are sums over ALL rows of the batch (all ranks); total_rows is that row count (device memory)
+  const float inv_rows = static_cast<float>(1.0 / fmax(*total_rows, 1.0));
   for (long long i = blockIdx.x * 1LL * blockDim.x + threadIdx.x; i < total; i += 1LL * gridDim.x * blockDim.x) {
     const int c = static_cast<int>(i % cols);
     const float g = gamma[c];
@@ -534,29 +550,66 @@ int me_col2im3_f32(const float* dcols, int n, int h, int w, int c, float* dx, me
   return ME_OK;
 }
 
-int me_bn_train_fwd(const float* z, long long rows, int cols, const float* gamma, const float* beta, float eps,
-                    float momentum, float* running_mean, float* running_var, float* mean_ws, float* inv_std,
-                    float* xhat, float* a, me_stream_t stream_) {
+int me_bn_partial_stats(const float* z, long long rows, int cols, double* sums, me_stream_t stream) {
   using namespace me;
-  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-  ME_REQUIRE(z && gamma && beta && mean_ws && inv_std && xhat && a && rows > 0 && cols > 0, "bn_train_fwd: bad argument");
-  bn_stats_kernel<<<(cols + 31) / 32, 256, 0, stream>>>(z, rows, cols, eps, momentum, running_mean, running_var, mean_ws,
-                                                       inv_std);
-  bn_apply_kernel<<<grid_for(rows * cols), 256, 0, stream>>>(z, rows, cols, mean_ws, inv_std, gamma, beta, xhat, a);
+  ME_REQUIRE(sums && cols > 0 && rows >= 0 && (rows == 0 || z), "bn_partial_stats: bad argument");
+  bn_partial_kernel<<<(cols + 31) / 32, 256, 0, static_cast<cudaStream_t>(stream)>>>(z, rows, cols, sums);
   ME_LAUNCH_CHECK();
   return ME_OK;
 }
 
-int me_bn_train_bwd(float* da_inout, const float* a, const float* xhat, long long rows, int cols, const float* gamma,
-                    const float* inv_std, float* dgamma, float* dbeta, float* dz, me_stream_t stream_) {
+int me_bn_finalize(const double* sums, int cols, float eps, float momentum, float* running_mean, float* running_var,
+                   float* mean_out, float* inv_std, me_stream_t stream) {
+  using namespace me;
+  ME_REQUIRE(sums && mean_out && inv_std && cols > 0, "bn_finalize: bad argument");
+  bn_finalize_kernel<<<(cols + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(sums, cols, eps, momentum, running_mean,
+                                                                                        running_var, mean_out, inv_std);
+  ME_LAUNCH_CHECK();
+  return ME_OK;
+}
+
+int me_bn_apply(const float* z, long long rows, int cols, const float* mean, const float* inv_std, const float* gamma,
+                const float* beta, float* xhat, float* a, me_stream_t stream) {
+  using namespace me;
+  if (rows <= 0) return ME_OK;
+  ME_REQUIRE(z && mean && inv_std && gamma && beta && xhat && a && cols > 0, "bn_apply: bad argument");
+  bn_apply_kernel<<<grid_for(rows * cols), 256, 0, static_cast<cudaStream_t>(stream)>>>(z, rows, cols, mean, inv_std, gamma, beta,
+                                                                                        xhat, a);
+  ME_LAUNCH_CHECK();
+  return ME_OK;
+}
+
+int me_bn_train_fwd(const float* z, long long rows, int cols, const float* gamma, const float* beta, float eps,
+                    float momentum, float* running_mean, float* running_var, double* sums_ws, float* mean_ws, float* inv_std,
+                    float* xhat, float* a, me_stream_t stream) {
+  int rc = me_bn_partial_stats(z, rows, cols, sums_ws, stream);
+  if (rc != ME_OK) return rc;
+  rc = me_bn_finalize(sums_ws, cols, eps, momentum, running_mean, running_var, mean_ws, inv_std, stream);
+  if (rc != ME_OK) return rc;
+  return me_bn_apply(z, rows, cols, mean_ws, inv_std, gamma, beta, xhat, a, stream);
+}
+
+int me_bn_bwd_sums(float* da_inout, const float* a, const float* xhat, long long rows, int cols, float* dgamma, float* dbeta,
+                   me_stream_t stream_) {
   using namespace me;
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
-  ME_REQUIRE(da_inout && a && xhat && gamma && inv_std && dgamma && dbeta && dz && rows > 0 && cols > 0,
-             "bn_train_bwd: bad argument");
-  leaky_bwd_kernel<<<grid_for(rows * cols), 256, 0, stream>>>(da_inout, a, rows * cols);
+  ME_REQUIRE(dgamma && dbeta && cols > 0 && rows >= 0 && (rows == 0 || (da_inout && a && xhat)), "bn_bwd_sums: bad argument");
+  if (rows > 0) leaky_bwd_kernel<<<grid_for(rows * cols), 256, 0, stream>>>(da_inout, a, rows * cols);
   colsum_kernel<<<(cols + 31) / 32, 256, 0, stream>>>(da_inout, xhat, rows, cols, cols, cols, dgamma);
   colsum_kernel<<<(cols + 31) / 32, 256, 0, stream>>>(da_inout, nullptr, rows, cols, cols, cols, dbeta);
-  bn_bwd_apply_kernel<<<grid_for(rows * cols), 256, 0, stream>>>(da_inout, xhat, rows, cols, gamma, inv_std, dgamma, dbeta, dz);
+  ME_LAUNCH_CHECK();
+  return ME_OK;
+}
+
+int me_bn_bwd_apply(const float* dy, const float* xhat, long long rows, int cols, const float* gamma, const float* inv_std,
+                    const float* dgamma_total, const float* dbeta_total, const double* total_rows, float* dz,
+                    me_stream_t stream) {
+  using namespace me;
+  if (rows <= 0) return ME_OK;
+  ME_REQUIRE(dy && xhat && gamma && inv_std && dgamma_total && dbeta_total && total_rows && dz && cols > 0,
+             "bn_bwd_apply: bad argument");
+  bn_bwd_apply_kernel<<<grid_for(rows * cols), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+      dy, xhat, rows, cols, gamma, inv_std, dgamma_total, dbeta_total, total_rows, dz);
   ME_LAUNCH_CHECK();
   return ME_OK;
 }

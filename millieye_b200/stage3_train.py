@@ -58,16 +58,48 @@ def colsum(x, out, y=None):
     return out
 
 
-def bn_train_fwd(z, gamma, beta, running_mean, running_var, mean_ws, inv_std, xhat, a):
+def _all_reduce(t, group):
+    """SUM over ranks in place (NCCL on GPUs; with the gloo backend - CPU-side tests - a CUDA tensor is staged through
+    host memory)."""
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        if t.is_cuda and dist.get_backend(group) == "gloo":
+            host = t.cpu()
+            dist.all_reduce(host, op=dist.ReduceOp.SUM, group=group)
+            t.copy_(host)
+        else:
+            dist.all_reduce(t, op=dist.ReduceOp.SUM, group=group)
+
+
+def bn_train_fwd(z, gamma, beta, running_mean, running_var, sums, mean_ws, inv_std, xhat, a, group=None, sync=False):
+    """BatchNorm on batch statistics + LeakyReLU.  sums: float64 [2*cols + 1] (sum, sum of squares, row count) - with
+    sync=True the ranks add theirs (ONE small all-reduce), so every rank normalises with the statistics of the whole
+    batch and updates its running statistics identically."""
+    L = _lib.lib()
     rows, cols = z.shape
-    check(_lib.lib().me_bn_train_fwd(ptr(z), rows, cols, ptr(gamma), ptr(beta), EPS, MOMENTUM, ptr(running_mean), ptr(running_var),
-                                     ptr(mean_ws), ptr(inv_std), ptr(xhat), ptr(a), stream_ptr()), "me_bn_train_fwd")
+    check(L.me_bn_partial_stats(ptr(z), rows, cols, ptr(sums), stream_ptr()), "me_bn_partial_stats")
+    if sync:
+        _all_reduce(sums, group)
+    check(L.me_bn_finalize(ptr(sums), cols, EPS, MOMENTUM, ptr(running_mean), ptr(running_var), ptr(mean_ws), ptr(inv_std),
+                           stream_ptr()), "me_bn_finalize")
+    check(L.me_bn_apply(ptr(z), rows, cols, ptr(mean_ws), ptr(inv_std), ptr(gamma), ptr(beta), ptr(xhat), ptr(a), stream_ptr()),
+          "me_bn_apply")
 
 
-def bn_train_bwd(da, a, xhat, gamma, inv_std, dgamma, dbeta, dz):
+def bn_train_bwd(da, a, xhat, gamma, inv_std, sums, dgamma, dbeta, dz, scratch, group=None, sync=False):
+    """dgamma / dbeta receive THIS rank's sums (the gradient all-reduce adds the ranks later); the input gradient uses
+    the sums over the whole batch (all-reduced copy in `scratch`, float32 [2*cols]) and its row count (sums[2*cols])."""
+    L = _lib.lib()
     rows, cols = a.shape
-    check(_lib.lib().me_bn_train_bwd(ptr(da), ptr(a), ptr(xhat), rows, cols, ptr(gamma), ptr(inv_std), ptr(dgamma), ptr(dbeta),
-                                     ptr(dz), stream_ptr()), "me_bn_train_bwd")
+    check(L.me_bn_bwd_sums(ptr(da), ptr(a), ptr(xhat), rows, cols, ptr(dgamma), ptr(dbeta), stream_ptr()), "me_bn_bwd_sums")
+    tg, tb = dgamma, dbeta
+    if sync:
+        scratch[:cols].copy_(dgamma.reshape(-1))
+        scratch[cols:2 * cols].copy_(dbeta.reshape(-1))
+        _all_reduce(scratch, group)
+        tg, tb = scratch[:cols], scratch[cols:2 * cols]
+    check(L.me_bn_bwd_apply(ptr(da), ptr(xhat), rows, cols, ptr(gamma), ptr(inv_std), ptr(tg), ptr(tb),
+                            ctypes.c_void_p(sums.data_ptr() + 16 * cols), ptr(dz), stream_ptr()), "me_bn_bwd_apply")
 
 
 def roi_align_f32(ps, feat, n, h, w, channels, rois, num_rois, out=None, grad_out=None, dfeat=None):
@@ -96,17 +128,28 @@ class HeadTrainer:
     """fp32 train-mode forward and backward of the heads.  `params` / `buffers`: {reference key: fp32 cuda tensor}
     (the live nn.Parameter / buffer storage: running statistics are updated in place like nn.BatchNorm2d does)."""
 
-    def __init__(self, device):
-        self.device = device
+    def __init__(self, device, group=None, sync_bn=None):
+        """sync_bn: None = synchronise BatchNorm statistics whenever torch.distributed runs with more than one rank
+        (the sharded step then reproduces the single-process step on the whole batch); False = per-shard statistics
+        (what DistributedDataParallel does without SyncBatchNorm)."""
+        self.device, self.group = device, group
+        if sync_bn is None:
+            import torch.distributed as dist
+            sync_bn = dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1
+        self.sync_bn = bool(sync_bn)
         self._bufs = {}
 
-    def _buf(self, name, shape, zero=False):
+    def _buf(self, name, shape, zero=False, dtype=torch.float32):
         t = self._bufs.get(name)
-        if t is None or tuple(t.shape) != tuple(shape):
-            t = self._bufs[name] = torch.zeros(shape, dtype=torch.float32, device=self.device)
+        if t is None or tuple(t.shape) != tuple(shape) or t.dtype != dtype:
+            t = self._bufs[name] = torch.zeros(shape, dtype=dtype, device=self.device)
         elif zero:
             t.zero_()
         return t
+
+    def _rows(self, name, rows, cols, zero=False):
+        """[rows, cols] view of a buffer that always has at least one row (kernels get valid pointers for 0 rows)."""
+        return self._buf(name, (max(rows, 1), cols), zero=zero)[:rows]
 
     # ------------------------------------------------------------------ forward
     def forward(self, params, buffers, feat_rows, maps_rows, n, g, rois, img_boxes, n_img, n_all, regress_out=None,
@@ -129,8 +172,10 @@ class HeadTrainer:
         zi = gemm_nt(feat_rows, wi, B("zi", (P, 490)), p["img_cnn_layers.net.conv_0.bias"])
         rm, rv = running("img_cnn_layers.net.batch_norm_0.")
         c["xhi"], c["ai"], c["istdi"] = B("xhi", (P, 490)), B("ai", (P, 490)), B("istdi", (490,))
+        sb = dict(group=self.group, sync=self.sync_bn)
+        c["sumsi"] = B("sumsi", (2 * 490 + 1,), dtype=torch.float64)
         bn_train_fwd(zi, p["img_cnn_layers.net.batch_norm_0.weight"], p["img_cnn_layers.net.batch_norm_0.bias"], rm, rv,
-                     B("meani", (490,)), c["istdi"], c["xhi"], c["ai"])
+                     c["sumsi"], B("meani", (490,)), c["istdi"], c["xhi"], c["ai"], **sb)
         # radar_cnn_layers: three 3x3 conv + BN + LeakyReLU, 1x1 conv + sigmoid   (:133-157)
         a = maps_rows
         c["a0"] = a
@@ -141,38 +186,39 @@ class HeadTrainer:
             z = gemm_nt(cols, w, B(f"z{i}", (P, cout)), p[f"radar_cnn_layers.{name}.0.bias"])
             rm, rv = running(f"radar_cnn_layers.{name}.1.")
             xh, act, istd = B(f"xh{i}", (P, cout)), B(f"a{i}", (P, cout)), B(f"istd{i}", (cout,))
+            c[f"sums{i}"] = B(f"sums{i}", (2 * cout + 1,), dtype=torch.float64)
             bn_train_fwd(z, p[f"radar_cnn_layers.{name}.1.weight"], p[f"radar_cnn_layers.{name}.1.bias"], rm, rv,
-                         B(f"mean{i}", (cout,)), istd, xh, act)
+                         c[f"sums{i}"], B(f"mean{i}", (cout,)), istd, xh, act, **sb)
             c[f"cols{i}"], c[f"xh{i}"], c[f"a{i}"], c[f"istd{i}"] = cols, xh, act, istd
             a = act
         w4 = p["radar_cnn_layers.conv3.3.weight"].view(10, 128)
         c["s"] = gemm_nt(a, w4, B("s", (P, 10)), p["radar_cnn_layers.conv3.3.bias"], ME_ACT_SIGMOID)
-        if n_all == 0:
-            return c
-        R = n_all
+        R = n_all   # may be 0 on this rank: every call below then works on empty row sets (the collectives still run)
+        RB = self._rows
         # RoI crops (:495-496), flatten order (c, ph, pw)
-        c["x_img"] = B("x_img", (R, 490))
-        c["x_rad"] = B("x_rad", (R, 490))
+        c["x_img"] = RB("x_img", R, 490)
+        c["x_rad"] = RB("x_rad", R, 490)
         roi_align_f32(True, c["ai"], n, g, g, 10, rois, R, out=c["x_img"])
         roi_align_f32(False, c["s"], n, g, g, 10, rois, R, out=c["x_rad"])
         # refinement_head (:260-284)
         h = "refinement_head."
-        c["t"] = gemm_nt(c["x_img"], p[h + "net0.0.weight"], B("t", (R, 256)), p[h + "net0.0.bias"], ME_ACT_LEAKY)
-        regress = regress_out if regress_out is not None else B("regress", (R, 4))
+        c["t"] = gemm_nt(c["x_img"], p[h + "net0.0.weight"], RB("t", R, 256), p[h + "net0.0.bias"], ME_ACT_LEAKY)
+        regress = regress_out if regress_out is not None else B("regress", (max(R, 1), 4))
         gemm_nt(c["t"], p[h + "net1.0.weight"], regress[:R], p[h + "net1.0.bias"])
-        c["cls"] = gemm_nt(c["t"], p[h + "net2.0.weight"], B("cls", (R, 13)), p[h + "net2.0.bias"], ME_ACT_SIGMOID)
+        c["cls"] = gemm_nt(c["t"], p[h + "net2.0.weight"], RB("cls", R, 13), p[h + "net2.0.bias"], ME_ACT_SIGMOID)
         wr = p[h + "radar_net.0.weight"].view(10, 490)
-        r1 = gemm_nt(c["x_rad"], wr, B("r1", (R, 10)), p[h + "radar_net.0.bias"])
+        r1 = gemm_nt(c["x_rad"], wr, RB("r1", R, 10), p[h + "radar_net.0.bias"])
         rm, rv = running(h + "radar_net.1.")
-        c["xhr"], c["ar"], c["istdr"] = B("xhr", (R, 10)), B("ar", (R, 10)), B("istdr", (10,))
-        bn_train_fwd(r1, p[h + "radar_net.1.weight"], p[h + "radar_net.1.bias"], rm, rv, B("meanr", (10,)), c["istdr"], c["xhr"],
-                     c["ar"])
-        r2 = gemm_nt(c["ar"], p[h + "radar_net.3.weight"].view(1, 10), B("r2", (R, 1)), p[h + "radar_net.3.bias"])
+        c["xhr"], c["ar"], c["istdr"] = RB("xhr", R, 10), RB("ar", R, 10), B("istdr", (10,))
+        c["sumsr"] = B("sumsr", (21,), dtype=torch.float64)
+        bn_train_fwd(r1, p[h + "radar_net.1.weight"], p[h + "radar_net.1.bias"], rm, rv, c["sumsr"], B("meanr", (10,)),
+                     c["istdr"], c["xhr"], c["ar"], **sb)
+        r2 = gemm_nt(c["ar"], p[h + "radar_net.3.weight"].view(1, 10), RB("r2", R, 1), p[h + "radar_net.3.bias"])
         # confidence, ensemble head, masks (:276-284, 202-210, 513-514)
         e = "ensemble_head."
-        c["rc"], c["p"] = B("rc", (R,)), B("p", (max(n_img, 1), 2))
-        refine = refine_out if refine_out is not None else B("refine", (R, 2))
-        mask = mask_out if mask_out is not None else B("mask", (R,))
+        c["rc"], c["p"] = B("rc", (max(R, 1),)), B("p", (max(n_img, 1), 2))
+        refine = refine_out if refine_out is not None else B("refine", (max(R, 1), 2))
+        mask = mask_out if mask_out is not None else B("mask", (max(R, 1),))
         check(L.me_stage3_tail_fwd(ptr(r2), ptr(c["cls"]), 13, ptr(img_boxes), n_img, R, ptr(p[e + "fc1.0.weight"]),
                                    ptr(p[e + "fc1.0.bias"]), ptr(p[e + "fc2.0.weight"]), ptr(p[e + "fc2.0.bias"]), ptr(c["rc"]),
                                    ptr(refine), ptr(mask), ptr(c["p"]), stream_ptr()), "me_stage3_tail_fwd")
@@ -193,15 +239,12 @@ class HeadTrainer:
             grads[name] = t
             return t
 
-        if R == 0:
-            for name in TRAINABLE:
-                if image_path or name not in IMAGE_PATH:
-                    G(name).zero_()
-            return grads
         e, h, q = "ensemble_head.", "refinement_head.", "radar_cnn_layers."
         ni = max(n_img, 1)
+        RB = self._rows
+        sb = dict(group=self.group, sync=self.sync_bn)
         d_o, hl, dhp, u = B("d_o", (ni, 2)), B("hl", (ni, 64)), B("dhp", (2 * ni, 32)), B("u", (2 * ni, 2))
-        dr2, dz2 = B("dr2", (R, 1)), B("dz2", (R, 13))
+        dr2, dz2 = RB("dr2", R, 1), RB("dz2", R, 13)
         check(L.me_stage3_tail_bwd(ptr(c["rc"]), ptr(c["refine"]), ptr(c["cls"]), 13, ptr(c["p"]), ptr(c["img_boxes"]), n_img, R,
                                    ptr(pos), ptr(sel), float(alpha), float(lambda_conf), ptr(p[e + "fc1.0.weight"]),
                                    ptr(p[e + "fc1.0.bias"]), ptr(p[e + "fc2.0.weight"]), ptr(d_o), ptr(hl), ptr(dhp), ptr(u),
@@ -219,14 +262,14 @@ class HeadTrainer:
         w3 = p[h + "radar_net.3.weight"].view(1, 10)
         gemm_tn(dr2, c["ar"], G(h + "radar_net.3.weight").view(1, 10))
         colsum(dr2, G(h + "radar_net.3.bias"))
-        dar = gemm_nn(dr2, w3, B("dar", (R, 10)))
-        dr1 = B("dr1", (R, 10))
-        bn_train_bwd(dar, c["ar"], c["xhr"], p[h + "radar_net.1.weight"], c["istdr"], G(h + "radar_net.1.weight"),
-                     G(h + "radar_net.1.bias"), dr1)
+        dar = gemm_nn(dr2, w3, RB("dar", R, 10))
+        dr1 = RB("dr1", R, 10)
+        bn_train_bwd(dar, c["ar"], c["xhr"], p[h + "radar_net.1.weight"], c["istdr"], c["sumsr"], G(h + "radar_net.1.weight"),
+                     G(h + "radar_net.1.bias"), dr1, B("bnsr", (20,)), **sb)
         wr = p[h + "radar_net.0.weight"].view(10, 490)
         gemm_tn(dr1, c["x_rad"], G(h + "radar_net.0.weight").view(10, 490))
         colsum(dr1, G(h + "radar_net.0.bias"))
-        dx_rad = gemm_nn(dr1, wr, B("dx_rad", (R, 490)))
+        dx_rad = gemm_nn(dr1, wr, RB("dx_rad", R, 490))
         # RoIAlign adjoint -> radar score map -> radar_cnn_layers
         ds = B("ds", (P, 10), zero=True)
         roi_align_f32(False, None, n, g, g, 10, c["rois"], R, grad_out=dx_rad, dfeat=ds)
@@ -237,8 +280,8 @@ class HeadTrainer:
         da = gemm_nn(ds, w4, B("da3", (P, 128)))
         for i, name, cin, cout in ((3, "conv3", 64, 128), (2, "conv2", 32, 64), (1, "conv1", 3, 32)):
             dz = B(f"dz{i}", (P, cout))
-            bn_train_bwd(da, c[f"a{i}"], c[f"xh{i}"], p[f"{q}{name}.1.weight"], c[f"istd{i}"], G(f"{q}{name}.1.weight"),
-                         G(f"{q}{name}.1.bias"), dz)
+            bn_train_bwd(da, c[f"a{i}"], c[f"xh{i}"], p[f"{q}{name}.1.weight"], c[f"istd{i}"], c[f"sums{i}"],
+                         G(f"{q}{name}.1.weight"), G(f"{q}{name}.1.bias"), dz, B(f"bns{i}", (2 * cout,)), **sb)
             w = p[f"{q}{name}.0.weight"].view(cout, cin * 9)
             gemm_tn(dz, c[f"cols{i}"], G(f"{q}{name}.0.weight").view(cout, cin * 9))
             colsum(dz, G(f"{q}{name}.0.bias"))
@@ -251,17 +294,17 @@ class HeadTrainer:
         # image path: net2 -> net0 -> PS-RoIAlign adjoint -> BN -> 1x1 conv
         gemm_tn(dz2, c["t"], G(h + "net2.0.weight"))
         colsum(dz2, G(h + "net2.0.bias"))
-        dt = gemm_nn(dz2, p[h + "net2.0.weight"], B("dt", (R, 256)))
+        dt = gemm_nn(dz2, p[h + "net2.0.weight"], RB("dt", R, 256))
         check(L.me_leaky_bwd_f32(ptr(dt), ptr(c["t"]), R * 256, stream_ptr()), "me_leaky_bwd_f32")
         gemm_tn(dt, c["x_img"], G(h + "net0.0.weight"))
         colsum(dt, G(h + "net0.0.bias"))
-        dx_img = gemm_nn(dt, p[h + "net0.0.weight"], B("dx_img", (R, 490)))
+        dx_img = gemm_nn(dt, p[h + "net0.0.weight"], RB("dx_img", R, 490))
         dai = B("dai", (P, 490), zero=True)
         roi_align_f32(True, None, n, g, g, 10, c["rois"], R, grad_out=dx_img, dfeat=dai)
         dzi = B("dzi", (P, 490))
         i_ = "img_cnn_layers.net."
-        bn_train_bwd(dai, c["ai"], c["xhi"], p[i_ + "batch_norm_0.weight"], c["istdi"], G(i_ + "batch_norm_0.weight"),
-                     G(i_ + "batch_norm_0.bias"), dzi)
+        bn_train_bwd(dai, c["ai"], c["xhi"], p[i_ + "batch_norm_0.weight"], c["istdi"], c["sumsi"],
+                     G(i_ + "batch_norm_0.weight"), G(i_ + "batch_norm_0.bias"), dzi, B("bnsi", (980,)), **sb)
         gemm_tn(dzi, c["feat"], G(i_ + "conv_0.weight").view(490, 256))
         colsum(dzi, G(i_ + "conv_0.bias"))
         return grads
@@ -300,9 +343,7 @@ class Stage3Optimizer:
         self.grad.zero_()
 
     def all_reduce(self, group=None):
-        import torch.distributed as dist
-        if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
-            dist.all_reduce(self.grad, op=dist.ReduceOp.SUM, group=group)
+        _all_reduce(self.grad, group)
 
     def step(self):
         self.steps += 1

@@ -239,6 +239,9 @@ def test_filter_nms_golden(golden_dir, tag, mu, thr):
 @pytest.mark.parametrize("rows,classes,mu,thr", [
     (2535, 12, -6.0, 0.01), (2535, 12, -2.0, 0.25), (10647, 80, -5.0, 0.01), (10647, 80, -2.5, 0.2),
     (375, 12, 3.0, 0.01), (135, 1, -1.0, 0.5), (10647, 80, 4.0, 0.01),
+    # YOLOv3 at 448 / 480 / 512 / 608: 12 257..16 384 rows used to fail the shared-memory limit (keys + fixed areas),
+    # 22 743 rows sort in the global workspace
+    (12348, 80, -4.0, 0.05), (14175, 12, -3.0, 0.2), (16128, 80, -4.5, 0.01), (22743, 12, -4.0, 0.1),
 ])
 def test_filter_nms_vs_oracle(rows, classes, mu, thr):
     _check_nms(synth.synth_predictions(3, rows, classes, seed=rows + classes, conf_mu=mu), thr)

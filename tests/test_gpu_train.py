@@ -185,3 +185,80 @@ def test_training_step_through_the_drop_in(golden_dir):
     model.eval()
     out_eval = model(imgs.to(DEV), maps.to(DEV), rb.clone().to(DEV), 0)
     assert out_eval.shape[1] == 8
+
+
+# ------------------------------------------------------------------------------------------------ two ranks
+def _shard_worker(rank, world, port, golden_dir, q):
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        torch.set_num_threads(2)
+        sd, sdf, maps, res, gl = _oracle_step(golden_dir)
+        n, gsz = 4, 12
+        per = n // world
+        lo = rank * per
+        hw = gsz * gsz
+        feat_rows = res["feat"].permute(0, 2, 3, 1).reshape(n * hw, 256)[lo * hw:(lo + per) * hw].contiguous().to(DEV)
+        maps_rows = maps.permute(0, 2, 3, 1).reshape(n * hw, 3)[lo * hw:(lo + per) * hw].contiguous().to(DEV)
+        rois_all = res["box_locations"].float()
+        n_img_all = res["n_img"]
+        frame = rois_all[:, 0].long()
+        mine = (frame >= lo) & (frame < lo + per)
+        idx = torch.nonzero(mine).reshape(-1)                       # image proposals first, then radar: order kept
+        n_img = int((idx < n_img_all).sum())
+        rois = rois_all[idx].clone()
+        rois[:, 0] -= lo
+        img_boxes = torch.zeros((max(n_img, 1), 9))
+        img_boxes[:n_img, 5] = res["yolo_vec"][idx[:n_img], 0]
+        img_boxes[:n_img, 8] = res["yolo_vec"][idx[:n_img], 1]
+        pos = torch.from_numpy(res["pos"])[idx].to(torch.uint8).to(DEV)
+        sel = torch.from_numpy(res["sample_filter"])[idx].to(torch.uint8).to(DEV)
+        params = {k: v.clone().to(DEV).contiguous() for k, v in sdf.items() if v.is_floating_point()
+                  and not k.startswith("base_detector.") and "running_" not in k}
+        buffers = {k: v.clone().to(DEV) for k, v in sdf.items() if "running_" in k and not k.startswith("base_detector.")}
+        tr = st.HeadTrainer(DEV)                                    # two ranks -> synchronised BatchNorm statistics
+        assert tr.sync_bn
+        cache = tr.forward(params, buffers, feat_rows, maps_rows, per, gsz, rois.contiguous().to(DEV), img_boxes.to(DEV), n_img,
+                           len(idx))
+        grads = tr.backward(params, cache, pos, sel, 0.75, 6.0, image_path=True)
+        flat = torch.cat([grads[k].reshape(-1) for k in st.TRAINABLE])
+        st._all_reduce(flat, None)                                  # the gradient all-reduce (SUM: the losses are sums)
+        torch.cuda.synchronize()
+        out, off = {}, 0
+        for k in st.TRAINABLE:
+            cnt = grads[k].numel()
+            out[k] = flat[off:off + cnt].reshape(grads[k].shape).cpu().numpy()
+            off += cnt
+        q.put((rank, out, {k: v.cpu().numpy() for k, v in buffers.items()}, len(idx)))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.timeout(300)
+def test_two_rank_sharded_step_equals_reference_single_process(golden_dir):
+    """The batch of the gradient fixture split over two ranks (two frames and their proposals each; both ranks on this
+    GPU, gloo for the collectives): with synchronised BatchNorm statistics and a SUM all-reduce of the gradients every
+    rank ends up with the gradients - and running statistics - of the reference's single-process step on the whole
+    batch, to the same 1e-4 as the single-rank test."""
+    import socket
+    import torch.multiprocessing as mp
+    g = np.load(os.path.join(golden_dir, "stage3_grads_tiny12_192.npz"))
+    with socket.socket() as sck:
+        sck.bind(("127.0.0.1", 0))
+        port = sck.getsockname()[1]
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_shard_worker, args=(r, 2, port, golden_dir, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    results = sorted([q.get(timeout=240) for _ in range(2)], key=lambda t: t[0])
+    for p in procs:
+        p.join(60)
+        assert p.exitcode == 0
+    assert sum(r[3] for r in results) == int(g["total"])
+    for rank, grads, bufs, _ in results:
+        _check_grads({k: torch.from_numpy(v) for k, v in grads.items()}, g)
+        for k in g.files:
+            if k.startswith("buf/"):
+                assert np.abs(bufs[k[4:]] - g[k]).max() <= 1e-5, (rank, k)
