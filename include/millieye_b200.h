@@ -303,6 +303,17 @@ typedef struct me_radar_cfg {
 int me_radar_maps(const float* points, const int* counts, int n, int cap, const me_radar_cfg* cfg,
                   float* maps_out, float* uvzv_out, int* kept_out, me_stream_t stream);
 
+/* ---- YOLO training loss --------------------------------------------------------------------------
+ * YOLOLayer.forward with targets (yolov3/models.py:180-232) + build_targets (utils/utils.py:381-440) for ONE detection
+ * layer, on the fp32 head logits [n][g][g][pitch] the forward leaves on the device; targets: device (m,6)
+ * [image, class, cx, cy, w, h] in 0..1.  out14 = loss, x, y, w, h, conf, cls, cls_acc, recall50, recall75, precision,
+ * conf_obj, conf_noobj, grid_size (the layer's `metrics` dictionary, in the reference's order).  Forward value only. */
+size_t me_yolo_loss_workspace(int n, int g, int num_anchors);
+int me_yolo_loss(const float* logits, int pitch, int n, int g, int num_anchors, int num_classes,
+                 const float* host_anchors_wh, float stride, const float* targets, int num_targets, float ignore_thres,
+                 float obj_scale, float noobj_scale, void* workspace, size_t workspace_bytes, float* out14,
+                 me_stream_t stream);
+
 /* ---- stage-3 training step (train.py:169-191, my_models.py:545-640 + autograd) -----------
  * fp32 building blocks of the train-mode forward and the hand-derived backward of the heads that train
  * (img_cnn_layers, radar_cnn_layers, refinement_head, ensemble_head); the frozen detector stays on the tensor-core

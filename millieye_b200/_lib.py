@@ -97,6 +97,9 @@ SIGNATURES = {
     "me_stage3_labels": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_void_p]),
     "me_stage3_loss": (c_int, [c_void_p] * 5 + [c_int, c_void_p, c_void_p, c_void_p, POINTER(Stage3LossCfg), c_void_p,
                                c_void_p]),
+    "me_yolo_loss_workspace": (c_size_t, [c_int, c_int, c_int]),
+    "me_yolo_loss": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, POINTER(c_float), c_float, c_void_p, c_int, c_float,
+                             c_float, c_float, c_void_p, c_size_t, c_void_p, c_void_p]),
     "me_gemm_f32": (c_int, [c_int, c_int, c_int, c_void_p, c_longlong, c_longlong, c_void_p, c_longlong, c_longlong, c_void_p,
                             c_longlong, c_void_p, c_int, c_int, c_void_p]),
     "me_colsum_f32": (c_int, [c_void_p, c_void_p, c_longlong, c_int, c_longlong, c_longlong, c_void_p, c_void_p]),

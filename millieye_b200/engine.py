@@ -373,6 +373,15 @@ class DarknetPlan:
         self.op_kinds.append(kind)
         self.op_blocks.append(block)
 
+    def head_logits(self):
+        """[(fp32 logits view of the current slot, yolo block, grid size)] in cfg order (empty views are skipped when
+        the decode is fused into the head conv)."""
+        out = []
+        for i, b in enumerate(self.blocks):
+            if b["type"] == "yolo" and self.views[i] is not None:
+                out.append((self._slot_view(self.views[i]), b, self.hw[i]))
+        return out
+
     def _slot_view(self, v):
         """The view's buffer of the current slot (only head-logit views have a second one)."""
         alt = getattr(v, "alt", None)

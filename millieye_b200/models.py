@@ -19,6 +19,11 @@ from .engine import DarknetPlan, describe_blocks
 from .parse_config import parse_model_config
 
 
+def _lib_bytes(n, g, na):
+    from . import _lib
+    return int(_lib.lib().me_yolo_loss_workspace(n, g, na))
+
+
 class _Holder(nn.Module):
     """Parameter-free placeholder keeping the reference's module names (route_, shortcut_, yolo_ ...)."""
 
@@ -129,9 +134,10 @@ class Darknet(nn.Module):
         return plan
 
     def forward(self, x, targets=None):
-        if targets is not None:
-            raise MeError("the YOLO training loss (models.py:180-232) is outside the accelerated path; "
-                          "no reference script calls it (SURVEY.md F10)")
+        """(featuremap, yolo_outputs), or with targets (m,6) [image, class, cx, cy, w, h] in 0..1 the reference's
+        (loss, featuremap, yolo_outputs) (models.py:247-267): loss = sum of the YOLO layers' losses, every layer's
+        `metrics` dictionary filled like models.py:212-227.  The loss is a value: the backward pass through the detector
+        is not part of the accelerated path (the reference has no stage-1 training script)."""
         plan = self.forward_device(x)
         n = plan.n
         with torch.cuda.device(plan.device):
@@ -141,7 +147,31 @@ class Darknet(nn.Module):
             else:
                 feat = torch.empty(0, device=plan.device)
             self.featuremap = feat
-            return feat, plan.yolo_out.clone()
+            if targets is None:
+                return feat, plan.yolo_out.clone()
+            return self._yolo_loss(plan, targets), feat, plan.yolo_out.clone()
+
+    def _yolo_loss(self, plan, targets):
+        heads = plan.head_logits()
+        if len(heads) != len(self.yolo_layers):
+            raise MeError("the YOLO loss needs the head logits: run without ME_FUSE_DECODE=1")
+        dev = plan.device
+        t = targets.detach().to(device=dev, dtype=torch.float32).contiguous()
+        out = torch.zeros((len(heads), 14), dtype=torch.float32, device=dev)
+        for k, (view, blk, g) in enumerate(heads):
+            need = _lib_bytes(plan.n, g, len(blk["anchors"]))
+            ws = getattr(plan, "_loss_ws", None)
+            if ws is None or ws.numel() < need:
+                ws = plan._loss_ws = torch.empty((need,), dtype=torch.uint8, device=dev)
+            layer = self.yolo_layers[k]
+            ops.yolo_loss(view.t, view.pitch, plan.n, g, blk["anchors"], blk["classes"], plan.size / g, t, out[k], ws,
+                          layer.ignore_thres, layer.obj_scale, layer.noobj_scale)
+        vals = out.cpu()
+        for k, layer in enumerate(self.yolo_layers):
+            layer.metrics = {key: (int(vals[k, j]) if key == "grid_size" else float(vals[k, j]))
+                             for j, key in enumerate(ops.METRIC_KEYS)}
+            layer.grid_size = int(vals[k, 13])
+        return out[:, 0].sum()
 
     # ------------------------------------------------------------------ darknet binary weights
     def _conv_bn_pairs(self, cutoff=None):

@@ -241,6 +241,27 @@ def yolo_decode(logits, pitch, out, n, g, anchors, num_classes, stride, rows_tot
     return out
 
 
+METRIC_KEYS = ("loss", "x", "y", "w", "h", "conf", "cls", "cls_acc", "recall50", "recall75", "precision", "conf_obj",
+               "conf_noobj", "grid_size")
+
+
+def yolo_loss(logits, pitch, n, g, anchors, num_classes, stride, targets, out14, workspace, ignore_thres=0.5, obj_scale=1.0,
+              noobj_scale=100.0):
+    """Loss + metrics of one YOLO layer (reference models.py:180-232, utils.py:381-440) -> out14 (fp32 cuda, 14 values)."""
+    _need_cuda(logits, out14, workspace)
+    m = 0 if targets is None else int(targets.shape[0])
+    if m:
+        _need_cuda(targets)
+        assert targets.dtype == torch.float32 and targets.is_contiguous()
+    flat = [float(v) for wh in anchors for v in wh]
+    arr = (c_float * len(flat))(*flat)
+    check(_lib.lib().me_yolo_loss(ptr(logits), pitch, n, g, len(anchors), num_classes, arr, float(stride),
+                                  ptr(targets) if m else None, m, float(ignore_thres), float(obj_scale), float(noobj_scale),
+                                  ptr(workspace), workspace.numel() * workspace.element_size(), ptr(out14), stream_ptr()),
+          "me_yolo_loss")
+    return out14
+
+
 class NmsBuffers:
     """Reusable outputs + workspace of filter_nms for one (n, rows, classes) shape."""
 
