@@ -239,9 +239,10 @@ typedef struct me_stage2_weights {
   const float* fc1_w;  const float* fc1_b;    /* 32 x 2                          */
   const float* fc2_w;  const float* fc2_b;    /* 2 x (32 * num_vec)              */
 } me_stage2_weights;
+/* refine_out (may be NULL): [cap][num_vec] refinement vectors (confidence, class scores), kept for the loss branch. */
 int me_stage2_heads(const void* hidden, int hidden_pitch, const me_stage2_weights* hw, const float* boxes,
                     int box_pitch, int num_vec, const int* counts, int cap, float* regress, float* mask,
-                    me_stream_t stream);
+                    float* refine_out, me_stream_t stream);
 
 /* Threshold, box regression, priority sort (my_models.py:516-539, box_regress :378-391).
  * out [cap][8] = [i,x1,y1,x2,y2,new_conf,class_score,class_pred] sorted by mask descending with
@@ -281,6 +282,20 @@ typedef struct me_stage3_loss_cfg {
 int me_stage3_loss(const float* rois, const float* refine, const float* regress, const float* mask, const int* counts,
                    int cap, const float* iou_labels, const float* target_location, const unsigned char* sample_filter,
                    const me_stage3_loss_cfg* cfg, float* out10, me_stream_t stream);
+
+/* Stage-2 training branch (module2_mixed/my_models.py:363-461) on the stage-2 forward's buffers (labels from
+ * me_stage3_labels - obtain_iou_labels is the same routine in both modules; sample_filter drawn on the host as above):
+ * FocalLoss over the sampled proposals' masks (:420), confidence BCE (:424-429), regression_loss (:432-435), category BCE
+ * over the num_vec - 1 class scores of the positives with the reference's row-i label indexing (:438-443).  out10:
+ *   [0] masks  [1] conf  [2] xy  [3] wh  [4] category  [5] loss = [0] + ([1] + [4]) / lambda0 + ([2] + [3]) / lambda1 (:445)
+ *   [6] true  [7] refined (mask > thr)  [8] true positives  [9] proposals.   pos_ws: cap ints of scratch. */
+typedef struct me_stage2_loss_cfg {
+  float iou_hi, alpha, lambda0, lambda1, thr;
+} me_stage2_loss_cfg;
+int me_stage2_loss(const float* boxes, int box_pitch, const float* rois, const float* refine, int refine_pitch,
+                   const float* regress, const float* mask, const int* counts, int cap, const float* iou_labels,
+                   const float* target_location, const unsigned char* sample_filter, const me_stage2_loss_cfg* cfg,
+                   int* pos_ws, float* out10, me_stream_t stream);
 
 /* ---- radar point cloud -> network input map (f1 + f2) ----------------------- */
 typedef struct me_radar_cfg {

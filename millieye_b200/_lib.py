@@ -45,6 +45,10 @@ class Stage3LossCfg(Structure):
     _fields_ = [(n, c_float) for n in ("iou_hi", "alpha", "lambda_conf", "thr_img", "thr_radar")]
 
 
+class Stage2LossCfg(Structure):
+    _fields_ = [(n, c_float) for n in ("iou_hi", "alpha", "lambda0", "lambda1", "thr")]
+
+
 class Stage2Weights(Structure):
     _fields_ = [(n, c_void_p) for n in ("net1_w", "net1_b", "net2_w", "net2_b", "fc1_w", "fc1_b", "fc2_w", "fc2_b")]
 
@@ -93,7 +97,9 @@ SIGNATURES = {
     "me_finalize_workspace": (c_size_t, [c_int]),
     "me_radar_maps": (c_int, [c_void_p, c_void_p, c_int, c_int, POINTER(RadarCfg), c_void_p, c_void_p, c_void_p, c_void_p]),
     "me_stage2_heads": (c_int, [c_void_p, c_int, POINTER(Stage2Weights), c_void_p, c_int, c_int, c_void_p, c_int, c_void_p,
-                                c_void_p, c_void_p]),
+                                c_void_p, c_void_p, c_void_p]),
+    "me_stage2_loss": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_int, c_void_p,
+                               c_void_p, c_void_p, POINTER(Stage2LossCfg), c_void_p, c_void_p, c_void_p]),
     "me_stage3_labels": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_int, c_void_p, c_int, c_void_p, c_void_p, c_void_p]),
     "me_stage3_loss": (c_int, [c_void_p] * 5 + [c_int, c_void_p, c_void_p, c_void_p, POINTER(Stage3LossCfg), c_void_p,
                                c_void_p]),

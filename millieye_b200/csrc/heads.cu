@@ -192,7 +192,7 @@ template <int NV>
 __global__ void __launch_bounds__(256)
 stage2_heads_kernel(const __half* __restrict__ hidden, int hidden_pitch, me_stage2_weights hw,
                     const float* __restrict__ boxes, int box_pitch, const int* __restrict__ counts, int cap,
-                    float* __restrict__ regress, float* __restrict__ mask) {
+                    float* __restrict__ regress, float* __restrict__ mask, float* __restrict__ refine) {
   const int lane = threadIdx.x & 31;
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int nwarps = (gridDim.x * blockDim.x) >> 5;
@@ -227,6 +227,7 @@ stage2_heads_kernel(const __half* __restrict__ hidden, int hidden_pitch, me_stag
 #pragma unroll
       for (int e = 0; e < 8; ++e) s = fmaf(hv[e], wrow[e], s);
       const float refv = sigmoidf_(warp_sum(s) + hw.net2_b[j]);
+      if (refine != nullptr && lane == 0) refine[static_cast<size_t>(r) * NV + j] = refv;   // kept for the loss branch
       const float yolo = j == 0 ? box[5] : box[8 + (j - 1)];  // (obj_conf, class scores) m2 :347
       const float hcell = leakyf_(fmaf(hw.fc1_w[lane * 2], refv, fmaf(hw.fc1_w[lane * 2 + 1], yolo, hw.fc1_b[lane])));
       o0 = fmaf(hcell, hw.fc2_w[j * 32 + lane], o0);
@@ -365,7 +366,8 @@ int me_fusion_heads(const void* hidden, int hidden_pitch, const void* radar_crop
 }
 
 int me_stage2_heads(const void* hidden, int hidden_pitch, const me_stage2_weights* hw, const float* boxes, int box_pitch,
-                    int num_vec, const int* counts, int cap, float* regress, float* mask, me_stream_t stream_) {
+                    int num_vec, const int* counts, int cap, float* regress, float* mask, float* refine_out,
+                    me_stream_t stream_) {
   using namespace me;
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   ME_REQUIRE(hidden && hw && boxes && counts && regress && mask, "stage2_heads: null argument");
@@ -375,7 +377,7 @@ int me_stage2_heads(const void* hidden, int hidden_pitch, const me_stage2_weight
   int blocks = ceil_div(cap, 8);
   if (blocks > 148 * 4) blocks = 148 * 4;
   stage2_heads_kernel<13><<<blocks, 256, 0, stream>>>(static_cast<const __half*>(hidden), hidden_pitch, *hw, boxes,
-                                                      box_pitch, counts, cap, regress, mask);
+                                                      box_pitch, counts, cap, regress, mask, refine_out);
   ME_LAUNCH_CHECK();
   return ME_OK;
 }

@@ -150,6 +150,91 @@ stage3_loss_kernel(const float* __restrict__ rois, const float* __restrict__ ref
   }
 }
 
+
+// Stage-2 training branch (reference module2_mixed/my_models.py:363-461) on the stage-2 forward's buffers: every
+// proposal is an image proposal with a 13-entry refinement vector [conf, 12 class scores].  One block.
+//   out[0..4] = masks (focal), conf, xy, wh, category;  out[5] = masks + (conf + category) / l0 + (xy + wh) / l1 (:445)
+//   out[6..9] = true (labels > iou_hi), refined (mask > thr), tp, rows
+__global__ void __launch_bounds__(kBlock)
+stage2_loss_kernel(const float* __restrict__ boxes, int box_pitch, const float* __restrict__ rois,
+                   const float* __restrict__ refine, int refine_pitch, const float* __restrict__ regress,
+                   const float* __restrict__ mask, const int* __restrict__ counts, int cap,
+                   const float* __restrict__ iou_labels, const float* __restrict__ target_location,
+                   const unsigned char* __restrict__ sample_filter, me_stage2_loss_cfg cfg, int* __restrict__ pos_list,
+                   float* __restrict__ out) {
+  __shared__ double s_red[kBlock / 32];
+  __shared__ int s_npos;
+  const int n_all = min(counts[1], cap);
+  const int nc = refine_pitch - 1;
+  // ordered list of the positive rows: class_label row i takes the class of the i-th positive (:440-441)
+  if (threadIdx.x < 32) {
+    int base = 0;
+    for (int r0 = 0; r0 < n_all; r0 += 32) {
+      const int r = r0 + threadIdx.x;
+      const bool pos = r < n_all && iou_labels[r] > cfg.iou_hi;
+      const unsigned int b = __ballot_sync(0xffffffffu, pos);
+      if (pos) pos_list[base + __popc(b & ((1u << threadIdx.x) - 1))] = r;
+      base += __popc(b);
+    }
+    if (threadIdx.x == 0) s_npos = base;
+  }
+  __syncthreads();
+  const int P = s_npos;
+  double focal = 0.0, conf = 0.0, lxy = 0.0, lwh = 0.0, cat = 0.0, positive = 0.0, tp = 0.0;
+  for (int r = threadIdx.x; r < n_all; r += kBlock) {
+    const bool pos = iou_labels[r] > cfg.iou_hi;
+    const bool sel = sample_filter[r] != 0;
+    const float m = mask[r];
+    const bool refined = m > cfg.thr;
+    positive += refined ? 1.0 : 0.0;
+    tp += (refined && pos) ? 1.0 : 0.0;
+    if (sel) {
+      const float p = pos ? m : 1.f - m;   // masks = softmax output [1 - m, m]
+      const float a = pos ? cfg.alpha : 1.f - cfg.alpha;
+      const float q = 1.f - p;
+      focal += static_cast<double>(-a * (q * q) * logf(p));
+      const float x = refine[static_cast<size_t>(r) * refine_pitch];
+      const float y = pos ? 1.f : 0.f;
+      conf += static_cast<double>(-(y * fmaxf(logf(x), -100.f) + (1.f - y) * fmaxf(logf(1.f - x), -100.f)));
+    }
+    if (pos) {
+      const float x1 = rois[r * 5 + 1], y1 = rois[r * 5 + 2], x2 = rois[r * 5 + 3], y2 = rois[r * 5 + 4];
+      const float* g = target_location + r * 4;
+      const float x = (x1 + x2) / 2.f, y = (y1 + y2) / 2.f, w = x2 - x1, h = y2 - y1;
+      const float xt = (g[0] + g[2]) / 2.f, yt = (g[1] + g[3]) / 2.f, wt = g[2] - g[0], ht = g[3] - g[1];
+      const float* q = regress + r * 4;
+      lxy += static_cast<double>(smooth_l1((xt - x) / (w + 1e-16f), q[0]) + smooth_l1((yt - y) / (h + 1e-16f), q[1]));
+      lwh += static_cast<double>(smooth_l1(logf(wt / w + 1e-16f), q[2]) + smooth_l1(logf(ht / h + 1e-16f), q[3]));
+      // class_label[r] is non-zero only for r < P: a one at the class of the r-th positive row
+      const int hot = r < P ? static_cast<int>(boxes[static_cast<size_t>(pos_list[r]) * box_pitch + 7]) : -1;
+      for (int c = 0; c < nc; ++c) {
+        const float xc = refine[static_cast<size_t>(r) * refine_pitch + 1 + c];
+        const float yc = c == hot ? 1.f : 0.f;
+        cat += static_cast<double>(-(yc * fmaxf(logf(xc), -100.f) + (1.f - yc) * fmaxf(logf(1.f - xc), -100.f)));
+      }
+    }
+  }
+  focal = block_sum(focal, s_red);
+  conf = block_sum(conf, s_red);
+  lxy = block_sum(lxy, s_red);
+  lwh = block_sum(lwh, s_red);
+  cat = block_sum(cat, s_red);
+  positive = block_sum(positive, s_red);
+  tp = block_sum(tp, s_red);
+  if (threadIdx.x == 0) {
+    out[0] = static_cast<float>(focal);
+    out[1] = static_cast<float>(conf);
+    out[2] = static_cast<float>(lxy);
+    out[3] = static_cast<float>(lwh);
+    out[4] = static_cast<float>(cat);
+    out[5] = out[0] + (out[1] + out[4]) / cfg.lambda0 + (out[2] + out[3]) / cfg.lambda1;
+    out[6] = static_cast<float>(P);
+    out[7] = static_cast<float>(positive);
+    out[8] = static_cast<float>(tp);
+    out[9] = static_cast<float>(n_all);
+  }
+}
+
 }  // namespace
 }  // namespace me
 
@@ -179,6 +264,21 @@ int me_stage3_loss(const float* rois, const float* refine, const float* regress,
   ME_REQUIRE(cap > 0, "stage3_loss: cap %d", cap);
   stage3_loss_kernel<<<1, kBlock, 0, stream>>>(rois, refine, regress, mask, counts, cap, iou_labels, target_location,
                                                sample_filter, *cfg, out10);
+  ME_LAUNCH_CHECK();
+  return ME_OK;
+}
+
+int me_stage2_loss(const float* boxes, int box_pitch, const float* rois, const float* refine, int refine_pitch,
+                   const float* regress, const float* mask, const int* counts, int cap, const float* iou_labels,
+                   const float* target_location, const unsigned char* sample_filter, const me_stage2_loss_cfg* cfg,
+                   int* pos_ws, float* out10, me_stream_t stream_) {
+  using namespace me;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  ME_REQUIRE(boxes && rois && refine && regress && mask && counts && iou_labels && target_location && sample_filter && cfg &&
+                 pos_ws && out10, "stage2_loss: null argument");
+  ME_REQUIRE(cap > 0 && box_pitch >= 8 && refine_pitch >= 2, "stage2_loss: bad cap / pitches");
+  stage2_loss_kernel<<<1, kBlock, 0, stream>>>(boxes, box_pitch, rois, refine, refine_pitch, regress, mask, counts, cap,
+                                               iou_labels, target_location, sample_filter, *cfg, pos_ws, out10);
   ME_LAUNCH_CHECK();
   return ME_OK;
 }

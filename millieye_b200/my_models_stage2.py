@@ -82,6 +82,7 @@ class _Stage2Plan:
         self.weights = ops.make_stage2_weights(self._w)
         self.regress = torch.zeros((cap, 4), **f32)
         self.mask = torch.zeros((cap,), **f32)
+        self.refine = torch.zeros((cap, 1 + nc), **f32)      # refinement vectors: [conf, class scores] (loss branch)
         self.out = torch.zeros((cap, 8), **f32)
         self.out_count = torch.zeros((1,), **i32)
         ws = 1
@@ -98,7 +99,7 @@ class _Stage2Plan:
         ops.psroi_align(self.roi_score, n, g, g, 512, 10, 7, 1.0 / 16, self.rois, self.counts, cap, self.crop, 512)
         ops.conv_gemm(self.crop, self.fc0, cap, 1, 1, 512, self.hidden, 256, act=ME_ACT_LEAKY, cin=490)
         ops.stage2_heads(self.hidden, 256, self.weights, self.boxes, self.box_pitch, self.box_pitch - 7, self.counts, cap,
-                         self.regress, self.mask)
+                         self.regress, self.mask, self.refine)
         ops.finalize_output(self.boxes, self.rois, self.mask, self.regress, self.mask, self.counts, cap,
                             refine_threshold, refine_threshold, True, self.out, self.out_count, self.final_ws,
                             box_pitch=self.box_pitch)
@@ -143,9 +144,9 @@ class Network(nn.Module):
     def forward(self, images, targets=None):
         """images (N,3,S,S) fp32 -> output (K,8) [image_i, x1,y1,x2,y2, new_conf, class_score, class_pred] on the
         CPU, sorted by new_conf descending (reference :299-361)."""
-        if targets is not None:
-            raise MeError("the stage-2 training branch (module2_mixed/my_models.py:363-461) is not accelerated; "
-                          "run inference (targets=None)")
+        if targets is not None and any(m.training for m in (self.fcn_layers, self.refinement_head)):
+            raise MeError("the stage-2 loss branch runs with running BatchNorm statistics and without Dropout: call .eval() "
+                          "(training the R-CNN heads - batch statistics, Dropout, backward - is not on the accelerated path)")
         base_plan = self.base_detector.forward_device(images)
         key = id(base_plan)
         plan = self._plans.get(key)
@@ -154,4 +155,56 @@ class Network(nn.Module):
                 plan = self._plans[key] = _Stage2Plan(self, base_plan)
             plan.run(self.conf_thresh, float(self.refine_threshold))
             k = int(plan.out_count.item())
-            return plan.out[:k].cpu()
+            output = plan.out[:k].cpu()
+            if targets is None:
+                return output
+            return self._loss_branch(plan, images.shape[-1], targets, output)
+
+    def _loss_branch(self, plan, img_size, targets, output):
+        """Reference module2_mixed/my_models.py:363-461 on the forward's device buffers: labels (me_stage3_labels -
+        obtain_iou_labels is the same routine in both modules), balanced sampling with python's `random` on the host
+        like the reference (:411), losses + counters (me_stage2_loss).  `targets` (m,6) is rewritten IN PLACE to pixel
+        x1y1x2y2 as the reference does (:367-368).  Returns (output, loss, metric); loss carries no autograd graph."""
+        import random
+
+        import numpy as np
+
+        from .utils import xywh2xyxy
+        targets[:, 2:] = xywh2xyxy(targets[:, 2:])
+        targets[:, 2:] *= img_size
+        t = int(targets.shape[0])
+        dev = plan.device
+        f32 = dict(dtype=torch.float32, device=dev)
+        if getattr(plan, "iou_labels", None) is None:
+            plan.iou_labels = torch.zeros((plan.cap,), **f32)
+            plan.target_location = torch.zeros((plan.cap, 4), **f32)
+            plan.sample_filter = torch.zeros((plan.cap,), dtype=torch.uint8, device=dev)
+            plan.pos_ws = torch.zeros((plan.cap,), dtype=torch.int32, device=dev)
+            plan.loss_out = torch.zeros((16,), **f32)
+        targets_dev = targets.to(**f32).contiguous() if t else None
+        ops.stage3_labels(plan.boxes, plan.rois, plan.counts, plan.cap, targets_dev, t, plan.iou_labels, plan.target_location)
+        n_all = int(plan.counts[1].item())
+        iou = plan.iou_labels[:n_all].cpu().numpy()
+        pos, neg = iou > self.iou_thresh[1], iou < self.iou_thresh[0]
+        pos_idx, neg_idx = np.where(pos)[0], np.where(neg)[0]
+        top_k = min(len(pos_idx) * self.balance_fac, len(neg_idx))
+        keep = pos.copy()
+        if top_k > 0:
+            keep[neg_idx[random.sample(range(len(neg_idx)), k=top_k)]] = True
+        plan.sample_filter.zero_()
+        if n_all:
+            plan.sample_filter[:n_all].copy_(torch.from_numpy(keep.astype(np.uint8)), non_blocking=True)
+        ops.stage2_loss(plan.boxes, plan.box_pitch, plan.rois, plan.refine, plan.regress, plan.mask, plan.counts, plan.cap,
+                        plan.iou_labels, plan.target_location, plan.sample_filter, plan.pos_ws, plan.loss_out,
+                        self.iou_thresh[1], self.alpha, self.loss_lambda[0], self.loss_lambda[1], float(self.refine_threshold))
+        vals = plan.loss_out.cpu()
+        conf_1 = plan.boxes[:n_all, 5].cpu()
+        conf_2 = plan.mask[:n_all].cpu()
+        lab = torch.from_numpy(iou)
+        confs = dict(conf_1_pos=conf_1[lab > 0.5], conf_1_neg=conf_1[lab < 0.5],
+                     conf_2_pos=conf_2[lab > 0.5], conf_2_neg=conf_2[lab < 0.5])
+        metric = dict(total=n_all, true=torch.tensor(int(vals[6])), positive=torch.tensor(int(vals[7])), tp=vals[8].clone(),
+                      conf=confs)
+        self.last_losses = dict(masks_loss=float(vals[0]), conf_loss=float(vals[1]), loss_xy=float(vals[2]),
+                                loss_wh=float(vals[3]), category_loss=float(vals[4]))
+        return output, plan.loss_out[5].clone(), metric

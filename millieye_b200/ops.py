@@ -327,10 +327,20 @@ def fusion_heads(hidden, hidden_pitch, crop, crop_pitch, head_weights, img_boxes
                                      stream_ptr()), "me_fusion_heads")
 
 
-def stage2_heads(hidden, hidden_pitch, weights, boxes, box_pitch, num_vec, counts, cap, regress, mask):
-    _need_cuda(hidden, boxes, counts, regress, mask)
+def stage2_heads(hidden, hidden_pitch, weights, boxes, box_pitch, num_vec, counts, cap, regress, mask, refine=None):
+    _need_cuda(hidden, boxes, counts, regress, mask, refine)
     check(_lib.lib().me_stage2_heads(ptr(hidden), hidden_pitch, byref(weights), ptr(boxes), box_pitch, num_vec,
-                                     ptr(counts), cap, ptr(regress), ptr(mask), stream_ptr()), "me_stage2_heads")
+                                     ptr(counts), cap, ptr(regress), ptr(mask), ptr(refine), stream_ptr()), "me_stage2_heads")
+
+
+def stage2_loss(boxes, box_pitch, rois, refine, regress, mask, counts, cap, iou_labels, target_location, sample_filter, pos_ws,
+                out10, iou_hi, alpha, lambda0, lambda1, thr):
+    """Losses + counters of reference module2_mixed/my_models.py:399-445 -> out10 (see include/millieye_b200.h)."""
+    _need_cuda(boxes, rois, refine, regress, mask, counts, iou_labels, target_location, sample_filter, pos_ws, out10)
+    cfg = _lib.Stage2LossCfg(float(iou_hi), float(alpha), float(lambda0), float(lambda1), float(thr))
+    check(_lib.lib().me_stage2_loss(ptr(boxes), box_pitch, ptr(rois), ptr(refine), refine.shape[1], ptr(regress), ptr(mask),
+                                    ptr(counts), cap, ptr(iou_labels), ptr(target_location), ptr(sample_filter), byref(cfg),
+                                    ptr(pos_ws), ptr(out10), stream_ptr()), "me_stage2_loss")
 
 
 def make_stage2_weights(tensors):

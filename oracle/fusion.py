@@ -150,7 +150,7 @@ def network_forward_train(module_defs, sd, images, maps, radar_boxes, conf_thres
 
 
 def network_forward_stage2(module_defs, sd, images, conf_thresh, refine_threshold=0.0, class_num=12,
-                           use_torchvision=False):
+                           use_torchvision=False, return_intermediates=False):
     """Stage-2 Network.forward with targets=None (reference module2_mixed/my_models.py:299-361): every class is
     kept after NMS (:325-330), fcn_layers (= cnn_layers_1), ps_roi_align (:344), refinement_head (:121-126, Dropout
     is the identity in eval), ensemble_head with a LeakyReLU before the softmax (:149-161), new confidence =
@@ -186,4 +186,53 @@ def network_forward_stage2(module_defs, sd, images, conf_thresh, refine_threshol
     positive = masks[:, 1] > refine_threshold
     out = torch.cat((boxes[positive, :1], box_regress(reg[positive], boxes[positive, 1:5]), masks[positive, 1:],
                      boxes[positive, 6:8]), -1)
-    return out[torch.sort(out[:, 5], descending=True, stable=True).indices]
+    out = out[torch.sort(out[:, 5], descending=True, stable=True).indices]
+    if return_intermediates:
+        return out, dict(boxes=boxes, masks=masks, ref_vec=ref_vec, reg=reg, positive=positive)
+    return out
+
+
+def network_forward_stage2_train(module_defs, sd, images, conf_thresh, targets, sample_filter=None, refine_threshold=0.0,
+                                 iou_thresh=(0.3, 0.7), alpha=0.75, balance_fac=5, loss_lambda=(15, 5), **kw):
+    """Stage-2 Network.forward with targets (reference module2_mixed/my_models.py:363-461), heads in eval mode: labels
+    (obtain_iou_labels :195-244, the same routine as stage 3's with multi_boxes=True), pos / neg filters, metric
+    (:387-397), balanced sample with python's random (:399-414), FocalLoss over the sampled proposals' masks (:420),
+    confidence BCE (:424-429), regression_loss over the positives (:432-435), category BCE over the 12 class scores of the
+    positives with the reference's row-i indexing (:438-443), and the total (:445)
+        loss = masks + (conf + category) / lambda[0] + (xy + wh) / lambda[1].
+    targets (m,6) [image, class, cx, cy, w, h] in 0..1 (a copy is converted).  Returns (output, loss, metric, aux)."""
+    from . import stage3_loss as s3
+    output, im = network_forward_stage2(module_defs, sd, images, conf_thresh, refine_threshold=refine_threshold,
+                                        return_intermediates=True, **kw)
+    boxes, masks, ref_vec, reg = (im[k].numpy().astype(np.float32) for k in ("boxes", "masks", "ref_vec", "reg"))
+    positive = im["positive"].numpy()
+    R = len(boxes)
+    tpx = s3.targets_to_pixels(np.asarray(targets, dtype=np.float32), images.shape[-1])
+    boxes6 = np.concatenate((boxes[:, :1], boxes[:, 7:8], boxes[:, 1:5]), 1)
+    iou_labels, target_location = s3.obtain_iou_labels(boxes6, tpx, True)
+    flat = iou_labels.reshape(-1)
+    pos, neg = flat > iou_thresh[1], flat < iou_thresh[0]
+    if sample_filter is None:
+        sample_filter = s3.sample_filter_reference(pos, neg, balance_fac)
+    pos_idx = np.where(pos)[0]
+    onehot = np.tile(np.array([1.0, 0.0], dtype=np.float32), (R, 1))
+    onehot[pos_idx] = np.array([0.0, 1.0], dtype=np.float32)
+    masks_loss = s3.focal_loss_sum(masks[sample_filter], onehot[sample_filter], alpha)
+    conf_label = np.zeros(R, dtype=np.float32)
+    conf_label[pos_idx] = 1
+    conf_loss = s3.bce_sum(ref_vec[sample_filter, 0], conf_label[sample_filter])
+    loss_xy, loss_wh = s3.regression_loss(reg[pos], target_location[pos], boxes[pos, 1:5])
+    class_num = ref_vec.shape[1] - 1
+    class_label = np.zeros((R, class_num), dtype=np.float32)
+    for i, idx in enumerate(pos_idx):            # row i (not idx) is set: the reference's indexing (:440-441)
+        class_label[i, int(boxes6[idx, 1])] = 1
+    category_loss = s3.bce_sum(ref_vec[pos, 1:].reshape(-1), class_label[pos].reshape(-1))
+    f32 = np.float32
+    loss = f32(masks_loss + f32(conf_loss + category_loss) / f32(loss_lambda[0]) + f32(loss_xy + loss_wh) / f32(loss_lambda[1]))
+    conf_1, conf_2 = boxes[:, 5], masks[:, 1]
+    metric = dict(total=R, true=int(pos.sum()), positive=int(positive.sum()), tp=float((positive & pos).sum()),
+                  conf=dict(conf_1_pos=conf_1[flat > 0.5], conf_1_neg=conf_1[flat < 0.5],
+                            conf_2_pos=conf_2[flat > 0.5], conf_2_neg=conf_2[flat < 0.5]))
+    aux = dict(masks_loss=masks_loss, conf_loss=conf_loss, loss_xy=loss_xy, loss_wh=loss_wh, category_loss=category_loss,
+               iou_labels=iou_labels, target_location=target_location, sample_filter=sample_filter, boxes=boxes)
+    return output, loss, metric, aux

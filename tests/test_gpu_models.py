@@ -108,8 +108,8 @@ def test_darknet_input_contract():
     net = Darknet(configs.cfg_path("yolov3-tiny-12")).eval().to(DEV)
     with pytest.raises(MeError):
         net(torch.rand(1, 3, 96, 128, device=DEV))      # non-square
-    with pytest.raises(MeError):
-        net(torch.rand(1, 3, 96, 96, device=DEV), targets=torch.zeros(1, 6))
+    out3 = net(torch.rand(1, 3, 96, 96, device=DEV), targets=torch.tensor([[0, 1, 0.5, 0.5, 0.2, 0.3]]))
+    assert len(out3) == 3 and out3[0].dim() == 0         # (loss, featuremap, yolo_outputs) like models.py:267
     # weights changed in place -> refresh_weights() rebuilds the packed copies
     x = torch.rand(1, 3, 96, 96, device=DEV)
     _, y0 = net(x)
@@ -225,6 +225,34 @@ def test_stage2_golden(golden_dir):
             matched += 1
     assert matched >= 0.97 * len(ref)
     assert np.all(np.diff(o[:, 5]) <= 0)                     # sorted by the new confidence
+
+
+def test_stage2_loss_golden(golden_dir):
+    """Stage-2 Network.forward(images, targets) in eval mode against the reference-generated fixture (labels, balanced
+    sample, FocalLoss + confidence / category BCE + box regression, metric; module2_mixed/my_models.py:363-461)."""
+    import random
+    from millieye_b200.my_models_stage2 import Network as Network2
+    g = np.load(os.path.join(golden_dir, "stage2_loss_tiny12_160.npz"))
+    model = Network2(define_yolo(configs.cfg_path("yolov3-tiny-12")), conf_thresh=float(g["conf_thresh"])).eval()
+    model.load_state_dict(synth.fill_state_dict(model.state_dict(), seed=6, obj_bias=-1.0, head_gain=1.0))
+    model.to(DEV)
+    targets = torch.from_numpy(g["targets"].copy())
+    random.seed(int(g["sampling_seed"]))
+    out, loss, metric = model(synth.synth_images(3, 160, seed=6).to(DEV), targets)
+    assert not out.is_cuda and out.shape[1] == 8
+    assert np.allclose(targets.numpy(), g["targets_after"], atol=1e-4)            # rewritten in place like the reference
+    assert metric["total"] == int(g["total"])
+    plan = next(iter(model._plans.values()))
+    lab, ref_lab = plan.iou_labels[:metric["total"]].cpu().numpy(), g["iou_labels"].reshape(-1)
+    assert np.array_equal(lab > 0.7, ref_lab > 0.7) and np.array_equal(lab < 0.3, ref_lab < 0.3)
+    assert int(metric["true"]) == int(g["true"]) and int(metric["positive"]) == int(g["positive"])
+    assert float(metric["tp"]) == float(g["tp"])
+    rel = abs(float(loss) - float(g["loss"])) / float(g["loss"])
+    _record("stage2_loss_golden", loss=float(loss), ref=float(g["loss"]), rel=rel, label_err=float(np.abs(lab - ref_lab).max()))
+    assert rel <= 2e-2
+    model.train()
+    with pytest.raises(MeError):
+        model(synth.synth_images(3, 160, seed=6).to(DEV), torch.from_numpy(g["targets"].copy()))
 
 
 def test_detect_pipeline_matches_sequential():

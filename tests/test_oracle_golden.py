@@ -146,6 +146,30 @@ def test_stage2_matches_reference(golden_dir):
     np.testing.assert_allclose(out.numpy(), g["out"], rtol=2e-4, atol=2e-4)
 
 
+def test_stage2_loss_matches_reference(golden_dir):
+    """Stage-2 training branch (module2_mixed/my_models.py:363-461): the oracle's loss, metric and labels equal the
+    unmodified reference's on the fixture of tests/golden/make_golden_stage2_loss.py (random seeded like there)."""
+    import random
+    from millieye_b200.my_models_stage2 import Network as Network2
+    from millieye_b200.my_models import define_yolo
+    g = np.load(os.path.join(golden_dir, "stage2_loss_tiny12_160.npz"))
+    cfg = configs.cfg_path("yolov3-tiny-12")
+    sd = synth.fill_state_dict(Network2(define_yolo(cfg), conf_thresh=float(g["conf_thresh"])).state_dict(), seed=6, obj_bias=-1.0,
+                               head_gain=1.0)
+    random.seed(int(g["sampling_seed"]))
+    with torch.no_grad():
+        out, loss, metric, aux = ofus.network_forward_stage2_train(
+            parse_model_config(cfg), {k: v.float() if v.is_floating_point() else v for k, v in sd.items()},
+            synth.synth_images(3, 160, seed=6), float(g["conf_thresh"]), g["targets"], use_torchvision=True)
+    assert np.array_equal(aux["iou_labels"], g["iou_labels"]) and np.array_equal(aux["target_location"], g["target_location"])
+    assert abs(float(loss) - float(g["loss"])) <= 1e-5 * float(g["loss"])
+    assert (metric["total"], metric["true"], metric["positive"], metric["tp"]) == (int(g["total"]), int(g["true"]),
+                                                                                  int(g["positive"]), float(g["tp"]))
+    for k in ("conf_1_pos", "conf_1_neg", "conf_2_pos", "conf_2_neg"):
+        assert np.abs(metric["conf"][k] - g[k]).max() <= 1e-5
+    assert out.shape == g["output"].shape and np.abs(out.numpy() - g["output"]).max() <= 1e-3
+
+
 def test_stage3_loss_matches_reference(golden_dir):
     """Labelling + loss branch (my_models.py:545-640): oracle == reference on the fixture generated by
     tests/golden/make_golden_stage3_loss.py - labels bit-exact, loss / output / attention to fp32 round-off."""
