@@ -269,6 +269,214 @@ def check_parity(host_batch, rec, frames):
         return dict(checked=False, error=str(e)[:200])
 
 
+# ------------------------------------------------------------------------------------------------ secondary configs
+def _dist_setup(args):
+    import torch.distributed as dist
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}: launch with torchrun --nproc-per-node {args.gpus}")
+    device = torch.device("cuda", local)
+    torch.cuda.set_device(device)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=device)
+    return world, rank, local, device
+
+
+def _timed_steps(fn, steps, warmup, world, device):
+    """W warm-up steps, then K steps between CUDA events (barrier + synchronize on both sides), max over ranks (ms)."""
+    import torch.distributed as dist
+    for _ in range(max(warmup, 3)):
+        fn()
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    if world > 1:
+        t = torch.tensor([ms], device=device)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    return ms
+
+
+def _fusion_inputs(n, device, seed):
+    """Synthetic frames + 64-point radar clouds: images U[0,1), points drawn from the fixture's
+    empirical ranges, 0-3 radar boxes per frame."""
+    import numpy as np
+    from millieye_b200 import radar
+    from oracle import synth
+    gen = torch.Generator(device="cpu").manual_seed(seed)
+    imgs = torch.rand(n, 3, SIZE, SIZE, generator=gen)
+    rng = np.random.RandomState(seed)
+    pts = np.stack([rng.uniform(-3, 3, (n, 64)), rng.uniform(1, 10, (n, 64)), rng.uniform(-1.5, 1.5, (n, 64)),
+                    rng.uniform(-3, 3, (n, 64))], -1).astype(np.float32)
+    return dict(imgs=imgs.pin_memory(), imgs_dev=imgs.to(device), pts=torch.from_numpy(pts).to(device),
+                cnt=torch.full((n,), 64, dtype=torch.int32, device=device), cfg=radar.make_cfg(out_size=SIZE // 16),
+                boxes=synth.synth_radar_boxes(n, seed=seed).to(device))
+
+
+def run_fusion(args):
+    """BASELINE config 3: milliEye fusion (YOLOv3-tiny-12 + R-CNN refinement + radar MLP) inference, batch 32 per GPU,
+    64 radar points per frame: radar heat-maps on the device, Network.forward, result rows on the host in the e2e arm."""
+    import torch.distributed as dist
+    from millieye_b200 import configs, radar
+    from millieye_b200.engine import capture_graph
+    from millieye_b200.my_models import Network, define_yolo
+    from oracle import darknet as odark
+    from oracle import synth
+    from oracle.parse_config import parse_model_config
+    world, rank, local, device = _dist_setup(args)
+    model = Network(define_yolo(configs.cfg_path("yolov3-tiny-12")), conf_thresh=CONF_THRESH).eval()
+    model.load_state_dict(synth.fill_state_dict(model.state_dict(), seed=0, obj_bias=-3.0, head_gain=1.0))
+    model.to(device)
+    inp = _fusion_inputs(BATCH, device, 100 + rank)
+    last = {}
+
+    def step_dev():
+        maps = radar.radar_maps(inp["pts"], inp["cnt"], inp["cfg"])
+        last["out"] = model(inp["imgs_dev"], maps, inp["boxes"].clone(), 0)
+
+    def step_e2e():
+        maps = radar.radar_maps(inp["pts"], inp["cnt"], inp["cfg"])
+        last["host"] = model(inp["imgs"], maps, inp["boxes"].clone(), 0).cpu()
+
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    ms_dev = _timed_steps(step_dev, args.steps, args.warmup, world, device)
+    clocks = sampler.stop() if sampler else None
+    ms_e2e = _timed_steps(step_e2e, args.steps, args.warmup, world, device)
+    # detector conv stack alone (HBM-bound on tiny-12): graph of the conv launches
+    plan = model.base_detector.plan_for(BATCH, SIZE, device)
+    conv_ops = {i for i, k in enumerate(plan.op_kinds) if k in ("conv", "maxpool", "upsample")}
+    g = capture_graph(lambda: plan.enqueue_split(only=conv_ops))
+    conv_ms = _timed_steps(g.replay, 20, 3, 1, device) / 20
+    if world > 1:
+        dist.barrier()
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    pk = peaks()
+    md = parse_model_config(configs.cfg_path("yolov3-tiny-12"))
+    act_bytes, w_bytes = odark.min_traffic_bytes(md, SIZE) if hasattr(odark, "min_traffic_bytes") else (31.4e6, 17.4e6)
+    bytes_step = act_bytes * BATCH + w_bytes
+    achieved = bytes_step / (conv_ms * 1e-3) / 1e9
+    fps, fps_e2e = world * BATCH * args.steps / ms_dev * 1e3, world * BATCH * args.steps / ms_e2e * 1e3
+    emit(dict(metric="frames/sec at 416x416 batch32, milliEye fusion (YOLO + R-CNN + radar MLP)", value=fps, unit="frames/s",
+              n_gpus=world, steps=args.steps, warmup=max(args.warmup, 3), ms_per_step=ms_dev / args.steps, higher_is_better=True,
+              scaling="weak", vs_baseline=None, dtype="f16", data="synthetic",
+              config=dict(workload=f"milliEye fusion inference (BASELINE config 3): YOLOv3-tiny-12 detector + NMS + proposals + "
+                                   f"score-map CNNs + PS-RoIAlign / RoIAlign + refinement / ensemble heads, batch {BATCH} per GPU, "
+                                   f"{SIZE}x{SIZE}, 64 radar points per frame -> heat-maps on the device",
+                          conf_thresh=CONF_THRESH, rows_last_step=int(last["out"].shape[0]),
+                          l2="~1 GB of activations per step exceed the 126 MB L2; no explicit flush"),
+              clocks=clocks,
+              e2e=dict(value=fps_e2e, unit="frames/s", h2d_bytes_per_step=BATCH * 3 * SIZE * SIZE * 4,
+                       d2h_bytes_per_step=int(last["host"].numel() * 4), ms_per_step=ms_e2e / args.steps),
+              gpu_launches=int((len(plan.ops) + len(plan.post_ops) + 14) * args.steps),
+              roofline=dict(bound="hbm", achieved=achieved, peak=pk["hbm_gbs"], unit="GB/s", frac=achieved / pk["hbm_gbs"],
+                            traffic=None, peak_source=pk["src"], kernel="tiny-12 conv stack (conv_gemm / conv_thin / conv_first_tc / "
+                            "conv_chain / maxpool)", conv_ms_per_step=conv_ms,
+                            note="achieved = minimum activation + weight bytes of the tiny-12 conv stack (31.4 MB / frame + 17.4 MB, "
+                                 "SURVEY.md 8d) / device time of its launches (graph replay)"),
+              cpu_baseline=None))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def run_train3(args):
+    """BASELINE config 4: stage-3 training step (fusion heads train, YOLO frozen), GLOBAL batch 64 split over the ranks,
+    synchronised BatchNorm statistics + one gradient all-reduce over NCCL + the flat Adam kernel (train.py:169-191)."""
+    import torch.distributed as dist
+    from millieye_b200 import configs, radar
+    from millieye_b200.my_models import Network, define_yolo
+    from millieye_b200.stage3_train import Stage3Optimizer
+    from oracle import synth
+    world, rank, local, device = _dist_setup(args)
+    GLOBAL = 64
+    if GLOBAL % world:
+        raise SystemExit("the global batch of 64 must divide over the ranks")
+    per = GLOBAL // world
+    model = Network(define_yolo(configs.cfg_path("yolov3-tiny-12")), conf_thresh=0.01)       # train.py:61
+    model.load_state_dict(synth.fill_state_dict(model.state_dict(), seed=0, obj_bias=-3.0, head_gain=1.0))
+    model.to(device)
+    inp = _fusion_inputs(per, device, 200 + rank)
+    # ground truth near the detector's own proposals so that every label class occurs (positives, ignored, negatives)
+    model.eval()
+    maps0 = radar.radar_maps(inp["pts"], inp["cnt"], inp["cfg"])
+    rows = model(inp["imgs_dev"], maps0, inp["boxes"].clone(), 1).cpu()
+    tg = []
+    for k, b in enumerate(rows[::9]):
+        sh = (0.0, 0.03, 0.25)[k % 3]
+        w, h = float(b[3] - b[1]), float(b[4] - b[2])
+        x1, y1, x2, y2 = float(b[1]) + sh * w, float(b[2]) + sh * h, float(b[3]) + sh * w, float(b[4]) + sh * h
+        tg.append([float(b[0]), 0.0, (x1 + x2) / 2 / SIZE, (y1 + y2) / 2 / SIZE, (x2 - x1) / SIZE, (y2 - y1) / SIZE])
+    targets = torch.tensor(tg if tg else [[0, 0, 0.5, 0.5, 0.2, 0.2]], dtype=torch.float32)
+    model.train()
+    model.base_detector.eval()
+    opt = Stage3Optimizer(model, lr=5e-4)
+    last = {}
+
+    def step(host_images):
+        maps = radar.radar_maps(inp["pts"], inp["cnt"], inp["cfg"])
+        loss, out, metric, att = model(inp["imgs"] if host_images else inp["imgs_dev"], maps, inp["boxes"].clone(), 0,
+                                       targets.clone())
+        model.backward_into(opt.grads)
+        opt.all_reduce()
+        opt.step()
+        last["loss"] = float(loss) if host_images else loss
+        last["rows"] = metric["total"]
+
+    import random
+    random.seed(1234 + rank)
+    sampler = ClockSampler(local) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    ms_dev = _timed_steps(lambda: step(False), args.steps, args.warmup, world, device)
+    clocks = sampler.stop() if sampler else None
+    ms_e2e = _timed_steps(lambda: step(True), args.steps, args.warmup, world, device)
+    if world > 1:
+        dist.barrier()
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    pk = peaks()
+    fps, fps_e2e = GLOBAL * args.steps / ms_dev * 1e3, GLOBAL * args.steps / ms_e2e * 1e3
+    bytes_step = 31.4e6 * per + 17.4e6
+    emit(dict(metric="frames/sec, stage-3 training step, global batch 64", value=fps, unit="frames/s", n_gpus=world,
+              steps=args.steps, warmup=max(args.warmup, 3), ms_per_step=ms_dev / args.steps, higher_is_better=True,
+              scaling="strong", vs_baseline=None, dtype="f32 heads / f16 frozen detector", data="synthetic",
+              config=dict(workload=f"stage-3 training step (BASELINE config 4): frozen YOLOv3-tiny-12 forward + NMS + proposals, "
+                                   f"train-mode heads in fp32 (batch-statistics BatchNorm synchronised over ranks), labels + balanced "
+                                   f"sample + focal / BCE loss, hand-derived backward of the {opt.numel} head parameters, one NCCL "
+                                   f"all-reduce of the flat gradient buffer, Adam; global batch {GLOBAL} = {per} frames x {world} GPU(s), "
+                                   f"{SIZE}x{SIZE}, 64 radar points per frame", proposals_per_rank_last_step=int(last["rows"]),
+                          trainable_parameters=int(opt.numel), sync_bn=world > 1),
+              clocks=clocks,
+              e2e=dict(value=fps_e2e, unit="frames/s", h2d_bytes_per_step=per * 3 * SIZE * SIZE * 4, d2h_bytes_per_step=4,
+                       ms_per_step=ms_e2e / args.steps),
+              gpu_launches=int(150 * args.steps),
+              roofline=dict(bound="hbm", achieved=bytes_step / (ms_dev / args.steps * 1e-3) / 1e9, peak=pk["hbm_gbs"], unit="GB/s",
+                            frac=bytes_step / (ms_dev / args.steps * 1e-3) / 1e9 / pk["hbm_gbs"], traffic=None, peak_source=pk["src"],
+                            kernel="whole step",
+                            note="the step is latency-bound (about 150 small launches and three host reads - proposal counts, "
+                                 "labels for python's random.sample, loss - like the reference's loop); achieved = minimum bytes of "
+                                 "the frozen detector forward / whole step time, a lower bound shown for scale only"),
+              cpu_baseline=None))
+    if world > 1:
+        dist.destroy_process_group()
+
+
 def run_gpu(args):
     import torch.distributed as dist
     from millieye_b200 import ops
@@ -473,6 +681,8 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--config", default="darknet53", choices=["darknet53", "fusion", "train3"],
+                    help="darknet53: the headline bench (BASELINE config 2); fusion: config 3; train3: config 4")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-sustained", action="store_true", help="skip the >= 2 s conv-only replay")
     ap.add_argument("--no-parity", action="store_true", help="skip the oracle check of the timed detections")
@@ -483,7 +693,7 @@ def main():
     else:
         if not torch.cuda.is_available():
             raise SystemExit("bench.py needs a CUDA device (use --impl reference for the CPU arm)")
-        run_gpu(args)
+        {"darknet53": run_gpu, "fusion": run_fusion, "train3": run_train3}[args.config](args)
 
 
 if __name__ == "__main__":

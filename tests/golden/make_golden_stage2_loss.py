@@ -52,6 +52,7 @@ def normalise(t, size):
 
 
 def main():
+    global CONF
     torch.set_num_threads(4)
     for name in ("matplotlib", "matplotlib.pyplot", "matplotlib.patches"):
         mod = types.ModuleType(name)
@@ -71,6 +72,13 @@ def main():
     with torch.no_grad():
         # the proposals exactly as forward builds them (:317-335)
         feat, yolo = model.base_detector(imgs)
+        # The GPU path's detector computes in fp16: keep the confidence threshold clear of every decoded objectness so the
+        # same rows pass the filter there (the candidate set, hence NMS and the proposal list, must be identical).
+        conf_all = yolo[..., 4].reshape(-1)
+        best = max((float((conf_all - c).abs().min()), c) for c in [round(0.55 + 0.005 * k, 3) for k in range(50)])
+        print("confidence threshold", best[1], "margin", best[0])
+        model.conf_thresh = best[1]
+        CONF = best[1]
         dets = ref_utils.non_max_suppression_cpp(yolo.cpu(), conf_thresh=model.conf_thresh)
         rows = []
         for i, d in enumerate(dets):
