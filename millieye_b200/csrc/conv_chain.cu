@@ -64,6 +64,7 @@ struct alignas(128) ChainLayer {
   int M, Ho, Wo, stride, pad;
   int kb_per_tap, num_kb, tiles_n, bn;
   int act, has_res, im2col;
+  int out_f32;       // 1: fp32 output (YOLO head logits): BN = 128, four 32-column staging sub-tiles
   int dep_kind;      // -1: input complete before the launch; 0: same rows (1x1); 1: 3x3 stride 1; 2: 3x3 stride 2
   int dep_base;      // first counter of the layer that produces the input
   int dep_target;    // arrivals that complete one of its m tiles (2 CTAs x its n tiles)
@@ -332,7 +333,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) conv_ch
     const int row = q * 32 + lane;
     const int half = (warp - 2) >> 2;   // which BN/2 columns this warp converts
     const int etid = threadIdx.x - 64;
-    int cur = -1, bn = 0, tiles_n = 1, act = 0, has_res = 0;
+    int cur = -1, bn = 0, tiles_n = 1, act = 0, has_res = 0, out_f32 = 0;
     const float* bias = nullptr;
     const bool eleader = threadIdx.x == 64;
     int bias_layer = -1, bias_tn = -1;
@@ -349,6 +350,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) conv_ch
         tiles_n = L->tiles_n;
         act = L->act;
         has_res = L->has_res;
+        out_f32 = L->out_f32;
         bias = L->bias;
       }
       const int tn = tile % tiles_n;
@@ -367,8 +369,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) conv_ch
       ME_CHAIN_TRACED(w_stg, mbar_wait(stg_ready, it & 1, p.debug, 0x500u));
 
       const int c_base = half * (bn / 2);
-      const int nch = bn / 64;   // 32-column chunks per warp: 2 or 4
-      // bias + activation (+ residual from the staging tile) -> fp16 -> swizzled staging tile, 32 columns of this row
+      const int nch = bn / 64;   // 32-column chunks per warp: 1, 2 or 4
+      // bias + activation (+ residual from the staging tile) -> fp16 -> swizzled staging tile, 32 columns of this row;
+      // fp32 layers (head logits): 32 fp32 columns = one 128-byte row of staging sub-tile c / 32
       auto convert_chunk = [&](int c, const uint32_t (&r)[32]) {
         float v[32];
 #pragma unroll
@@ -385,6 +388,17 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) conv_ch
         } else if (act == ME_ACT_SIGMOID) {
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] = 1.f / (1.f + __expf(-v[j]));
+        }
+        if (out_f32) {
+          uint8_t* sub = staging + (c >> 5) * kSubBytes;
+          const uint32_t rbase = row * 128;
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            uint32_t off = rbase + j * 16;
+            off ^= ((off >> 7) & 7u) << 4;
+            *reinterpret_cast<float4*>(sub + off) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+          }
+          return;
         }
         uint8_t* sub = staging + (c >> 6) * kSubBytes;
         const uint32_t rbase = row * 128 + (c & 63) * 2;
@@ -416,11 +430,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) conv_ch
       ptx::tmem_ld_32x32b_x32(t_row, r0);
       for (int ci = 0; ci < nch; ci += 2) {
         ptx::tmem_ld_wait_regs(r0);
-        ptx::tmem_ld_32x32b_x32(t_row + (ci + 1) * 32, r1);
+        if (ci + 1 < nch) ptx::tmem_ld_32x32b_x32(t_row + (ci + 1) * 32, r1);
         convert_chunk(c_base + ci * 32, r0);
-        ptx::tmem_ld_wait_regs(r1);
-        if (ci + 2 < nch) ptx::tmem_ld_32x32b_x32(t_row + (ci + 2) * 32, r0);
-        convert_chunk(c_base + (ci + 1) * 32, r1);
+        if (ci + 1 < nch) {
+          ptx::tmem_ld_wait_regs(r1);
+          if (ci + 2 < nch) ptx::tmem_ld_32x32b_x32(t_row + (ci + 2) * 32, r0);
+          convert_chunk(c_base + (ci + 1) * 32, r1);
+        }
       }
       ptx::tc_fence_before();
       __syncwarp();
@@ -452,7 +468,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) conv_ch
           wait_counter(p.counters + N->res_base + tm, N->res_target, p.debug, 0x800u);
           fence_proxy_async_all();
         }
-        const int nsub = N->bn / 64;
+        const int nsub = N->bn / 64;   // (residual layers are fp16)
         ptx::mbar_arrive_expect_tx(stg_ready, nsub * kSubBytes);
         for (int sub = 0; sub < nsub; ++sub)
           ptx::tma_load_2d(&N->tmR, stg_ready, staging + sub * kSubBytes, tn * N->bn + sub * 64, m0);
@@ -473,9 +489,10 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) conv_ch
         const int m0 = tm * 2 * kBM + static_cast<int>(rank) * kBM, n0 = tn * L->bn;
         mbar_wait(&stg_full[w], (i >> 1) & 1, p.debug, 0x600u + w);
         if (m0 < L->M) {
-          const int nsub = L->bn / 64;
+          const int sub_cols = L->out_f32 ? 32 : 64;
+          const int nsub = L->bn / sub_cols;
           for (int sub = 0; sub < nsub; ++sub)
-            ptx::tma_store_2d(&L->tmC, staging + sub * kSubBytes, n0 + sub * 64, m0);
+            ptx::tma_store_2d(&L->tmC, staging + sub * kSubBytes, n0 + sub * sub_cols, m0);
           ptx::tma_store_commit();
           ptx::tma_store_wait_read0();    // the staging tile has been read
         }
@@ -501,6 +518,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) conv_ch
   if (warp == 1) ptx::tmem_dealloc_pair(tmem_base, kTmemCols);
 }
 
+// Tile width of a layer: the widest of 256 / 128 / 64 that divides cout (fp32 layers: 128, their staging rows are 32 columns)
+inline int chain_bn(const me_conv_desc& d) {
+  if (d.out_f32) return 128;
+  return d.cout % 256 == 0 ? 256 : (d.cout % 128 == 0 ? 128 : 64);
+}
+
 struct HostLayer {
   int tiles_m, tiles_n, num_kb, dep, res, dep_kind;
   int M, Ho, Wo, Hin, Win, dep_M;
@@ -515,10 +538,15 @@ int me_conv_chain_eligible(const me_conv_desc* d) {
   if (!d) return 0;
   if (d->ksize != 1 && d->ksize != 3) return 0;
   if (!(d->stride == 1 || (d->stride == 2 && d->ksize == 3))) return 0;
-  if (d->out_f32) return 0;
   if (d->cin <= 0 || d->cin % me::kBK != 0) return 0;
-  if (d->cout <= 0 || d->cout % 128 != 0) return 0;
-  if (d->in_pitch < d->cin || d->in_pitch % 8 != 0 || d->out_pitch < d->cout || d->out_pitch % 8 != 0) return 0;
+  if (d->out_f32) {   // YOLO head logits: 128-column tiles of fp32, no residual
+    if (d->cout <= 0 || d->cout % 128 != 0 || d->res_pitch > 0) return 0;
+    if (d->out_pitch < d->cout || d->out_pitch % 4 != 0) return 0;
+  } else {
+    if (d->cout <= 0 || d->cout % 64 != 0) return 0;
+    if (d->out_pitch < d->cout || d->out_pitch % 8 != 0) return 0;
+  }
+  if (d->in_pitch < d->cin || d->in_pitch % 8 != 0) return 0;
   return 1;
 }
 
@@ -535,7 +563,7 @@ size_t me_conv_chain_blob_bytes(const me_chain_layer* layers, int n_layers) {
     const long long Ho = (d.h + 2 * pad - d.ksize) / d.stride + 1, Wo = (d.w + 2 * pad - d.ksize) / d.stride + 1;
     const long long M = d.n * Ho * Wo;
     const long long tm = (M + 2 * kBM - 1) / (2 * kBM);
-    const int bn = d.cout % 256 == 0 ? 256 : 128;
+    const int bn = chain_bn(d);
     tiles += tm * (d.cout / bn);
     mtiles += tm;
   }
@@ -582,7 +610,7 @@ int me_conv_chain_build(const me_chain_layer* layers, int n_layers, void* host_b
     const int taps = d.ksize * d.ksize;
     const int cin_pad = round_up(d.cin, kBK);
     const int ktot = taps * cin_pad;
-    const int bn = d.cout % 256 == 0 ? 256 : 128;
+    const int bn = chain_bn(d);
     ChainLayer& L = CL[l];
     L.bias = a.bias;
     L.M = M;
@@ -597,6 +625,7 @@ int me_conv_chain_build(const me_chain_layer* layers, int n_layers, void* host_b
     L.act = d.act;
     L.has_res = (d.res_pitch > 0 && a.residual != nullptr) ? 1 : 0;
     L.im2col = d.ksize == 3 ? 1 : 0;
+    L.out_f32 = d.out_f32 ? 1 : 0;
     const int tiles_m = ceil_div(M, 2 * kBM);
     ME_REQUIRE(tiles_m * L.tiles_n < (1 << kItemShift), "conv_chain: too many tiles in layer %d", l);
     L.ctr_base = ctr;
@@ -640,8 +669,12 @@ int me_conv_chain_build(const me_chain_layer* layers, int n_layers, void* host_b
     rc = encode_tiled_2d(&L.tmB, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, a.w_packed, ktot, d.cout, ktot, kBK, bn / 2,
                          CU_TENSOR_MAP_SWIZZLE_128B);
     if (rc != ME_OK) return rc;
-    rc = encode_tiled_2d(&L.tmC, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, a.y, d.cout, M, d.out_pitch, 64, kBM,
-                         CU_TENSOR_MAP_SWIZZLE_128B);
+    if (d.out_f32)
+      rc = encode_tiled_2d(&L.tmC, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, a.y, d.cout, M, d.out_pitch, 32, kBM,
+                           CU_TENSOR_MAP_SWIZZLE_128B);
+    else
+      rc = encode_tiled_2d(&L.tmC, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, a.y, d.cout, M, d.out_pitch, 64, kBM,
+                           CU_TENSOR_MAP_SWIZZLE_128B);
     if (rc != ME_OK) return rc;
     if (L.has_res) {
       rc = encode_tiled_2d(&L.tmR, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, a.residual, d.cout, M, d.res_pitch, 64, kBM,

@@ -289,8 +289,19 @@ class DarknetPlan:
         trunk + first head trunk, 26^2 head trunk, 52^2 head trunk) separated by the two upsamples, and the three
         head convs."""
         n_ops = len(self.ops)
-        order = [k for k in range(n_ops) if not self._conv_meta.get(k, {}).get("leaf")] + \
-                [k for k in range(n_ops) if self._conv_meta.get(k, {}).get("leaf")]
+
+        def describe(k):
+            m = self._conv_meta[k]
+            sv, o, rv = m["src"], m["out"], m["res"]
+            return ops.conv_desc(m["packed"], self.n, sv.h, sv.w, sv.pitch, o.pitch, stride=m["stride"], act=m["act"],
+                                 res_pitch=0 if rv is None else rv.pitch, cin=m["cin"], cout=m["cout"], out_f32=m["f32"])
+
+        # head convs that cannot join a chain go to the end of the list so that they do not interrupt a run
+        def deferred(k):
+            m = self._conv_meta.get(k)
+            return m is not None and m["leaf"] and not ops.conv_chain_eligible(describe(k))
+
+        order = [k for k in range(n_ops) if not deferred(k)] + [k for k in range(n_ops) if deferred(k)]
         # producer op of every conv output view: buffer -> [(channel offset, channels, op)]
         written = {}
         for k in order:
@@ -304,29 +315,31 @@ class DarknetPlan:
                 return []
             return [k for (off, c, k) in written.get(id(view.buf), []) if off < view.off + view.c and view.off < off + c]
 
-        def describe(k):
-            m = self._conv_meta[k]
-            sv, o, rv = m["src"], m["out"], m["res"]
-            return ops.conv_desc(m["packed"], self.n, sv.h, sv.w, sv.pitch, o.pitch, stride=m["stride"], act=m["act"],
-                                 res_pitch=0 if rv is None else rv.pitch, cin=m["cin"], cout=m["cout"], out_f32=m["f32"])
-
         new_ops, new_kinds, new_blocks = [], [], []
         run = []   # op indices of the chain being collected
 
         def flush():
             if len(run) >= 2:
                 pos = {k: j for j, k in enumerate(run)}
-                layers = []
-                for k in run:
-                    m = self._conv_meta[k]
-                    dep = [pos[q] for q in producers(m["src"]) if q in pos]
-                    res = [pos[q] for q in producers(m["res"]) if q in pos]
-                    layers.append(dict(desc=describe(k), x=m["src"].t, packed=m["packed"], y=m["out"].t,
-                                       residual=None if m["res"] is None else m["res"].t,
-                                       dep=dep[0] if dep else -1, res=res[0] if res else -1))
-                chain = ops.ConvChain(layers, self.device)
-                self.chains.append(chain)
-                new_ops.append(lambda b0, nb, c=chain: c.run())
+                # head logits exist once per slot (the decode of batch i overlaps the forward of batch i+1): a chain
+                # that writes them is built once per slot and the launch picks the current one
+                slots = 2 if any(getattr(self._conv_meta[k]["out"], "alt", None) is not None for k in run) else 1
+                per_slot = []
+                for slot in range(slots):
+                    layers = []
+                    for k in run:
+                        m = self._conv_meta[k]
+                        dep = [pos[q] for q in producers(m["src"]) if q in pos]
+                        res = [pos[q] for q in producers(m["res"]) if q in pos]
+                        o = m["out"]
+                        if slot == 1 and getattr(o, "alt", None) is not None:
+                            o = o.alt
+                        layers.append(dict(desc=describe(k), x=m["src"].t, packed=m["packed"], y=o.t,
+                                           residual=None if m["res"] is None else m["res"].t,
+                                           dep=dep[0] if dep else -1, res=res[0] if res else -1))
+                    per_slot.append(ops.ConvChain(layers, self.device))
+                self.chains.extend(per_slot)
+                new_ops.append(lambda b0, nb, cs=per_slot: cs[self._slot if len(cs) > 1 else 0].run())
                 new_kinds.append("conv")
                 new_blocks.append([self.op_blocks[k] for k in run])
             else:
@@ -340,7 +353,7 @@ class DarknetPlan:
         cuts = {int(v) for v in os.environ.get("ME_CHAIN_CUT", "").split(",") if v}
         for k in order:
             m = self._conv_meta.get(k)
-            ok = m is not None and not m["f32"] and ops.conv_chain_eligible(describe(k))
+            ok = m is not None and ops.conv_chain_eligible(describe(k))
             if ok and self.op_blocks[k] in cuts:
                 flush()
             if ok:

@@ -9,39 +9,49 @@ pytestmark = pytest.mark.gpu
 DEV = "cuda:0"
 
 
-def _packed(cout, cin, k, seed):
+def _packed(cout, cin, k, seed, head=False):
     g = torch.Generator().manual_seed(seed)
     wt = torch.randn(cout, cin, k, k, generator=g) / (cin * k * k) ** 0.5
+    if head:   # YOLO head conv: bias, no BatchNorm
+        return ops.pack_conv(wt.to(DEV), (torch.randn(cout, generator=g) * 0.3).to(DEV), None, cout_pad=cout)
     bn = (torch.rand(cout, generator=g) + 0.5, torch.randn(cout, generator=g) * 0.1, torch.randn(cout, generator=g) * 0.1,
           torch.rand(cout, generator=g) + 0.5, 1e-5)
     return ops.pack_conv(wt.to(DEV), None, tuple(t.to(DEV) if torch.is_tensor(t) else t for t in bn), cout_pad=cout)
 
 
 def _run_case(n, size, cin0, spec):
-    """spec: list of (k, stride, cout, res_from) with res_from = index of the layer whose output is added (or None);
-    layer j reads layer j-1 (layer 0 reads the input)."""
+    """spec: list of (k, stride, cout, res_from[, "head"]) with res_from = index of the layer whose output is added (or
+    None); layer j reads layer j-1 (layer 0 reads the input), or the layer before a head; "head" marks a linear fp32
+    layer (YOLO head conv) whose output nothing reads."""
     torch.manual_seed(0)
     x0 = (torch.randn(n, size, size, cin0) * 0.5).half().to(DEV)
     layers, shapes = [], []
     h, c = size, cin0
-    for j, (k, s, cout, res_from) in enumerate(spec):
+    src_of = []
+    prev = -1
+    for j, entry in enumerate(spec):
+        k, s, cout, res_from = entry[:4]
+        head = len(entry) > 4
         pad = (k - 1) // 2
         ho = (h + 2 * pad - k) // s + 1
         shapes.append((h, c, ho, cout))
-        layers.append(dict(k=k, s=s, packed=_packed(cout, c, k, 100 + j), res_from=res_from))
-        h, c = ho, cout
+        layers.append(dict(k=k, s=s, packed=_packed(cout, c, k, 100 + j, head), res_from=res_from, head=head))
+        src_of.append(prev)
+        if not head:
+            h, c, prev = ho, cout, j
 
     def outputs():
-        return [torch.full((n, ho, ho, cout), float("nan"), dtype=torch.float16, device=DEV) for (_, _, ho, cout) in shapes]
+        return [torch.full((n, ho, ho, cout), float("nan"), dtype=torch.float32 if L["head"] else torch.float16, device=DEV)
+                for (_, _, ho, cout), L in zip(shapes, layers)]
 
     # per-layer reference launches
     ref = outputs()
     for j, L in enumerate(layers):
         h_in, c_in, ho, cout = shapes[j]
-        src = x0 if j == 0 else ref[j - 1]
+        src = x0 if src_of[j] < 0 else ref[src_of[j]]
         res = None if L["res_from"] is None else ref[L["res_from"]]
-        ops.conv_gemm(src, L["packed"], n, h_in, h_in, c_in, ref[j], cout, stride=L["s"], act=1, residual=res,
-                      res_pitch=0 if res is None else cout)
+        ops.conv_gemm(src, L["packed"], n, h_in, h_in, c_in, ref[j], cout, stride=L["s"], act=0 if L["head"] else 1, residual=res,
+                      res_pitch=0 if res is None else cout, out_f32=L["head"])
     torch.cuda.synchronize()
 
     got = outputs()
@@ -49,11 +59,11 @@ def _run_case(n, size, cin0, spec):
     for j, L in enumerate(layers):
         h_in, c_in, ho, cout = shapes[j]
         res = None if L["res_from"] is None else got[L["res_from"]]
-        desc = ops.conv_desc(L["packed"], n, h_in, h_in, c_in, cout, stride=L["s"], act=1,
-                             res_pitch=0 if res is None else cout)
+        desc = ops.conv_desc(L["packed"], n, h_in, h_in, c_in, cout, stride=L["s"], act=0 if L["head"] else 1,
+                             res_pitch=0 if res is None else cout, out_f32=L["head"])
         assert ops.conv_chain_eligible(desc)
-        chain_layers.append(dict(desc=desc, x=x0 if j == 0 else got[j - 1], packed=L["packed"], y=got[j], residual=res,
-                                 dep=j - 1, res=-1 if L["res_from"] is None else L["res_from"]))
+        chain_layers.append(dict(desc=desc, x=x0 if src_of[j] < 0 else got[src_of[j]], packed=L["packed"], y=got[j], residual=res,
+                                 dep=src_of[j], res=-1 if L["res_from"] is None else L["res_from"]))
     chain = ops.ConvChain(chain_layers, torch.device(DEV))
     for _ in range(3):   # counters are reset by every run
         chain.run()
@@ -82,6 +92,13 @@ def test_chain_13_stage_long_k():
     # 13^2 at batch 32: 22 m tiles x 4 n tiles per 3x3 layer, 72 K blocks per tile, tiles of consecutive layers
     # overlap in time across pairs
     _run_case(32, 26, 512, [(3, 2, 1024, None), (1, 1, 512, None), (3, 1, 1024, 0), (1, 1, 512, None), (3, 1, 1024, 2)])
+
+
+def test_chain_thin_layers_and_fp32_head():
+    # 64-column tiles (Darknet-53's 104^2 bottlenecks: 1x1 128 -> 64), a residual across them, and a linear fp32 head conv
+    # in the middle of the run (its output feeds nothing; the next layer reads the layer in front of it)
+    _run_case(4, 104, 64, [(3, 2, 128, None), (1, 1, 64, None), (3, 1, 128, 0), (1, 1, 64, None), (3, 1, 128, 2),
+                           (1, 1, 256, None, "head"), (1, 1, 64, None), (3, 1, 256, None), (1, 1, 128, None, "head")])
 
 
 def test_chain_rejects_ineligible():

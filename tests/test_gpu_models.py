@@ -74,7 +74,8 @@ def test_darknet53_golden(golden_dir):
 
 
 @pytest.mark.parametrize("cfg,n,size,gain", [("yolov3-tiny-12", 3, 416, 1.0), ("yolov3-tiny-12", 2, 320, 1.0),
-                                              ("yolov3", 2, 416, 0.6), ("yolov3", 1, 512, 0.6)])
+                                              ("yolov3", 2, 416, 0.6), ("yolov3", 1, 512, 0.6),
+                                              ("yolov3", 32, 416, 0.6)])     # BASELINE config 2's own shape
 def test_darknet_vs_oracle(cfg, n, size, gain):
     net = Darknet(configs.cfg_path(cfg)).eval()
     sd = synth.fill_state_dict(net.state_dict(), seed=9, conv_gain=gain, head_gain=0.5)
@@ -181,6 +182,46 @@ def test_fusion_vs_oracle(n, size, thr):
                 matched += 1
     assert matched >= 0.97 * len(ref)
     assert len(ref) > 10  # the case must actually exercise the heads
+
+
+def test_fusion_batch32_radar_points_vs_oracle():
+    """BASELINE config 3's own shape: batch 32, 416 x 416, 64 radar points per frame.  The heat-maps come from the device
+    kernel (me_radar_maps, checked against the oracle in tests/test_radar.py) and feed both the model under test and the
+    oracle; rows are matched like in test_fusion_vs_oracle and the match statistics are recorded."""
+    from millieye_b200 import radar
+    n, size, thr = 32, 416, 0.2
+    model = Network(define_yolo(configs.cfg_path("yolov3-tiny-12")), conf_thresh=thr).eval()
+    sd = synth.fill_state_dict(model.state_dict(), seed=31, obj_bias=-2.0, head_gain=0.4)
+    model.load_state_dict(sd)
+    model.to(DEV)
+    rng = np.random.RandomState(7)
+    pts = np.stack([rng.uniform(-3, 3, (n, 64)), rng.uniform(1, 10, (n, 64)), rng.uniform(-1.5, 1.5, (n, 64)),
+                    rng.uniform(-3, 3, (n, 64))], -1).astype(np.float32)
+    maps = radar.radar_maps(torch.from_numpy(pts).to(DEV), torch.full((n,), 64, dtype=torch.int32, device=DEV),
+                            radar.make_cfg(out_size=size // 16))
+    assert maps.shape == (n, 3, size // 16, size // 16)
+    imgs = synth.synth_images(n, size, seed=31)
+    rb = synth.synth_radar_boxes(n, seed=32)
+    out = model(imgs.to(DEV), maps, rb.clone().to(DEV), 0).cpu().numpy()
+    md = parse_model_config(configs.cfg_path("yolov3-tiny-12"))
+    torch.set_num_threads(max(1, os.cpu_count() or 1))
+    with torch.no_grad():
+        ref = ofus.network_forward(md, {k: v.float() for k, v in sd.items()}, imgs, maps.cpu(), rb, thr).numpy()
+    assert len(ref) > 100
+    assert abs(len(out) - len(ref)) <= max(2, len(ref) // 50)
+    matched, box_err, score_err = 0, 0.0, 0.0
+    for r in ref:
+        cand = out[(out[:, 0] == r[0]) & (out[:, 7] == r[7])]
+        if not len(cand):
+            continue
+        scale = max(size, float(np.abs(r[1:5]).max()))
+        err = np.abs(cand[:, 1:5] - r[1:5]).max(1) / scale
+        j = int(err.argmin())
+        if err[j] <= 3e-3 and abs(cand[j, 5] - r[5]) <= 5e-3 and abs(cand[j, 6] - r[6]) <= 5e-3:
+            matched += 1
+            box_err, score_err = max(box_err, float(err[j])), max(score_err, float(np.abs(cand[j, 5:7] - r[5:7]).max()))
+    _record("fusion_batch32_vs_oracle", rows_ref=len(ref), rows_gpu=len(out), matched=matched, box_err=box_err, score_err=score_err)
+    assert matched >= 0.97 * len(ref)
 
 
 def test_fusion_empty_and_errors():
