@@ -175,10 +175,13 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) conv_ch
   uint64_t* empty_bar = bars + kMaxStages;      // per CTA, multicast-arrived by the leader's commits
   uint64_t* tmem_full = bars + 2 * kMaxStages;  // per CTA
   uint64_t* tmem_empty = tmem_full + 2;         // leader CTA only, 16 arrivals
-  uint64_t* stg_ready = tmem_empty + 2;         // staging tile free (and the residual, if any, landed)
-  uint64_t* stg_full = stg_ready + 1;           // [2] staging tile written by the 8 epilogue warps; tile i uses [i & 1],
-                                                // so each store warp observes every phase of its own barrier
+  // Staging: 64 KB.  Tiles of <= 128 fp16 columns (<= 32 KB) alternate between its two halves, so the epilogue of tile
+  // i+1 writes one half while tile i's store still reads the other (the short-K 1x1 layers were bound by that hand-over);
+  // 256-column and fp32 tiles take the whole area.  Work item i uses barrier / store warp i & 1:
+  uint64_t* stg_ready = tmem_empty + 2;         // [2] the tile's staging region is free (and its residual, if any, landed)
+  uint64_t* stg_full = stg_ready + 2;           // [2] the region has been written by the 8 epilogue warps
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(stg_full + 2);
+  volatile int* released = reinterpret_cast<volatile int*>(tmem_ptr + 2);   // [2] last item whose staging reads are done
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -200,9 +203,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) conv_ch
         ptx::mbar_init(&tmem_full[a], 1);
         ptx::mbar_init(&tmem_empty[a], 16);  // 8 epilogue warps x 2 CTAs
       }
-      ptx::mbar_init(stg_ready, 1);
+      ptx::mbar_init(&stg_ready[0], 1);
+      ptx::mbar_init(&stg_ready[1], 1);
       ptx::mbar_init(&stg_full[0], kEpiThreads / 32);
       ptx::mbar_init(&stg_full[1], kEpiThreads / 32);
+      released[0] = -1;
+      released[1] = -1;
       ptx::fence_mbar_init();
     }
     __syncwarp();
@@ -366,7 +372,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) conv_ch
       }
       ME_CHAIN_TRACED(w_tfull, mbar_wait(&tmem_full[acc], acc_phase, p.debug, 0x400u + acc));
       ptx::tc_fence_after();
-      ME_CHAIN_TRACED(w_stg, mbar_wait(stg_ready, it & 1, p.debug, 0x500u));
+      ME_CHAIN_TRACED(w_stg, mbar_wait(&stg_ready[it & 1], (it >> 1) & 1, p.debug, 0x500u + (it & 1)));
+      // this tile's staging region (see the layout comment at the top of the kernel)
+      uint8_t* stg = staging + ((bn <= 128 && !out_f32) ? (it & 1) * (kStagingBytes / 2) : 0);
 
       const int c_base = half * (bn / 2);
       const int nch = bn / 64;   // 32-column chunks per warp: 1, 2 or 4
@@ -390,7 +398,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) conv_ch
           for (int j = 0; j < 32; ++j) v[j] = 1.f / (1.f + __expf(-v[j]));
         }
         if (out_f32) {
-          uint8_t* sub = staging + (c >> 5) * kSubBytes;
+          uint8_t* sub = stg + (c >> 5) * kSubBytes;
           const uint32_t rbase = row * 128;
 #pragma unroll
           for (int j = 0; j < 8; ++j) {
@@ -400,7 +408,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) conv_ch
           }
           return;
         }
-        uint8_t* sub = staging + (c >> 6) * kSubBytes;
+        uint8_t* sub = stg + (c >> 6) * kSubBytes;
         const uint32_t rbase = row * 128 + (c & 63) * 2;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
@@ -448,17 +456,23 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) conv_ch
     if (tr) { tr[9] = w_tfull; tr[10] = w_stg; tr[12] = clock64(); }
   } else {
     // ------------------------------------------------------------------ store warps (alternating tiles)
+    // Warp w owns the work items i with (i & 1) == w: it hands item i its staging region (stg_ready[w]; the residual
+    // tile is TMA-loaded into the region first), waits for the epilogue (stg_full[w]), issues the TMA store, marks the
+    // region's reads done (released[w] = i), then waits for the store to COMPLETE and publishes the tile's counter.
     const int w = warp - (2 + kEpiThreads / 32);
     if (ptx::elect_one()) {
-      int cur = -1;
-      const ChainLayer* L = nullptr;
-      // Gives the staging tile to work item `item`: its residual tile is TMA-loaded into it (after the layer that
-      // produces the residual has stored those rows), or the barrier is simply arrived on.
-      auto hand_over = [&](int item) {
+      auto half_tile = [&](int item) {   // <= 32 KB of staging: alternates between the two halves
+        const ChainLayer* N = p.layers + (item >> kItemShift);
+        return N->bn <= 128 && !N->out_f32;
+      };
+      auto region = [&](int i, int item) { return staging + (half_tile(item) ? (i & 1) * (kStagingBytes / 2) : 0); };
+      // Gives work item i its staging region: the residual tile is loaded into it (after the layer that produces the
+      // residual has stored those rows), or the barrier is simply arrived on.
+      auto hand_over = [&](int i, int item) {
         const ChainLayer* N = p.layers + (item >> kItemShift);
         const int tile = item & ((1 << kItemShift) - 1);
         if (!N->has_res) {
-          ptx::mbar_arrive(stg_ready);
+          ptx::mbar_arrive(&stg_ready[w]);
           return;
         }
         const int tm = tile / N->tiles_n, tn = tile - tm * N->tiles_n;
@@ -469,10 +483,15 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) conv_ch
           fence_proxy_async_all();
         }
         const int nsub = N->bn / 64;   // (residual layers are fp16)
-        ptx::mbar_arrive_expect_tx(stg_ready, nsub * kSubBytes);
+        uint8_t* dst = region(i, item);
+        ptx::mbar_arrive_expect_tx(&stg_ready[w], nsub * kSubBytes);
         for (int sub = 0; sub < nsub; ++sub)
-          ptx::tma_load_2d(&N->tmR, stg_ready, staging + sub * kSubBytes, tn * N->bn + sub * 64, m0);
+          ptx::tma_load_2d(&N->tmR, &stg_ready[w], dst + sub * kSubBytes, tn * N->bn + sub * 64, m0);
       };
+      int cur = -1;
+      const ChainLayer* L = nullptr;
+      int prev_item = -1;        // item i - 1 (the other warp's)
+      bool handed = false;       // item i was already handed over at the end of item i - 2
       for (int i = 0;; ++i) {
         const int item = __ldg(wl + i);
         if (item < 0) break;
@@ -483,29 +502,53 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1) conv_ch
           ptx::prefetch_tmap(&L->tmC);
           if (L->has_res) ptx::prefetch_tmap(&L->tmR);
         }
-        if (i == 0 && w == 0) hand_over(item);
-        if ((i & 1) != w) continue;
+        if ((i & 1) != w) {
+          prev_item = item;
+          continue;
+        }
+        if (!handed) {
+          // the region overlaps item i - 1's when either takes the whole area: wait until the other warp's store has
+          // read it (item i - 2's region was released by this warp before it got here)
+          if (i >= 1 && (!half_tile(item) || !half_tile(prev_item))) {
+            const long long t0 = clock64();
+            uint32_t spins = 0;
+            while (released[1 - w] < i - 1) {
+              if ((++spins & 1023u) == 0 && clock64() - t0 > 4000000000LL) watchdog_trap(p.debug, 0x900u + w, 0);
+            }
+            __threadfence_block();
+          }
+          hand_over(i, item);
+        }
+        handed = false;
         const int tm = tile / L->tiles_n, tn = tile - tm * L->tiles_n;
         const int m0 = tm * 2 * kBM + static_cast<int>(rank) * kBM, n0 = tn * L->bn;
         mbar_wait(&stg_full[w], (i >> 1) & 1, p.debug, 0x600u + w);
         if (m0 < L->M) {
           const int sub_cols = L->out_f32 ? 32 : 64;
           const int nsub = L->bn / sub_cols;
+          const uint8_t* src = region(i, item);
           for (int sub = 0; sub < nsub; ++sub)
-            ptx::tma_store_2d(&L->tmC, staging + sub * kSubBytes, n0 + sub * sub_cols, m0);
+            ptx::tma_store_2d(&L->tmC, src + sub * kSubBytes, n0 + sub * sub_cols, m0);
           ptx::tma_store_commit();
-          ptx::tma_store_wait_read0();    // the staging tile has been read
+          ptx::tma_store_wait_read0();    // the staging region has been read
         }
-        const int next = __ldg(wl + i + 1);
-        // The next tile's residual may be (or depend on) the tile just stored: publish first in that case, or the
-        // wait inside hand_over() would wait for this very thread.  Otherwise the staging tile is handed over first
-        // and the wait for the store's completion stays off the epilogue's critical path.
-        const bool next_waits = next >= 0 && p.layers[next >> kItemShift].has_res && p.layers[next >> kItemShift].res_base >= 0;
-        if (next >= 0 && !next_waits) hand_over(next);
+        __threadfence_block();
+        released[w] = i;
+        // Item i + 2 reuses this very half when items i, i+1, i+2 are all half tiles: hand it over right away, unless
+        // its residual may depend on the tile just stored (then this thread must publish first, or it would wait for
+        // itself inside hand_over()).
+        const int next1 = __ldg(wl + i + 1);
+        const int next2 = next1 >= 0 ? __ldg(wl + i + 2) : -1;
+        if (next2 >= 0 && half_tile(item) && half_tile(next1) && half_tile(next2)) {
+          const ChainLayer* N2 = p.layers + (next2 >> kItemShift);
+          if (!(N2->has_res && N2->res_base >= 0)) {
+            hand_over(i + 2, next2);
+            handed = true;
+          }
+        }
         ptx::tma_store_wait_all0();       // the tile is in memory
         fence_proxy_async_all();
         publish_counter(p.counters + L->ctr_base + tm);
-        if (next_waits) hand_over(next);
       }
     }
     __syncwarp();

@@ -296,10 +296,17 @@ class DarknetPlan:
             return ops.conv_desc(m["packed"], self.n, sv.h, sv.w, sv.pitch, o.pitch, stride=m["stride"], act=m["act"],
                                  res_pitch=0 if rv is None else rv.pitch, cin=m["cin"], cout=m["cout"], out_f32=m["f32"])
 
+        # Measured on B200 (profiles/round2/chain_trace_r2k.log): the 256-row pair tiles lose to the single-CTA kernels on
+        # the thin 104^2 layers (1x1 128 -> 64 etc.: 2 K blocks per tile, the epilogue outlasts the MMAs - the run of
+        # blocks 5..9 took 285 us chained against 212 us as four launches), so layers with fewer than 128 filters, and 1x1
+        # layers over fewer than 128 channels, stay per-layer launches.
+        def profitable(m):
+            return m["cout"] >= 128 and (m["cin"] >= 128 or m["packed"].ksize == 3)
+
         # head convs that cannot join a chain go to the end of the list so that they do not interrupt a run
         def deferred(k):
             m = self._conv_meta.get(k)
-            return m is not None and m["leaf"] and not ops.conv_chain_eligible(describe(k))
+            return m is not None and m["leaf"] and not (ops.conv_chain_eligible(describe(k)) and profitable(m))
 
         order = [k for k in range(n_ops) if not deferred(k)] + [k for k in range(n_ops) if deferred(k)]
         # producer op of every conv output view: buffer -> [(channel offset, channels, op)]
@@ -353,7 +360,7 @@ class DarknetPlan:
         cuts = {int(v) for v in os.environ.get("ME_CHAIN_CUT", "").split(",") if v}
         for k in order:
             m = self._conv_meta.get(k)
-            ok = m is not None and ops.conv_chain_eligible(describe(k))
+            ok = m is not None and ops.conv_chain_eligible(describe(k)) and profitable(m)
             if ok and self.op_blocks[k] in cuts:
                 flush()
             if ok:

@@ -211,9 +211,10 @@ def test_plan_launch_list_on_cpu(monkeypatch):
 
 
 def test_chain_formation_on_cpu(monkeypatch):
-    """DarknetPlan._form_chains without a GPU: Darknet-53's launch list becomes 4 per-layer launches (the 416^2 / 208^2
-    layers with fewer than 64 channels on one side), three chains (the trunk from the first 104^2 layer down plus the 13^2
-    head, the 26^2 head, the 52^2 head - each including its fp32 head conv) separated by the two upsamples; every chain
+    """DarknetPlan._form_chains without a GPU: Darknet-53's launch list becomes 8 per-layer launches (the 416^2 .. 104^2
+    layers with fewer than 128 filters, and the 3x3 layers between them), three chains (the trunk from the last 104^2
+    layer down plus the 13^2 head, the 26^2 head, the 52^2 head - each including its fp32 head conv) separated by the two
+    upsamples; every chain
     layer names the layer that produces its input / residual, or -1 when that tensor is complete before the chain
     starts; chains that write head logits exist once per output slot."""
     import torch
@@ -250,9 +251,9 @@ def test_chain_formation_on_cpu(monkeypatch):
     kinds = plan.op_kinds
     assert kinds.count("upsample") == 2 and len(chains) == 6     # three chains x two output slots
     sizes = [len(c.layers) for c in chains[::2]]
-    assert sizes == [56, 8, 7] and sum(sizes) + 4 == 75          # every conv is launched exactly once
-    # launch order: 4 early layers, chain, upsample, chain, upsample, chain
-    assert [isinstance(b, list) for b in plan.op_blocks] == [False] * 4 + [True, False, True, False, True]
+    assert sizes == [52, 8, 7] and sum(sizes) + 8 == 75          # every conv is launched exactly once
+    # launch order: 8 early layers, chain, upsample, chain, upsample, chain
+    assert [isinstance(b, list) for b in plan.op_blocks] == [False] * 8 + [True, False, True, False, True]
     for c0, c1 in zip(chains[::2], chains[1::2]):
         heads = [j for j, l in enumerate(c0.layers) if l["desc"].out_f32]
         assert len(heads) == 1
@@ -267,9 +268,10 @@ def test_chain_formation_on_cpu(monkeypatch):
             if l["residual"] is not None and l["res"] >= 0:
                 assert c.layers[l["res"]]["y"].data_ptr() == l["residual"].data_ptr()
     first = chains[0].layers
-    assert first[0]["dep"] == -1 and first[0]["desc"].stride == 2 and first[0]["desc"].cout == 128   # 208^2 -> 104^2
-    assert [l["dep"] for l in first[1:54]] == list(range(53))    # a straight line down to the last 13^2 trunk conv
-    assert first[54]["desc"].out_f32 == 1 and first[54]["dep"] == 53     # the 13^2 head conv reads the 3x3 before it
-    assert first[55]["dep"] == 52 and first[55]["desc"].cout == 256      # route -4: the 1x1 in front of the upsample
-    assert sum(1 for l in first if l["residual"] is not None) == 22      # 2 + 8 + 8 + 4 residual blocks
+    assert first[0]["dep"] == -1 and first[0]["res"] == -1 and first[0]["residual"] is not None   # 104^2 3x3 64->128 + shortcut
+    assert first[1]["desc"].stride == 2 and first[1]["desc"].cout == 256
+    assert [l["dep"] for l in first[1:50]] == list(range(49))    # a straight line down to the last 13^2 trunk conv
+    assert first[50]["desc"].out_f32 == 1 and first[50]["dep"] == 49     # the 13^2 head conv reads the 3x3 before it
+    assert first[51]["dep"] == 48 and first[51]["desc"].cout == 256      # route -4: the 1x1 in front of the upsample
+    assert sum(1 for l in first if l["residual"] is not None) == 21      # 1 + 8 + 8 + 4 residual blocks
     assert all(l["dep"] == -1 for l in (chains[2].layers[0], chains[4].layers[0]))   # they read concat buffers
