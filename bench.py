@@ -227,9 +227,11 @@ def check_parity(host_batch, rec, frames):
         md = parse_model_config(configs.cfg_path(CFG))
         sd = synth.fill_state_dict(Darknet(configs.cfg_path(CFG)).state_dict(), seed=0, conv_gain=0.6, **WEIGHTS)
         x = host_batch[:frames].clone()
+        if x.dtype == torch.uint8:
+            x = x.float() / 255.0     # ToTensor, what the device applies to uploaded bytes
         with torch.no_grad():
             _, y = odark.darknet_forward(md, sd, x)
-        ref = obox.non_max_suppression_cpp(y.clone().numpy(), CONF_THRESH, use_torchvision=True)
+        ref, _ = obox.non_max_suppression_cpp(y.clone().numpy(), CONF_THRESH, use_torchvision=True)
         det = rec.host_det.numpy()
         cnt = rec.host_cnt.numpy()
         rows_ref = rows_gpu = matched = exact_order = 0
@@ -314,11 +316,12 @@ def _fusion_inputs(n, device, seed):
     from millieye_b200 import radar
     from oracle import synth
     gen = torch.Generator(device="cpu").manual_seed(seed)
-    imgs = torch.rand(n, 3, SIZE, SIZE, generator=gen)
+    imgs_u8 = torch.randint(0, 256, (n, 3, SIZE, SIZE), generator=gen, dtype=torch.uint8)   # frames as bytes (cv2 / camera)
+    imgs = imgs_u8.float() / 255.0
     rng = np.random.RandomState(seed)
     pts = np.stack([rng.uniform(-3, 3, (n, 64)), rng.uniform(1, 10, (n, 64)), rng.uniform(-1.5, 1.5, (n, 64)),
                     rng.uniform(-3, 3, (n, 64))], -1).astype(np.float32)
-    return dict(imgs=imgs.pin_memory(), imgs_dev=imgs.to(device), pts=torch.from_numpy(pts).to(device),
+    return dict(imgs=imgs_u8.pin_memory(), imgs_dev=imgs.to(device), pts=torch.from_numpy(pts).to(device),
                 cnt=torch.full((n,), 64, dtype=torch.int32, device=device), cfg=radar.make_cfg(out_size=SIZE // 16),
                 boxes=synth.synth_radar_boxes(n, seed=seed).to(device))
 
@@ -380,8 +383,9 @@ def run_fusion(args):
                           conf_thresh=CONF_THRESH, rows_last_step=int(last["out"].shape[0]),
                           l2="~1 GB of activations per step exceed the 126 MB L2; no explicit flush"),
               clocks=clocks,
-              e2e=dict(value=fps_e2e, unit="frames/s", h2d_bytes_per_step=BATCH * 3 * SIZE * SIZE * 4,
-                       d2h_bytes_per_step=int(last["host"].numel() * 4), ms_per_step=ms_e2e / args.steps),
+              e2e=dict(value=fps_e2e, unit="frames/s", h2d_bytes_per_step=BATCH * 3 * SIZE * SIZE,
+                       d2h_bytes_per_step=int(last["host"].numel() * 4), ms_per_step=ms_e2e / args.steps,
+                       input="uint8 (N,3,S,S) frames in pinned host memory, ToTensor (x / 255) on the device"),
               gpu_launches=int((len(plan.ops) + len(plan.post_ops) + 14) * args.steps),
               roofline=dict(bound="hbm", achieved=achieved, peak=pk["hbm_gbs"], unit="GB/s", frac=achieved / pk["hbm_gbs"],
                             traffic=None, peak_source=pk["src"], kernel="tiny-12 conv stack (conv_gemm / conv_thin / conv_first_tc / "
@@ -463,8 +467,8 @@ def run_train3(args):
                                    f"{SIZE}x{SIZE}, 64 radar points per frame", proposals_per_rank_last_step=int(last["rows"]),
                           trainable_parameters=int(opt.numel), sync_bn=world > 1),
               clocks=clocks,
-              e2e=dict(value=fps_e2e, unit="frames/s", h2d_bytes_per_step=per * 3 * SIZE * SIZE * 4, d2h_bytes_per_step=4,
-                       ms_per_step=ms_e2e / args.steps),
+              e2e=dict(value=fps_e2e, unit="frames/s", h2d_bytes_per_step=per * 3 * SIZE * SIZE, d2h_bytes_per_step=4,
+                       ms_per_step=ms_e2e / args.steps, input="uint8 frames in pinned host memory, ToTensor on the device"),
               gpu_launches=int(150 * args.steps),
               roofline=dict(bound="hbm", achieved=bytes_step / (ms_dev / args.steps * 1e-3) / 1e9, peak=pk["hbm_gbs"], unit="GB/s",
                             frac=bytes_step / (ms_dev / args.steps * 1e-3) / 1e9 / pk["hbm_gbs"], traffic=None, peak_source=pk["src"],
@@ -499,8 +503,10 @@ def run_gpu(args):
     net, _ = build_models(device)
     gen = torch.Generator(device="cpu").manual_seed(1234 + rank)
     n_inputs = 3
-    host = [torch.rand(BATCH, 3, SIZE, SIZE, generator=gen).pin_memory() for _ in range(n_inputs)]
-    resident = [h.to(device) for h in host]
+    # Frames arrive as bytes (cv2 / camera frames, run_sp.py:205-211): the e2e arm uploads uint8 (N,3,S,S) from pinned host
+    # memory and the device applies ToTensor's x / 255; the device-resident arm starts from the same values in fp32.
+    host = [torch.randint(0, 256, (BATCH, 3, SIZE, SIZE), generator=gen, dtype=torch.uint8).pin_memory() for _ in range(n_inputs)]
+    resident = [h.to(device).float() / 255.0 for h in host]
     plan = net.plan_for(BATCH, SIZE, device)
     from millieye_b200.models import DetectPipeline
     pipe = DetectPipeline(net, CONF_THRESH, 0.5, 200, gather=world > 1)
@@ -606,7 +612,7 @@ def run_gpu(args):
     fps_e2e = world * BATCH * args.steps / ms_e2e * 1e3
     achieved_burst = flops_frame * BATCH / (conv_ms * 1e-3) / 1e12
     achieved_long = flops_frame * BATCH / (conv_ms_long * 1e-3) / 1e12 if conv_ms_long else None
-    h2d = BATCH * 3 * SIZE * SIZE * 4
+    h2d = BATCH * 3 * SIZE * SIZE     # uint8 frames
     d2h = rec.host_det.numel() * 4 + rec.host_cnt.numel() * 4
 
     cpu = None
@@ -661,7 +667,8 @@ def run_gpu(args):
                             sub_batches=plan.splits, detections_last_step=int(sum(counts))),
                 clocks=clocks,
                 e2e=dict(value=fps_e2e, unit="frames/s", h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h,
-                         ms_per_step=ms_e2e / args.steps),
+                         ms_per_step=ms_e2e / args.steps,
+                         input="uint8 (N,3,S,S) frames in pinned host memory, ToTensor (x / 255) on the device"),
                 gpu_launches=int(launches_per_step * args.steps),
                 roofline=roofline, parity_checked=bool(parity and parity.get("checked")), parity=parity,
                 cpu_baseline=cpu)

@@ -160,6 +160,10 @@ int me_copy_channels(const void* x, void* y, long long pixels, int c, int in_pit
 /* NHWC fp16 (pitch) -> NCHW fp32 contiguous: the featuremap handed back to PyTorch callers
  * (models.py:254-255). */
 int me_nhwc_to_nchw_f32(const void* x, float* y, int n, int h, int w, int c, int in_pitch, me_stream_t stream);
+/* uint8 image bytes -> fp32 in 0..1 (x / 255): torchvision ToTensor, which the reference applies on the HOST before the
+ * upload (utils/datasets.py:209; run_sp.py:205-211 for camera frames).  Doing it here lets callers upload bytes: a quarter
+ * of the host -> device traffic.  Same layout in and out; both buffers 16-byte aligned. */
+int me_u8_to_unit_f32(const void* x, float* y, long long count, me_stream_t stream);
 /* NCHW fp32 -> NHWC fp16 (pitch, zero padded channels). */
 int me_nchw_f32_to_nhwc(const float* x, void* y, int n, int h, int w, int c, int out_pitch, me_stream_t stream);
 

@@ -80,6 +80,7 @@ SIGNATURES = {
     "me_upsample2": (c_int, [c_void_p, c_void_p] + [c_int] * 6 + [c_void_p]),
     "me_copy_channels": (c_int, [c_void_p, c_void_p, c_longlong, c_int, c_int, c_int, c_void_p]),
     "me_nhwc_to_nchw_f32": (c_int, [c_void_p, c_void_p] + [c_int] * 5 + [c_void_p]),
+    "me_u8_to_unit_f32": (c_int, [c_void_p, c_void_p, c_longlong, c_void_p]),
     "me_nchw_f32_to_nhwc": (c_int, [c_void_p, c_void_p] + [c_int] * 5 + [c_void_p]),
     "me_yolo_decode": (c_int, [c_void_p, c_int, c_void_p, c_int, c_int, c_int, c_int, POINTER(c_float), c_float,
                                c_int, c_int, c_void_p]),

@@ -168,6 +168,22 @@ __global__ void upsample2_kernel(const __half* __restrict__ x, __half* __restric
   }
 }
 
+// ToTensor on the device: uint8 0..255 -> fp32 0..1 (x / 255, the division torchvision's ToTensor performs), 16 values per thread
+__global__ void u8_to_unit_f32_kernel(const uint4* __restrict__ x, float4* __restrict__ y, long long n16, const unsigned char* tail_x,
+                                      float* tail_y, int tail) {
+  for (long long i = blockIdx.x * 1LL * blockDim.x + threadIdx.x; i < n16; i += 1LL * gridDim.x * blockDim.x) {
+    const uint4 v = x[i];
+    const unsigned int wds[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const unsigned int u = wds[k];
+      y[i * 4 + k] = make_float4(static_cast<float>(u & 0xffu) / 255.f, static_cast<float>((u >> 8) & 0xffu) / 255.f,
+                                 static_cast<float>((u >> 16) & 0xffu) / 255.f, static_cast<float>(u >> 24) / 255.f);
+    }
+  }
+  if (blockIdx.x == 0 && static_cast<int>(threadIdx.x) < tail) tail_y[threadIdx.x] = static_cast<float>(tail_x[threadIdx.x]) / 255.f;
+}
+
 __global__ void copy_channels_kernel(const __half* __restrict__ x, __half* __restrict__ y, long long pixels, int c8,
                                      int in_pitch, int out_pitch) {
   const long long total = pixels * c8;
@@ -370,6 +386,22 @@ int me_nhwc_to_nchw_f32(const void* x, float* y, int n, int h, int w, int c, int
   const int hw = h * w;
   dim3 grid(ceil_div(hw, 32), ceil_div(c, 32), n), block(32, 8);
   nhwc_to_nchw_kernel<<<grid, block, 0, stream>>>(static_cast<const __half*>(x), y, hw, c, in_pitch);
+  ME_LAUNCH_CHECK();
+  return ME_OK;
+}
+
+int me_u8_to_unit_f32(const void* x, float* y, long long count, me_stream_t stream_) {
+  using namespace me;
+  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+  if (count <= 0) return ME_OK;
+  ME_REQUIRE(x && y, "u8_to_unit_f32: null argument");
+  ME_REQUIRE((reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(y) & 15) == 0,
+             "u8_to_unit_f32: buffers must be 16-byte aligned");
+  const long long n16 = count / 16;
+  const int tail = static_cast<int>(count - n16 * 16);
+  const unsigned char* xb = static_cast<const unsigned char*>(x);
+  u8_to_unit_f32_kernel<<<grid_for(n16 > 0 ? n16 : 1, 256), 256, 0, stream>>>(static_cast<const uint4*>(x), reinterpret_cast<float4*>(y),
+                                                                             n16, xb + n16 * 16, y + n16 * 16, tail);
   ME_LAUNCH_CHECK();
   return ME_OK;
 }

@@ -120,6 +120,7 @@ class DarknetPlan:
         # Two input buffers (and one captured graph per buffer): the host->device copy of batch i+1 runs on a
         # copy stream while the graph of batch i is still executing.
         self._x_bufs = [torch.zeros((n, in_channels, size, size), dtype=torch.float32, device=device) for _ in range(2)]
+        self._u8_bufs = [None, None]     # staging for uint8 frames (load_input)
         self._slot = 0
         self._graphs = [None, None]
         self._post_graphs = [None, None]
@@ -505,12 +506,20 @@ class DarknetPlan:
     def load_input(self, x):
         """Stages the next batch: switches to the other input buffer and copies x into it (nothing to copy when x is
         next_input()).  A pinned host tensor is copied on a separate stream, so the PCIe transfer overlaps the previous
-        forward."""
+        forward.  x may be fp32 in 0..1 (the reference's contract) or uint8 0..255 in the same (N,C,S,S) layout: bytes
+        are uploaded as they are and divided by 255 on the device - exactly ToTensor's values, a quarter of the traffic."""
         self._slot ^= 1
         buf = self._x_bufs[self._slot]
         cur = torch.cuda.current_stream()
+        is_u8 = x.dtype == torch.uint8
+        if is_u8 and (tuple(x.shape) != tuple(buf.shape) or not x.is_contiguous()):
+            raise MeError(f"uint8 frames must be contiguous {tuple(buf.shape)} (N,C,S,S) bytes")
+        if is_u8 and self._u8_bufs[self._slot] is None:
+            self._u8_bufs[self._slot] = torch.zeros(buf.shape, dtype=torch.uint8, device=self.device)
         if x.is_cuda:
-            if x.data_ptr() != buf.data_ptr() or x.shape != buf.shape or not x.is_contiguous():
+            if is_u8:
+                ops.u8_to_unit_f32(x, buf)
+            elif x.data_ptr() != buf.data_ptr() or x.shape != buf.shape or not x.is_contiguous():
                 buf.copy_(x, non_blocking=True)
             return
         if self._copy_stream is None:
@@ -519,7 +528,12 @@ class DarknetPlan:
         if self._slot_free[self._slot] is not None:
             cs.wait_event(self._slot_free[self._slot])
         with torch.cuda.stream(cs):
-            buf.copy_(x, non_blocking=True)
+            if is_u8:
+                # camera frames as bytes: a quarter of the PCIe traffic; ToTensor's x / 255 runs on the device
+                self._u8_bufs[self._slot].copy_(x, non_blocking=True)
+                ops.u8_to_unit_f32(self._u8_bufs[self._slot], buf)
+            else:
+                buf.copy_(x, non_blocking=True)
         cur.wait_stream(cs)
 
     def run_decode(self, use_graph=True):

@@ -220,6 +220,14 @@ def nhwc_to_nchw_f32(x, n, h, w, c, in_pitch, out=None):
     return out
 
 
+def u8_to_unit_f32(x, out):
+    """uint8 image bytes -> fp32 0..1 (x / 255, ToTensor) on the device; same shape in and out."""
+    _need_cuda(x, out)
+    assert x.dtype == torch.uint8 and out.dtype == torch.float32 and x.numel() == out.numel() and x.is_contiguous()
+    check(_lib.lib().me_u8_to_unit_f32(ptr(x), ptr(out), x.numel(), stream_ptr()), "me_u8_to_unit_f32")
+    return out
+
+
 def nchw_f32_to_nhwc(x, out_pitch=None, out=None):
     _need_cuda(x)
     assert x.dtype == torch.float32 and x.is_contiguous()

@@ -405,3 +405,23 @@ def test_fused_decode_equals_separate_kernels(monkeypatch):
         assert (len(plan.post_ops) > 0) == (flag == "0")
         outs.append(plan.yolo_out.clone())
     assert torch.equal(outs[0], outs[1])
+
+
+def test_uint8_frames_equal_totensor():
+    """Frames uploaded as bytes ((N,3,S,S) uint8, pinned host or device) give exactly the result of the reference's
+    contract input, ToTensor's x / 255 in fp32 - through Darknet.forward, DetectPipeline and Network.forward."""
+    from millieye_b200.models import DetectPipeline
+    net = Darknet(configs.cfg_path("yolov3-tiny-12")).eval()
+    net.load_state_dict(synth.fill_state_dict(net.state_dict(), seed=4, obj_bias=-1.0))
+    net.to(DEV)
+    g = torch.Generator().manual_seed(5)
+    u8 = torch.randint(0, 256, (3, 3, 160, 160), generator=g, dtype=torch.uint8)
+    want = net(u8.float().div(255).to(DEV))[1]
+    assert torch.equal(net(u8.to(DEV))[1], want)                 # bytes already on the device
+    assert torch.equal(net(u8.pin_memory())[1], want)            # bytes in pinned host memory (copy stream)
+    pipe = DetectPipeline(net, 0.1)
+    a = pipe.submit(u8.pin_memory(), readback=True).wait()
+    b = pipe.submit(u8.float().div(255).pin_memory(), readback=True).wait()
+    assert torch.equal(a.host_cnt, b.host_cnt) and torch.equal(a.host_det, b.host_det)
+    with pytest.raises(MeError):
+        net(u8.permute(0, 2, 3, 1).contiguous().to(DEV))          # NHWC bytes are not the contract layout
