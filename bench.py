@@ -31,9 +31,11 @@ CFG = "yolov3"
 CONF_THRESH = 0.2     # test_fusion.py:143
 CPU_BATCH = 4         # bounded CPU sample (Darknet-53 on CPU is run at N=4)
 METRIC = "frames/sec at 416x416 batch32"
-# synthetic head statistics: objectness logits come out ~ N(-3.3, 0.8), so a few hundred of the 10 647 boxes per frame
-# pass the 0.2 confidence filter and the NMS has real work (random-init heads give conf ~ 0.5 everywhere)
-WEIGHTS = dict(obj_bias=-2.5, head_gain=3.0)
+# Synthetic head statistics (random-init heads give conf ~ 0.5 everywhere): head logits are kept narrow
+# (std ~ 0.13: boxes near their anchor sizes, like a trained detector's) and the objectness bias puts the 0.2 confidence
+# threshold about two standard deviations above the mean, so a few hundred of the 10 647 boxes per frame pass the filter and
+# the NMS has real work.  Wide logits (the round-1 recipe, gain 3) only amplify the fp16 error through exp() in the decode.
+WEIGHTS = dict(obj_bias=-1.5, head_gain=0.5)
 
 
 _JSON_FD = None

@@ -87,14 +87,14 @@ typedef struct me_conv_desc {
 int me_conv_gemm(const me_conv_desc* d, const void* x, const void* w_packed, const float* bias,
                  const void* residual, void* y, me_stream_t stream);
 
-/* Optional workspace of me_conv_gemm's split-K tail (layers whose last wave of 256 x 256 tiles would leave most SM
- * pairs idle cut those tiles along K; partial sums and arrival counters live here).  Zero-filled by the caller once,
- * me_conv_workspace_bytes() long, 256-byte aligned; kernels that may overlap on different streams need different
- * workspaces (set it before enqueueing on each stream).  NULL (the initial state) disables the split.  The setting is
- * process-global, like the device; results are deterministic and independent of whether the split is used up to fp32
- * summation order. */
+/* me_conv_gemm with a workspace for the split-K tail: layers whose last wave of 256 x 256 tiles would leave most SM pairs
+ * idle cut those tiles along K; partial sums and arrival counters live in `workspace` (zero-filled by the caller once,
+ * me_conv_workspace_bytes() long, 256-byte aligned; NULL: no split).  The workspace belongs to the call, not to the
+ * library: launches that may overlap (different streams, different host threads) simply pass different buffers - there is
+ * no process-global state.  Results are deterministic and equal to me_conv_gemm's up to fp32 summation order. */
 size_t me_conv_workspace_bytes(void);
-int me_conv_set_workspace(void* dev_workspace, size_t bytes);
+int me_conv_gemm_ws(const me_conv_desc* d, const void* x, const void* w_packed, const float* bias, const void* residual,
+                    void* y, void* workspace, size_t workspace_bytes, me_stream_t stream);
 
 /* ---- a run of conv layers as one persistent kernel --------------------------------------------------------------
  * Darknet.forward walks its module list one layer at a time (yolov3/models.py:247-262); launched that way a third of

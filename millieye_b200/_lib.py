@@ -70,7 +70,8 @@ SIGNATURES = {
     "me_conv_chain_build": (c_int, [POINTER(ChainLayer), c_int, c_void_p, c_size_t]),
     "me_conv_chain_run": (c_int, [c_void_p, c_void_p, c_void_p]),
     "me_conv_workspace_bytes": (c_size_t, []),
-    "me_conv_set_workspace": (c_int, [c_void_p, c_size_t]),
+    "me_conv_gemm_ws": (c_int, [POINTER(ConvDesc), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t,
+                                c_void_p]),
     "me_conv_gemm_yolo": (c_int, [POINTER(ConvDesc), c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, POINTER(c_float),
                                   c_float, c_int, c_int, c_void_p, c_void_p]),
     "me_fold_first_weights": (c_int, [c_void_p] * 6 + [c_float, c_int, c_int, c_void_p, c_void_p, c_void_p]),

@@ -22,7 +22,8 @@
 namespace me {
 
 int conv_gemm_pair(int bn, const me_conv_desc* d, const void* x, const void* w, const float* bias, const void* residual,
-                   void* y, cudaStream_t stream);  // conv_gemm_pair.cu
+                   void* y, void* tail_ws, cudaStream_t stream);  // conv_gemm_pair.cu
+size_t conv_pair_workspace_bytes();
 bool conv_thin_enabled();                          // conv_thin.cu
 bool conv_thin_supported(const me_conv_desc* d);
 int conv_thin(const me_conv_desc* d, const void* x, const void* w, const float* bias, const void* residual, void* y,
@@ -703,7 +704,8 @@ int me_debug_status(unsigned long long* host_word) {
 }
 
 static int conv_dispatch(const me_conv_desc* d, const void* x, const void* w_packed, const float* bias,
-                         const void* residual, void* y, me_stream_t stream_, const me::DecodeParams* dec) {
+                         const void* residual, void* y, me_stream_t stream_, const me::DecodeParams* dec,
+                         void* tail_ws = nullptr) {
   using namespace me;
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   ME_REQUIRE(d && x && w_packed && bias && y, "conv: null argument");
@@ -758,7 +760,7 @@ static int conv_dispatch(const me_conv_desc* d, const void* x, const void* w_pac
     // 128-channel layers are faster on single-CTA tiles.  (13^2 x 32 frames = 5408 rows: pair256 52.7 us vs
     // 57.2 us on single-CTA tiles, profiles/round1/attr_r1e.log)
     else if (mode == 0 && d->ksize == 3 && cout >= 256 && m >= 4096) pair_bn = 256;
-    if (pair_bn) return conv_gemm_pair(pair_bn, d, x, w_packed, bias, residual, y, stream);
+    if (pair_bn) return conv_gemm_pair(pair_bn, d, x, w_packed, bias, residual, y, tail_ws, stream);
   }
   // Epilogue groups (see Cfg): two for the thin tiles (N <= 64), whose epilogue outlasts their MMAs, and for short-K
   // 1x1 layers with N = 128 (52^2 256->128: -23 %); the 3x3 and long-K N = 128 layers keep one group because the
@@ -796,6 +798,17 @@ static int conv_dispatch(const me_conv_desc* d, const void* x, const void* w_pac
 int me_conv_gemm(const me_conv_desc* d, const void* x, const void* w_packed, const float* bias, const void* residual,
                  void* y, me_stream_t stream) {
   return conv_dispatch(d, x, w_packed, bias, residual, y, stream, nullptr);
+}
+
+int me_conv_gemm_ws(const me_conv_desc* d, const void* x, const void* w_packed, const float* bias, const void* residual,
+                    void* y, void* workspace, size_t workspace_bytes, me_stream_t stream) {
+  using namespace me;
+  if (workspace != nullptr) {
+    ME_REQUIRE(workspace_bytes >= conv_pair_workspace_bytes(), "conv workspace: %zu bytes given, %zu needed", workspace_bytes,
+               conv_pair_workspace_bytes());
+    ME_REQUIRE((reinterpret_cast<uintptr_t>(workspace) & 255) == 0, "conv workspace must be 256-byte aligned");
+  }
+  return conv_dispatch(d, x, w_packed, bias, residual, y, stream, nullptr, workspace);
 }
 
 int me_conv_gemm_yolo(const me_conv_desc* d, const void* x, const void* w_packed, const float* bias, int g,

@@ -514,12 +514,11 @@ conv_gemm_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_cons
 }
 
 // Workspace of the tail split: at most one work item per pair, so 96 x 2 partial tiles of 128 x 256 fp32 (25 MB) and
-// 96 x 2 counters bound it for every layer.  It is the caller's (me_conv_set_workspace): the library allocates nothing,
+// 96 x 2 counters bound it for every layer.  It is the caller's (me_conv_gemm_ws): the library allocates nothing,
 // and kernels that may overlap on different streams must be given different workspaces.
 constexpr int kMaxPairs = 96;
 constexpr size_t kWsPartialBytes = static_cast<size_t>(kMaxPairs) * 2 * kBM * 256 * sizeof(float);
 constexpr size_t kWsBytes = kWsPartialBytes + kMaxPairs * 2 * sizeof(int);
-float* g_tail_ws = nullptr;
 
 // ME_PAIR_SPLIT=0 disables the tail split (A/B measurements).
 bool tail_split_enabled() {
@@ -533,7 +532,7 @@ bool tail_split_enabled() {
 
 template <int BN>
 int launch_pair(const me_conv_desc* d, const void* x, const void* w, const float* bias, const void* residual, void* y,
-                cudaStream_t stream) {
+                void* tail_ws, cudaStream_t stream) {
   using C = PCfg<BN>;
   const int pad = (d->ksize - 1) / 2;
   const int Ho = (d->h + 2 * pad - d->ksize) / d->stride + 1;
@@ -635,12 +634,12 @@ int launch_pair(const me_conv_desc* d, const void* x, const void* w, const float
     int slices = pairs / tail;
     if (slices > p.num_kb / 4) slices = p.num_kb / 4;
     if (slices > 4) slices = 4;   // the finisher reads every slice's partial tile: beyond 4 that costs what the split saves
-    if (slices >= 4 && g_tail_ws != nullptr) {
+    if (slices >= 4 && tail_ws != nullptr) {
       p.whole_limit = total - tail;
       p.tail_tiles = tail;
       p.slices = slices;
-      p.ws = g_tail_ws;
-      p.counters = reinterpret_cast<int*>(reinterpret_cast<unsigned char*>(g_tail_ws) + kWsPartialBytes);
+      p.ws = static_cast<float*>(tail_ws);
+      p.counters = reinterpret_cast<int*>(static_cast<unsigned char*>(tail_ws) + kWsPartialBytes);
     }
   }
   cudaLaunchConfig_t cfg{};
@@ -662,27 +661,17 @@ int launch_pair(const me_conv_desc* d, const void* x, const void* w, const float
 
 // Entry used by me_conv_gemm's dispatcher. bn is 128 or 256.
 int conv_gemm_pair(int bn, const me_conv_desc* d, const void* x, const void* w, const float* bias, const void* residual,
-                   void* y, cudaStream_t stream) {
-  if (bn == 256) return launch_pair<256>(d, x, w, bias, residual, y, stream);
-  return launch_pair<128>(d, x, w, bias, residual, y, stream);
+                   void* y, void* tail_ws, cudaStream_t stream) {
+  if (bn == 256) return launch_pair<256>(d, x, w, bias, residual, y, tail_ws, stream);
+  return launch_pair<128>(d, x, w, bias, residual, y, tail_ws, stream);
 }
+
+size_t conv_pair_workspace_bytes() { return kWsBytes; }
 
 }  // namespace me
 
 extern "C" {
 
-size_t me_conv_workspace_bytes(void) { return me::kWsBytes; }
-
-int me_conv_set_workspace(void* dev_workspace, size_t bytes) {
-  using namespace me;
-  if (dev_workspace == nullptr) {
-    g_tail_ws = nullptr;
-    return ME_OK;
-  }
-  ME_REQUIRE(bytes >= kWsBytes, "conv workspace: %zu bytes given, %zu needed", bytes, kWsBytes);
-  ME_REQUIRE((reinterpret_cast<uintptr_t>(dev_workspace) & 255) == 0, "conv workspace must be 256-byte aligned");
-  g_tail_ws = static_cast<float*>(dev_workspace);
-  return ME_OK;
-}
+size_t me_conv_workspace_bytes(void) { return me::conv_pair_workspace_bytes(); }
 
 }  // extern "C"

@@ -125,6 +125,7 @@ class DarknetPlan:
         self._graphs = [None, None]
         self._post_graphs = [None, None]
         self._conv_ws = []
+        self._ws_now = None
         self._conv_meta = {}   # op index -> conv launch description
         self.chains = []       # ops.ConvChain objects (kept alive; the op list holds their run())
         # ME_CONV_CHAIN=0: one kernel per conv layer (per-layer tools: conv_trace.py, ncu_layers.py)
@@ -214,7 +215,7 @@ class DarknetPlan:
                 is_head = nxt is not None and nxt["type"] == "yolo"
                 out_idx = i + 1 if fuse_res is not None else i
                 cout = b["filters"]
-                if is_head and self.fuse_decode and b["size"] == 1 and not b["leaky"] and readers[i] == []:
+                if is_head and self.fuse_decode and b["size"] == 1 and not b["leaky"] and readers[i] == [] and i not in target:
                     g = s_out
                     packed = self._pack(i, b)
                     self._add(lambda b0, nb, sv=src, p=packed, bb=nxt, g=g, st=self.size / g, ro=row_off: ops.conv_gemm_yolo(
@@ -244,6 +245,9 @@ class DarknetPlan:
             elif t == "maxpool":
                 if b["size"] != 2:
                     raise MeError("only 2x2 max-pool is supported")
+                if i in target:
+                    raise MeError("a max-pool that feeds a two-input route is not supported (its output would have to be "
+                                  "written into the concat buffer)")
                 ov = View(self._new(s_out, s_out, ops.round_up(src.c, 8)), 0, src.c, s_out, s_out, real_c=src.real_c)
                 self._add(lambda b0, nb, sv=src, o=ov, st=b["stride"]: ops.maxpool2(
                     sv.at(b0), o.at(b0), nb, sv.h, sv.w, ops.round_up(sv.c, 8), sv.pitch, o.pitch, st), "maxpool", i)
@@ -253,9 +257,9 @@ class DarknetPlan:
                     raise MeError("only x2 upsample is supported")
                 if i in target:
                     buf, off = target[i]
-                    ov = View(buf, off, src.c, s_out, s_out)
+                    ov = View(buf, off, src.c, s_out, s_out, real_c=src.real_c)
                 else:
-                    ov = View(self._new(s_out, s_out, ops.round_up(src.c, 8)), 0, src.c, s_out, s_out)
+                    ov = View(self._new(s_out, s_out, ops.round_up(src.c, 8)), 0, src.c, s_out, s_out, real_c=src.real_c)
                 self._add(lambda b0, nb, sv=src, o=ov: ops.upsample2(sv.at(b0), o.at(b0), nb, sv.h, sv.w, sv.c, sv.pitch,
                                                                      o.pitch), "upsample", i)
                 views[i] = ov
@@ -439,7 +443,7 @@ class DarknetPlan:
         self._add(lambda b0, nb, sv=src, p=packed, o=ov, st=b["stride"], a=act, rv=res_v, f32=is_head: ops.conv_gemm(
             sv.at(b0), p, nb, sv.h, sv.w, sv.pitch, self._slot_view(o).at(b0), o.pitch, stride=st, act=a,
             residual=None if rv is None else rv.at(b0), res_pitch=0 if rv is None else rv.pitch,
-            cin=sv.real_c if sv.real_c != sv.c else sv.c, cout=p.cout_pad, out_f32=f32), "conv", i)
+            cin=sv.real_c if sv.real_c != sv.c else sv.c, cout=p.cout_pad, out_f32=f32, workspace=self._ws_now), "conv", i)
 
     # ------------------------------------------------------------------ execution
     def enqueue(self, b0=0, nb=None, only=None):
@@ -448,13 +452,10 @@ class DarknetPlan:
         k = b0 // nb if nb else 0
         while len(self._conv_ws) <= k:
             self._conv_ws.append(ops.conv_workspace(self.device))
-        ops.conv_set_workspace(self._conv_ws[k])
-        try:
-            for i, fn in enumerate(self.ops):
-                if only is None or i in only:
-                    fn(b0, nb)
-        finally:
-            ops.conv_set_workspace(None)
+        self._ws_now = self._conv_ws[k]      # what the conv ops of this sub-batch pass to me_conv_gemm_ws
+        for i, fn in enumerate(self.ops):
+            if only is None or i in only:
+                fn(b0, nb)
 
     def enqueue_post(self):
         """The decode kernels of the current slot (head logits -> yolo_out)."""

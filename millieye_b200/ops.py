@@ -63,14 +63,21 @@ def pack_conv(weight, conv_bias=None, bn=None, cout_pad=None):
 
 
 def conv_gemm(x, packed, n, h, w, in_pitch, out, out_pitch, stride=1, act=ME_ACT_LEAKY, residual=None, res_pitch=0,
-              cin=None, cout=None, out_f32=False):
-    """x / out / residual are NHWC fp16 buffers (any tensor whose data_ptr is the first pixel of the view)."""
-    _need_cuda(x, out, residual)
+              cin=None, cout=None, out_f32=False, workspace=None):
+    """x / out / residual are NHWC fp16 buffers (any tensor whose data_ptr is the first pixel of the view).
+    workspace: conv_workspace() buffer that lets the pair kernel split its tail tiles along K (per call: launches that may
+    overlap pass different buffers)."""
+    _need_cuda(x, out, residual, workspace)
     d = ConvDesc(n=n, h=h, w=w, cin=cin or packed.cin, in_pitch=in_pitch, cout=cout or packed.cout_pad,
                  out_pitch=out_pitch, ksize=packed.ksize, stride=stride, act=act, out_f32=1 if out_f32 else 0,
                  res_pitch=res_pitch if residual is not None else 0)
-    check(_lib.lib().me_conv_gemm(byref(d), ptr(x), ptr(packed.w), ptr(packed.bias), ptr(residual), ptr(out),
-                                  stream_ptr()), "me_conv_gemm")
+    if workspace is None:
+        check(_lib.lib().me_conv_gemm(byref(d), ptr(x), ptr(packed.w), ptr(packed.bias), ptr(residual), ptr(out),
+                                      stream_ptr()), "me_conv_gemm")
+    else:
+        check(_lib.lib().me_conv_gemm_ws(byref(d), ptr(x), ptr(packed.w), ptr(packed.bias), ptr(residual), ptr(out),
+                                         ptr(workspace), workspace.numel() * workspace.element_size(), stream_ptr()),
+              "me_conv_gemm_ws")
     return out
 
 
@@ -140,17 +147,8 @@ class ConvChain:
 
 
 def conv_workspace(device):
-    """Zero-filled workspace for the conv kernels' split-K tail (include/millieye_b200.h: me_conv_set_workspace)."""
+    """Zero-filled workspace for the conv kernels' split-K tail (include/millieye_b200.h: me_conv_gemm_ws)."""
     return torch.zeros((_lib.lib().me_conv_workspace_bytes(),), dtype=torch.uint8, device=device)
-
-
-def conv_set_workspace(ws):
-    """Selects the workspace the following me_conv_gemm launches use (None: no split-K tail)."""
-    if ws is None:
-        check(_lib.lib().me_conv_set_workspace(None, 0), "me_conv_set_workspace")
-    else:
-        _need_cuda(ws)
-        check(_lib.lib().me_conv_set_workspace(ptr(ws), ws.numel() * ws.element_size()), "me_conv_set_workspace")
 
 
 class FirstConv:

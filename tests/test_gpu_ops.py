@@ -49,12 +49,9 @@ def _conv_case(n, h, w, cin, cout, k, s, act, bn=True, res=False, f32=False, see
     if res:
         ref = ref + resid[..., :cout].float().permute(0, 3, 1, 2)
     out = torch.full((n, ho, wo, cout_pad), float("nan"), dtype=torch.float32 if f32 else torch.float16, device=DEV)
-    ops.conv_set_workspace(_conv_ws())          # like the engine: lets the pair kernel split the tail tiles along K
-    try:
-        ops.conv_gemm(xh.to(DEV), packed, n, h, w, in_pitch, out, cout_pad, stride=s, act=act,
-                      residual=None if resid is None else resid.to(DEV), res_pitch=cout_pad, out_f32=f32)
-    finally:
-        ops.conv_set_workspace(None)
+    # like the engine: the workspace lets the pair kernel split the tail tiles along K
+    ops.conv_gemm(xh.to(DEV), packed, n, h, w, in_pitch, out, cout_pad, stride=s, act=act,
+                  residual=None if resid is None else resid.to(DEV), res_pitch=cout_pad, out_f32=f32, workspace=_conv_ws())
     torch.cuda.synchronize()
     got = out.float().cpu()[..., :cout].permute(0, 3, 1, 2)
     assert not torch.isnan(got).any()
@@ -432,11 +429,8 @@ def test_pair_tail_split_is_deterministic_and_reusable():
     outs = []
     for k in range(4):
         out = torch.zeros(n, g, g, cout, dtype=torch.float16, device=DEV)
-        ops.conv_set_workspace(_conv_ws() if k < 3 else None)      # the last run has no workspace: unsplit kernel
-        try:
-            ops.conv_gemm(x, packed, n, g, g, cin, out, cout)
-        finally:
-            ops.conv_set_workspace(None)
+        # the last run has no workspace: unsplit kernel
+        ops.conv_gemm(x, packed, n, g, g, cin, out, cout, workspace=_conv_ws() if k < 3 else None)
         outs.append(out)
     torch.cuda.synchronize()
     assert torch.equal(outs[0], outs[1]) and torch.equal(outs[0], outs[2])
