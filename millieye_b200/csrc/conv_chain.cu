@@ -27,6 +27,8 @@
 #include "common.cuh"
 #include "ptx.cuh"
 #include <cstdlib>
+#include <queue>
+#include <utility>
 #include <vector>
 
 namespace me {
@@ -755,57 +757,151 @@ int me_conv_chain_build(const me_chain_layer* layers, int n_layers, void* host_b
   H->total_bytes = static_cast<long long>(need);
   int* work = reinterpret_cast<int*>(base + H->work_off);
 
-  const double kKb = 512.0, kTile = 1500.0, kHand = 3000.0;
+  // Rows [lo, hi] of the producer that m tile `tm` of layer h reads, as producer m tiles [a, b] (same rule as dep_rows()).
+  auto dep_tiles = [&](const HostLayer& h, int tm, int* a, int* b) {
+    int m0 = tm * 2 * kBM, m1 = m0 + 2 * kBM - 1;
+    if (m1 > h.M - 1) m1 = h.M - 1;
+    int lo, hi;
+    if (h.dep_kind == 0) {
+      lo = m0;
+      hi = m1;
+    } else if (h.dep_kind == 1) {
+      lo = m0 - h.Win - 1;
+      hi = m1 + h.Win + 1;
+    } else {
+      const int hw = h.Ho * h.Wo;
+      const int n0 = m0 / hw, y0 = (m0 - n0 * hw) / h.Wo, n1 = m1 / hw, y1 = (m1 - n1 * hw) / h.Wo;
+      int r0 = 2 * y0 - 1, r1 = 2 * y1 + 1;
+      if (r0 < 0) r0 = 0;
+      if (r1 > h.Hin - 1) r1 = h.Hin - 1;
+      lo = (n0 * h.Hin + r0) * h.Win;
+      hi = (n1 * h.Hin + r1) * h.Win + h.Win - 1;
+    }
+    if (lo < 0) lo = 0;
+    if (hi > h.dep_M - 1) hi = h.dep_M - 1;
+    *a = lo / (2 * kBM);
+    *b = hi / (2 * kBM);
+  };
+  // Timing model (clocks): a K block is operand-bound at ~750 clocks on 256-column tiles and on 128-column ones (A fetch);
+  // a fixed cost per tile; a dependent tile can start kHand after the tile it reads was stored (store completion, counter,
+  // first TMA load).  ME_CHAIN_SCHED=0: the round-2a greedy in strict layer-major order (A/B measurements).
+  const double kKb = 750.0, kTile = 2500.0, kHand = 6000.0;
   std::vector<double> pair_t(npairs, 0.0);
   std::vector<int> pair_n(npairs, 0);
   std::vector<std::vector<double>> done(n_layers);   // completion time of every m tile
-  for (int l = 0; l < n_layers; ++l) {
-    const HostLayer& h = hl[l];
-    done[l].assign(h.tiles_m, 0.0);
-    const double cost = h.num_kb * kKb + kTile;
-    for (int tm = 0; tm < h.tiles_m; ++tm) {
-      double ready = 0.0;
-      if (h.dep >= 0) {
-        int m0 = tm * 2 * kBM, m1 = m0 + 2 * kBM - 1;
-        if (m1 > h.M - 1) m1 = h.M - 1;
-        int lo, hi;
-        if (h.dep_kind == 0) {
-          lo = m0;
-          hi = m1;
-        } else if (h.dep_kind == 1) {
-          lo = m0 - h.Win - 1;
-          hi = m1 + h.Win + 1;
-        } else {
-          const int hw = h.Ho * h.Wo;
-          const int n0 = m0 / hw, y0 = (m0 - n0 * hw) / h.Wo, n1 = m1 / hw, y1 = (m1 - n1 * hw) / h.Wo;
-          int r0 = 2 * y0 - 1, r1 = 2 * y1 + 1;
-          if (r0 < 0) r0 = 0;
-          if (r1 > h.Hin - 1) r1 = h.Hin - 1;
-          lo = (n0 * h.Hin + r0) * h.Win;
-          hi = (n1 * h.Hin + r1) * h.Win + h.Win - 1;
+  for (int l = 0; l < n_layers; ++l) done[l].assign(hl[l].tiles_m, 0.0);
+  const char* sched_env = getenv("ME_CHAIN_SCHED");
+  const bool list_sched = !(sched_env && sched_env[0] == '0');
+  if (!list_sched) {
+    for (int l = 0; l < n_layers; ++l) {
+      const HostLayer& h = hl[l];
+      const double cost = h.num_kb * kKb + kTile;
+      for (int tm = 0; tm < h.tiles_m; ++tm) {
+        double ready = 0.0;
+        if (h.dep >= 0) {
+          int a, b;
+          dep_tiles(h, tm, &a, &b);
+          for (int t = a; t <= b; ++t)
+            if (done[h.dep][t] > ready) ready = done[h.dep][t];
+          ready += kHand;
         }
-        if (lo < 0) lo = 0;
-        if (hi > h.dep_M - 1) hi = h.dep_M - 1;
-        for (int t = lo / (2 * kBM); t <= hi / (2 * kBM); ++t)
-          if (done[h.dep][t] > ready) ready = done[h.dep][t];
-        ready += kHand;
+        if (h.res >= 0 && done[h.res][tm] + kHand > ready) ready = done[h.res][tm] + kHand;
+        for (int tn = 0; tn < h.tiles_n; ++tn) {
+          int best = 0;
+          double best_key = 1e300;
+          for (int q = 0; q < npairs; ++q) {
+            const double key = pair_t[q] >= ready ? pair_t[q] : ready + (ready - pair_t[q]) * 1e-6;
+            if (key < best_key) {
+              best_key = key;
+              best = q;
+            }
+          }
+          const double start = pair_t[best] > ready ? pair_t[best] : ready;
+          pair_t[best] = start + cost;
+          if (pair_t[best] > done[l][tm]) done[l][tm] = pair_t[best];
+          work[static_cast<long long>(best) * stride + pair_n[best]++] = (l << kItemShift) | (tm * h.tiles_n + tn);
+        }
       }
-      if (h.res >= 0 && done[h.res][tm] + kHand > ready) ready = done[h.res][tm] + kHand;
-      for (int tn = 0; tn < h.tiles_n; ++tn) {
-        // the pair that becomes free first; among pairs already free at `ready`, the one that has idled least
-        int best = 0;
-        double best_key = 1e300;
-        for (int q = 0; q < npairs; ++q) {
-          const double key = pair_t[q] >= ready ? pair_t[q] : ready + (ready - pair_t[q]) * 1e-6;
-          if (key < best_key) {
-            best_key = key;
-            best = q;
+    }
+  } else {
+    // Event-driven list scheduling: whenever a pair becomes free it takes, among the tiles whose inputs are (in the model)
+    // already stored, the one earliest in layer-major order - so tiles of layer l+1 start while the tail of layer l is
+    // still running, and a tile whose inputs come late does not sit at the head of a list blocking ready work behind it.
+    // Lists are ordered by modelled start time; every tile starts after the tiles it reads, so that order is a valid
+    // global order and the run-time waits cannot deadlock (see the kernel comment).
+    struct MT { int waiting; double ready; int assigned; double finish; };
+    std::vector<std::vector<MT>> mt(n_layers);
+    std::vector<std::vector<std::vector<std::pair<int, int>>>> wakes(n_layers);   // (layer, tm) -> dependents
+    for (int l = 0; l < n_layers; ++l) {
+      mt[l].assign(hl[l].tiles_m, MT{0, 0.0, 0, 0.0});
+      wakes[l].resize(hl[l].tiles_m);
+    }
+    for (int l = 0; l < n_layers; ++l) {
+      const HostLayer& h = hl[l];
+      for (int tm = 0; tm < h.tiles_m; ++tm) {
+        if (h.dep >= 0) {
+          int a, b;
+          dep_tiles(h, tm, &a, &b);
+          for (int t = a; t <= b; ++t) {
+            wakes[h.dep][t].push_back({l, tm});
+            ++mt[l][tm].waiting;
           }
         }
-        const double start = pair_t[best] > ready ? pair_t[best] : ready;
-        pair_t[best] = start + cost;
-        if (pair_t[best] > done[l][tm]) done[l][tm] = pair_t[best];
-        work[static_cast<long long>(best) * stride + pair_n[best]++] = (l << kItemShift) | (tm * h.tiles_n + tn);
+        if (h.res >= 0) {
+          wakes[h.res][tm].push_back({l, tm});
+          ++mt[l][tm].waiting;
+        }
+      }
+    }
+    // min-heaps: pairs by free time; pending m tiles by ready time; available m tiles by (layer, tm)
+    typedef std::pair<double, int> DI;
+    std::priority_queue<DI, std::vector<DI>, std::greater<DI>> pairs_q;
+    for (int q = 0; q < npairs; ++q) pairs_q.push({0.0, q});
+    typedef std::pair<double, std::pair<int, int>> RT;
+    std::priority_queue<RT, std::vector<RT>, std::greater<RT>> pending;
+    typedef std::pair<int, int> LT;
+    std::priority_queue<LT, std::vector<LT>, std::greater<LT>> avail;
+    std::vector<std::vector<int>> next_tn(n_layers);
+    for (int l = 0; l < n_layers; ++l) {
+      next_tn[l].assign(hl[l].tiles_m, 0);
+      for (int tm = 0; tm < hl[l].tiles_m; ++tm)
+        if (mt[l][tm].waiting == 0) pending.push({0.0, {l, tm}});
+    }
+    long long left = tiles;
+    while (left > 0) {
+      DI pq = pairs_q.top();
+      pairs_q.pop();
+      double t = pq.first;
+      const int q = pq.second;
+      while (!pending.empty() && pending.top().first <= t) {
+        avail.push(pending.top().second);
+        pending.pop();
+      }
+      if (avail.empty()) {
+        if (pending.empty()) return fail(ME_ERR_ARG, "conv_chain: the layer dependencies form a cycle");
+        t = pending.top().first;    // the pair idles until the next tile becomes ready
+        while (!pending.empty() && pending.top().first <= t) {
+          avail.push(pending.top().second);
+          pending.pop();
+        }
+      }
+      const LT cur = avail.top();
+      const int l = cur.first, tm = cur.second;
+      const HostLayer& h = hl[l];
+      const int tn = next_tn[l][tm]++;
+      if (next_tn[l][tm] == h.tiles_n) avail.pop();
+      const double finish = t + h.num_kb * kKb + kTile;
+      work[static_cast<long long>(q) * stride + pair_n[q]++] = (l << kItemShift) | (tm * h.tiles_n + tn);
+      --left;
+      pairs_q.push({finish, q});
+      MT& m = mt[l][tm];
+      if (finish > m.finish) m.finish = finish;
+      if (++m.assigned == h.tiles_n) {
+        for (const auto& d : wakes[l][tm]) {
+          MT& w = mt[d.first][d.second];
+          if (m.finish + kHand > w.ready) w.ready = m.finish + kHand;
+          if (--w.waiting == 0) pending.push({w.ready, d});
+        }
       }
     }
   }

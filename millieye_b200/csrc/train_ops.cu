@@ -27,7 +27,9 @@ template <int BM, int BN>
 __global__ void __launch_bounds__(256)
 gemm_f32_kernel(int M, int N, int K, const float* __restrict__ A, long long sai, long long sak,
                 const float* __restrict__ B, long long sbk, long long sbj, float* __restrict__ C, long long ldc,
-                const float* __restrict__ bias, int act, int accumulate) {
+                const float* __restrict__ bias, int act, int accumulate, int k_chunk) {
+  // blockIdx.z selects a K range of k_chunk (split-K for the weight-gradient products: a few output tiles, tens of
+  // thousands of rows to reduce over); the slices add their partial tiles with atomicAdd into a zero-filled C
   constexpr int BK = 16, TM = BM / 16, TN = BN / 16;
   __shared__ float As[BK][BM + 1];
   __shared__ float Bs[BK][BN + 1];
@@ -40,7 +42,10 @@ gemm_f32_kernel(int M, int N, int K, const float* __restrict__ A, long long sai,
     for (int b = 0; b < TN; ++b) acc[a][b] = 0.f;
   // the faster-varying index of a tile load follows the operand's unit stride, so either layout loads coalesced
   const bool a_k_fast = sak == 1, b_j_fast = sbj == 1;
-  for (int k0 = 0; k0 < K; k0 += BK) {
+  const bool split = gridDim.z > 1;
+  const int k_begin = blockIdx.z * k_chunk;
+  if (split) K = min(K, k_begin + k_chunk);
+  for (int k0 = k_begin; k0 < K; k0 += BK) {
     for (int e = threadIdx.x; e < BM * BK; e += 256) {
       const int i = a_k_fast ? e / BK : e % BM, k = a_k_fast ? e % BK : e / BM;
       const int gi = i0 + i, gk = k0 + k;
@@ -76,7 +81,9 @@ gemm_f32_kernel(int M, int N, int K, const float* __restrict__ A, long long sai,
       if (gj >= N) continue;
       float v = acc[a][b];
       float* c = C + gi * ldc + gj;
-      if (accumulate) {
+      if (split) {
+        atomicAdd(c, v);
+      } else if (accumulate) {
         *c += v;
       } else {
         if (bias) v += bias[gj];
@@ -89,25 +96,42 @@ gemm_f32_kernel(int M, int N, int K, const float* __restrict__ A, long long sai,
 }
 
 // ------------------------------------------------------------------------------------------------ column sums
-// out[c] = sum_r X[r][c] * (Y ? Y[r][c] : 1), double accumulation.  One block per 32 columns, 8 row lanes.
-__global__ void __launch_bounds__(256)
+// out[c] = sum_r X[r][c] * (Y ? Y[r][c] : 1), double accumulation.  One block of 32 x 32 threads per 32 columns: a warp
+// reads 32 consecutive columns of one row (128 bytes), the 32 warps take rows r, r+32, ... four at a time (memory-level
+// parallelism: with 8 row lanes and one load in flight the 43 264-row sums of a batch-64 step took ~0.3 ms each).
+// Fixed reduction order: deterministic.
+constexpr int kColsumLanes = 32;
+__global__ void __launch_bounds__(32 * kColsumLanes)
 colsum_kernel(const float* __restrict__ X, const float* __restrict__ Y, long long rows, int cols, long long ldx,
               long long ldy, float* __restrict__ out) {
-  __shared__ double s[8][33];
+  __shared__ double s[kColsumLanes][33];
   const int c = blockIdx.x * 32 + (threadIdx.x & 31);
   const int lane_r = threadIdx.x >> 5;
   double acc = 0.0;
-  if (c < cols)
-    for (long long r = lane_r; r < rows; r += 8) {
+  if (c < cols) {
+    long long r = lane_r;
+    for (; r + 3 * kColsumLanes < rows; r += 4 * kColsumLanes) {
+      float x[4], y[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) x[u] = X[(r + u * kColsumLanes) * ldx + c];
+      if (Y) {
+#pragma unroll
+        for (int u = 0; u < 4; ++u) y[u] = Y[(r + u * kColsumLanes) * ldy + c];
+      }
+#pragma unroll
+      for (int u = 0; u < 4; ++u) acc += Y ? static_cast<double>(x[u]) * static_cast<double>(y[u]) : static_cast<double>(x[u]);
+    }
+    for (; r < rows; r += kColsumLanes) {
       const float x = X[r * ldx + c];
       acc += Y ? static_cast<double>(x) * static_cast<double>(Y[r * ldy + c]) : static_cast<double>(x);
     }
+  }
   s[lane_r][threadIdx.x & 31] = acc;
   __syncthreads();
   if (lane_r == 0 && c < cols) {
     double t = 0.0;
 #pragma unroll
-    for (int k = 0; k < 8; ++k) t += s[k][threadIdx.x & 31];
+    for (int k = 0; k < kColsumLanes; ++k) t += s[k][threadIdx.x & 31];
     out[c] = static_cast<float>(t);
   }
 }
@@ -172,25 +196,38 @@ __global__ void col2im3_kernel(const float* __restrict__ dcols, int n, int h, in
 //   partial : sums[c] = sum_r z[r][c], sums[cols + c] = sum_r z[r][c]^2 (double), sums[2 cols] = rows
 //   finalize: mean, biased variance -> inv_std; running statistics updated like nn.BatchNorm2d in training mode
 //             (momentum m, unbiased variance into running_var).  The row count is read from device memory.
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(32 * kColsumLanes)
 bn_partial_kernel(const float* __restrict__ z, long long rows, int cols, double* __restrict__ sums) {
-  __shared__ double s1[8][33], s2[8][33];
+  __shared__ double s1[kColsumLanes][33], s2[kColsumLanes][33];
   const int c = blockIdx.x * 32 + (threadIdx.x & 31);
   const int lr = threadIdx.x >> 5;
   double a = 0.0, b = 0.0;
-  if (c < cols)
-    for (long long r = lr; r < rows; r += 8) {
+  if (c < cols) {
+    long long r = lr;
+    for (; r + 3 * kColsumLanes < rows; r += 4 * kColsumLanes) {
+      float x[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) x[u] = z[(r + u * kColsumLanes) * cols + c];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) {
+        const double v = static_cast<double>(x[u]);
+        a += v;
+        b += v * v;
+      }
+    }
+    for (; r < rows; r += kColsumLanes) {
       const double v = static_cast<double>(z[r * cols + c]);
       a += v;
       b += v * v;
     }
+  }
   s1[lr][threadIdx.x & 31] = a;
   s2[lr][threadIdx.x & 31] = b;
   __syncthreads();
   if (lr == 0 && c < cols) {
     double t1 = 0.0, t2 = 0.0;
 #pragma unroll
-    for (int k = 0; k < 8; ++k) {
+    for (int k = 0; k < kColsumLanes; ++k) {
       t1 += s1[k][threadIdx.x & 31];
       t2 += s2[k][threadIdx.x & 31];
     }
@@ -493,14 +530,28 @@ int me_gemm_f32(int M, int N, int K, const float* A, long long sai, long long sa
   if (M <= 0 || N <= 0) return ME_OK;
   ME_REQUIRE(A && B && C && K >= 0, "gemm_f32: null argument");
   ME_REQUIRE(!accumulate || (!bias && act == ME_ACT_LINEAR), "gemm_f32: accumulate excludes bias / activation");
-  // few output tiles (the dW products: small M x N, long K): 32 x 32 tiles put more CTAs on the machine
   const long long tiles64 = 1LL * ((M + 63) / 64) * ((N + 63) / 64);
-  if (tiles64 >= 148) {
+  // Few output tiles and a long reduction (the weight gradients dW = dZ^T x over all pixels / proposals of the batch):
+  // split K over blockIdx.z so that ~4 waves of CTAs work, partial tiles added with atomicAdd into a zero-filled C.
+  int splits = 1, k_chunk = K;
+  if (tiles64 < 148 && K >= 4096 && !bias && act == ME_ACT_LINEAR) {
+    splits = static_cast<int>((4 * 148 + tiles64 - 1) / tiles64);
+    if (splits > K / 512) splits = K / 512;
+    if (splits < 1) splits = 1;
+    k_chunk = (((K + splits - 1) / splits) + 15) / 16 * 16;
+    splits = (K + k_chunk - 1) / k_chunk;
+  }
+  if (splits > 1) {
+    if (!accumulate) ME_CUDA(cudaMemset2DAsync(C, static_cast<size_t>(ldc) * sizeof(float), 0, static_cast<size_t>(N) * sizeof(float), M, stream));
+    dim3 grid((N + 63) / 64, (M + 63) / 64, splits);
+    gemm_f32_kernel<64, 64><<<grid, 256, 0, stream>>>(M, N, K, A, sai, sak, B, sbk, sbj, C, ldc, nullptr, ME_ACT_LINEAR, 0, k_chunk);
+  } else if (tiles64 >= 148) {
     dim3 grid((N + 63) / 64, (M + 63) / 64);
-    gemm_f32_kernel<64, 64><<<grid, 256, 0, stream>>>(M, N, K, A, sai, sak, B, sbk, sbj, C, ldc, bias, act, accumulate);
+    gemm_f32_kernel<64, 64><<<grid, 256, 0, stream>>>(M, N, K, A, sai, sak, B, sbk, sbj, C, ldc, bias, act, accumulate, K);
   } else {
+    // few output tiles, short K: 32 x 32 tiles put more CTAs on the machine
     dim3 grid((N + 31) / 32, (M + 31) / 32);
-    gemm_f32_kernel<32, 32><<<grid, 256, 0, stream>>>(M, N, K, A, sai, sak, B, sbk, sbj, C, ldc, bias, act, accumulate);
+    gemm_f32_kernel<32, 32><<<grid, 256, 0, stream>>>(M, N, K, A, sai, sak, B, sbk, sbj, C, ldc, bias, act, accumulate, K);
   }
   ME_LAUNCH_CHECK();
   return ME_OK;
@@ -511,7 +562,7 @@ int me_colsum_f32(const float* X, const float* Y, long long rows, int cols, long
   using namespace me;
   if (cols <= 0) return ME_OK;
   ME_REQUIRE(X && out, "colsum_f32: null argument");
-  colsum_kernel<<<(cols + 31) / 32, 256, 0, static_cast<cudaStream_t>(stream)>>>(X, Y, rows, cols, ldx, ldy, out);
+  colsum_kernel<<<(cols + 31) / 32, 32 * kColsumLanes, 0, static_cast<cudaStream_t>(stream)>>>(X, Y, rows, cols, ldx, ldy, out);
   ME_LAUNCH_CHECK();
   return ME_OK;
 }
@@ -553,7 +604,7 @@ int me_col2im3_f32(const float* dcols, int n, int h, int w, int c, float* dx, me
 int me_bn_partial_stats(const float* z, long long rows, int cols, double* sums, me_stream_t stream) {
   using namespace me;
   ME_REQUIRE(sums && cols > 0 && rows >= 0 && (rows == 0 || z), "bn_partial_stats: bad argument");
-  bn_partial_kernel<<<(cols + 31) / 32, 256, 0, static_cast<cudaStream_t>(stream)>>>(z, rows, cols, sums);
+  bn_partial_kernel<<<(cols + 31) / 32, 32 * kColsumLanes, 0, static_cast<cudaStream_t>(stream)>>>(z, rows, cols, sums);
   ME_LAUNCH_CHECK();
   return ME_OK;
 }
@@ -595,8 +646,8 @@ int me_bn_bwd_sums(float* da_inout, const float* a, const float* xhat, long long
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   ME_REQUIRE(dgamma && dbeta && cols > 0 && rows >= 0 && (rows == 0 || (da_inout && a && xhat)), "bn_bwd_sums: bad argument");
   if (rows > 0) leaky_bwd_kernel<<<grid_for(rows * cols), 256, 0, stream>>>(da_inout, a, rows * cols);
-  colsum_kernel<<<(cols + 31) / 32, 256, 0, stream>>>(da_inout, xhat, rows, cols, cols, cols, dgamma);
-  colsum_kernel<<<(cols + 31) / 32, 256, 0, stream>>>(da_inout, nullptr, rows, cols, cols, cols, dbeta);
+  colsum_kernel<<<(cols + 31) / 32, 32 * kColsumLanes, 0, stream>>>(da_inout, xhat, rows, cols, cols, cols, dgamma);
+  colsum_kernel<<<(cols + 31) / 32, 32 * kColsumLanes, 0, stream>>>(da_inout, nullptr, rows, cols, cols, cols, dbeta);
   ME_LAUNCH_CHECK();
   return ME_OK;
 }
