@@ -27,8 +27,6 @@
 #include "common.cuh"
 #include "ptx.cuh"
 #include <cstdlib>
-#include <queue>
-#include <utility>
 #include <vector>
 
 namespace me {
@@ -782,17 +780,16 @@ int me_conv_chain_build(const me_chain_layer* layers, int n_layers, void* host_b
     *a = lo / (2 * kBM);
     *b = hi / (2 * kBM);
   };
-  // Timing model (clocks): a K block is operand-bound at ~750 clocks on 256-column tiles and on 128-column ones (A fetch);
-  // a fixed cost per tile; a dependent tile can start kHand after the tile it reads was stored (store completion, counter,
-  // first TMA load).  ME_CHAIN_SCHED=0: the round-2a greedy in strict layer-major order (A/B measurements).
-  const double kKb = 750.0, kTile = 2500.0, kHand = 6000.0;
+  // Work lists: the tiles in strict layer-major order, each given to the pair that can start it first in a small timing
+  // model (clocks): K blocks of 512 tensor clocks, a fixed cost per tile, a tile can start kHand after the m tiles it reads
+  // were stored.  (An event-driven list scheduler that lets tiles of layer l+1 overtake the tail of layer l was measured
+  // and dropped: conv stack 2.46 vs 2.42 ms on Darknet-53, and the kernel relies on layer-major lists.)
+  const double kKb = 512.0, kTile = 1500.0, kHand = 3000.0;
   std::vector<double> pair_t(npairs, 0.0);
   std::vector<int> pair_n(npairs, 0);
   std::vector<std::vector<double>> done(n_layers);   // completion time of every m tile
   for (int l = 0; l < n_layers; ++l) done[l].assign(hl[l].tiles_m, 0.0);
-  const char* sched_env = getenv("ME_CHAIN_SCHED");
-  const bool list_sched = !(sched_env && sched_env[0] == '0');
-  if (!list_sched) {
+  {
     for (int l = 0; l < n_layers; ++l) {
       const HostLayer& h = hl[l];
       const double cost = h.num_kb * kKb + kTile;
@@ -820,87 +817,6 @@ int me_conv_chain_build(const me_chain_layer* layers, int n_layers, void* host_b
           pair_t[best] = start + cost;
           if (pair_t[best] > done[l][tm]) done[l][tm] = pair_t[best];
           work[static_cast<long long>(best) * stride + pair_n[best]++] = (l << kItemShift) | (tm * h.tiles_n + tn);
-        }
-      }
-    }
-  } else {
-    // Event-driven list scheduling: whenever a pair becomes free it takes, among the tiles whose inputs are (in the model)
-    // already stored, the one earliest in layer-major order - so tiles of layer l+1 start while the tail of layer l is
-    // still running, and a tile whose inputs come late does not sit at the head of a list blocking ready work behind it.
-    // Lists are ordered by modelled start time; every tile starts after the tiles it reads, so that order is a valid
-    // global order and the run-time waits cannot deadlock (see the kernel comment).
-    struct MT { int waiting; double ready; int assigned; double finish; };
-    std::vector<std::vector<MT>> mt(n_layers);
-    std::vector<std::vector<std::vector<std::pair<int, int>>>> wakes(n_layers);   // (layer, tm) -> dependents
-    for (int l = 0; l < n_layers; ++l) {
-      mt[l].assign(hl[l].tiles_m, MT{0, 0.0, 0, 0.0});
-      wakes[l].resize(hl[l].tiles_m);
-    }
-    for (int l = 0; l < n_layers; ++l) {
-      const HostLayer& h = hl[l];
-      for (int tm = 0; tm < h.tiles_m; ++tm) {
-        if (h.dep >= 0) {
-          int a, b;
-          dep_tiles(h, tm, &a, &b);
-          for (int t = a; t <= b; ++t) {
-            wakes[h.dep][t].push_back({l, tm});
-            ++mt[l][tm].waiting;
-          }
-        }
-        if (h.res >= 0) {
-          wakes[h.res][tm].push_back({l, tm});
-          ++mt[l][tm].waiting;
-        }
-      }
-    }
-    // min-heaps: pairs by free time; pending m tiles by ready time; available m tiles by (layer, tm)
-    typedef std::pair<double, int> DI;
-    std::priority_queue<DI, std::vector<DI>, std::greater<DI>> pairs_q;
-    for (int q = 0; q < npairs; ++q) pairs_q.push({0.0, q});
-    typedef std::pair<double, std::pair<int, int>> RT;
-    std::priority_queue<RT, std::vector<RT>, std::greater<RT>> pending;
-    typedef std::pair<int, int> LT;
-    std::priority_queue<LT, std::vector<LT>, std::greater<LT>> avail;
-    std::vector<std::vector<int>> next_tn(n_layers);
-    for (int l = 0; l < n_layers; ++l) {
-      next_tn[l].assign(hl[l].tiles_m, 0);
-      for (int tm = 0; tm < hl[l].tiles_m; ++tm)
-        if (mt[l][tm].waiting == 0) pending.push({0.0, {l, tm}});
-    }
-    long long left = tiles;
-    while (left > 0) {
-      DI pq = pairs_q.top();
-      pairs_q.pop();
-      double t = pq.first;
-      const int q = pq.second;
-      while (!pending.empty() && pending.top().first <= t) {
-        avail.push(pending.top().second);
-        pending.pop();
-      }
-      if (avail.empty()) {
-        if (pending.empty()) return fail(ME_ERR_ARG, "conv_chain: the layer dependencies form a cycle");
-        t = pending.top().first;    // the pair idles until the next tile becomes ready
-        while (!pending.empty() && pending.top().first <= t) {
-          avail.push(pending.top().second);
-          pending.pop();
-        }
-      }
-      const LT cur = avail.top();
-      const int l = cur.first, tm = cur.second;
-      const HostLayer& h = hl[l];
-      const int tn = next_tn[l][tm]++;
-      if (next_tn[l][tm] == h.tiles_n) avail.pop();
-      const double finish = t + h.num_kb * kKb + kTile;
-      work[static_cast<long long>(q) * stride + pair_n[q]++] = (l << kItemShift) | (tm * h.tiles_n + tn);
-      --left;
-      pairs_q.push({finish, q});
-      MT& m = mt[l][tm];
-      if (finish > m.finish) m.finish = finish;
-      if (++m.assigned == h.tiles_n) {
-        for (const auto& d : wakes[l][tm]) {
-          MT& w = mt[d.first][d.second];
-          if (m.finish + kHand > w.ready) w.ready = m.finish + kHand;
-          if (--w.waiting == 0) pending.push({w.ready, d});
         }
       }
     }
