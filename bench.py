@@ -71,9 +71,11 @@ def peaks():
 
 def measured_traffic():
     """DRAM bytes (read + write) of one step's conv launches, from the committed ncu capture
-    (profiles/round1/traffic.json; `ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum` over this script).
-    The capture is per step, like `achieved`; None if the profile is not in the tree."""
-    path = os.path.join(ROOT, "profiles", "round1", "traffic.json")
+    (profiles/round2/traffic.json, else round 1's; `ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum` over this
+    script).  The capture is per step, like `achieved`; None if the profile is not in the tree."""
+    path = os.path.join(ROOT, "profiles", "round2", "traffic.json")
+    if not os.path.exists(path):
+        path = os.path.join(ROOT, "profiles", "round1", "traffic.json")
     if not os.path.exists(path):
         return None
     with open(path) as fh:
