@@ -31,11 +31,12 @@ CFG = "yolov3"
 CONF_THRESH = 0.2     # test_fusion.py:143
 CPU_BATCH = 4         # bounded CPU sample (Darknet-53 on CPU is run at N=4)
 METRIC = "frames/sec at 416x416 batch32"
-# Synthetic head statistics (random-init heads give conf ~ 0.5 everywhere): head logits are kept narrow
-# (std ~ 0.13: boxes near their anchor sizes, like a trained detector's) and the objectness bias puts the 0.2 confidence
-# threshold about 2.6 standard deviations above the mean, so a few dozen of the 10 647 boxes per frame pass the filter and
-# the NMS has real work.  Wide logits (the round-1 recipe, gain 3) only amplify the fp16 error through exp() in the decode.
-WEIGHTS = dict(obj_bias=-1.6, head_gain=0.5)
+# Synthetic head statistics (random-init heads give conf ~ 0.5 everywhere): head logits of moderate width
+# (std ~ 0.3: boxes near their anchor sizes, like a trained detector's) and an objectness bias that lets ~75 of the 10 647
+# boxes per frame pass the 0.2 confidence filter, of which the NMS keeps ~18.  Wide logits (the round-1 recipe, gain 3) only
+# amplify the fp16 error through exp() in the decode; narrower ones (gain 0.5) pile hundreds of boxes within 1e-3 of one
+# confidence value, so that any threshold lands on a cliff and the kept set depends on differences below the tolerance.
+WEIGHTS = dict(obj_bias=-2.0, head_gain=1.0)
 
 
 _JSON_FD = None
@@ -239,7 +240,31 @@ def check_parity(host_batch, rec, frames):
         det = rec.host_det.numpy()
         cnt = rec.host_cnt.numpy()
         rows_ref = rows_gpu = matched = exact_order = 0
+        near_threshold = near_tie = unexplained = 0
         box_err = score_err = 0.0
+        tol = 1e-3
+
+        def iou(a, b):
+            ix = max(0.0, min(a[2], b[2]) - max(a[0], b[0]))
+            iy = max(0.0, min(a[3], b[3]) - max(a[1], b[1]))
+            inter = ix * iy
+            u = (a[2] - a[0]) * (a[3] - a[1]) + (b[2] - b[0]) * (b[3] - b[1]) - inter
+            return inter / u if u > 0 else 0.0
+
+        def explain(row, other, other_only):
+            """A row only one side reports is within tolerance if a score error <= tol explains it: its confidence is
+            within tol of the threshold, or it overlaps (IoU > nms threshold - tol) a same-class row the other side kept
+            whose score is within tol of its own (the NMS order of the two flipped)."""
+            if abs(row[4] - CONF_THRESH) <= tol:
+                return "threshold"
+            for o in other:
+                if o[6] == row[6] and abs(o[4] * o[5] - row[4] * row[5]) <= tol and iou(row, o) > 0.5 - tol:
+                    return "tie"
+            for o in other_only:     # second order: the row that suppressed it on the other side is itself such a flip
+                if o[6] == row[6] and iou(row, o) > 0.5 - tol:
+                    return "tie"
+            return None
+
         for f in range(frames):
             r = ref[f] if ref[f] is not None else np.zeros((0, det.shape[2]), np.float32)
             r = np.asarray(r)
@@ -247,30 +272,37 @@ def check_parity(host_batch, rec, frames):
             rows_ref += len(r)
             rows_gpu += len(g)
             used = np.zeros(len(r), bool)
+            got_used = np.zeros(len(g), bool)
             for i, row in enumerate(g):
                 best, bj = 0.0, -1
                 for j, rr in enumerate(r):
                     if used[j] or rr[6] != row[6]:
                         continue
-                    ix = max(0.0, min(row[2], rr[2]) - max(row[0], rr[0]))
-                    iy = max(0.0, min(row[3], rr[3]) - max(row[1], rr[1]))
-                    inter = ix * iy
-                    u = (row[2] - row[0]) * (row[3] - row[1]) + (rr[2] - rr[0]) * (rr[3] - rr[1]) - inter
-                    iou = inter / u if u > 0 else 0.0
-                    if iou > best:
-                        best, bj = iou, j
+                    v = iou(row, rr)
+                    if v > best:
+                        best, bj = v, j
                 if bj >= 0 and best >= 0.9:
-                    used[bj] = True
+                    used[bj] = got_used[i] = True
                     matched += 1
                     exact_order += int(bj == i)
                     rr = r[bj]
                     scale = max(abs(rr[2] - rr[0]), abs(rr[3] - rr[1]), 1.0)
                     box_err = max(box_err, float(np.abs(row[:4] - rr[:4]).max() / scale))
                     score_err = max(score_err, float(np.abs(row[4:6] - rr[4:6]).max()))
+            for rows, flags, other, oflags in ((g, got_used, r, used), (r, used, g, got_used)):
+                for row in rows[~flags]:
+                    why = explain(row, other, other[~oflags])
+                    near_threshold += int(why == "threshold")
+                    near_tie += int(why == "tie")
+                    unexplained += int(why is None)
         return dict(checked=True, frames=frames, rows_oracle=rows_ref, rows_gpu=rows_gpu, rows_matched=matched,
-                    rows_same_rank=exact_order, max_box_err_rel=box_err, max_score_err_abs=score_err,
-                    tolerance=1e-3, within_tolerance=bool(matched == rows_ref == rows_gpu and box_err <= 1e-3 and score_err <= 1e-3),
-                    how="oracle (CPU fp32 restatement of the reference) on the same images / weights; rows matched by class and IoU >= 0.9")
+                    rows_same_rank=exact_order, rows_only_one_side=dict(conf_within_tol_of_threshold=near_threshold,
+                                                                        nms_order_flip_within_tol=near_tie, unexplained=unexplained),
+                    max_box_err_rel=box_err, max_score_err_abs=score_err, tolerance=tol,
+                    within_tolerance=bool(unexplained == 0 and matched > 0 and box_err <= tol and score_err <= tol),
+                    how="oracle (CPU fp32 restatement of the reference) on the same images / weights; rows matched by class and "
+                        "IoU >= 0.9; a row only one side reports must be explained by a score difference <= tolerance (at the "
+                        "confidence threshold, or an NMS order flip between two overlapping rows)")
     except Exception as e:  # noqa: BLE001
         return dict(checked=False, error=str(e)[:200])
 
@@ -336,7 +368,7 @@ def run_fusion(args):
     import torch.distributed as dist
     from millieye_b200 import configs, radar
     from millieye_b200.engine import capture_graph
-    from millieye_b200.my_models import Network, define_yolo
+    from millieye_b200.my_models import FusionPipeline, Network, define_yolo
     from oracle import darknet as odark
     from oracle import synth
     from oracle.parse_config import parse_model_config
@@ -347,20 +379,36 @@ def run_fusion(args):
     inp = _fusion_inputs(BATCH, device, 100 + rank)
     last = {}
 
-    def step_dev():
+    pipe = FusionPipeline(model)
+
+    def step_call():     # the reference scripts' own call pattern: one blocking forward per batch
         maps = radar.radar_maps(inp["pts"], inp["cnt"], inp["cfg"])
         last["out"] = model(inp["imgs_dev"], maps, inp["boxes"].clone(), 0)
 
-    def step_e2e():
+    def step_dev():      # stream of batches, frames resident in HBM, rows stay on the device
         maps = radar.radar_maps(inp["pts"], inp["cnt"], inp["cfg"])
-        last["host"] = model(inp["imgs"], maps, inp["boxes"].clone(), 0).cpu()
+        last["rec_dev"] = pipe.submit(inp["imgs_dev"], maps, inp["boxes"].clone(), 0, readback=False)
+
+    def step_e2e():      # stream of batches, uint8 frames from pinned host memory, every batch's rows read on the host
+        maps = radar.radar_maps(inp["pts"], inp["cnt"], inp["cfg"])
+        rec = pipe.submit(inp["imgs"], maps, inp["boxes"].clone(), 0, readback=True)
+        prev = last.get("rec")
+        if prev is not None:
+            last["host"] = prev.wait()       # consume the previous batch while this one runs
+        last["rec"] = rec
 
     sampler = ClockSampler(local) if rank == 0 else None
     if sampler:
         sampler.start()
     ms_dev = _timed_steps(step_dev, args.steps, args.warmup, world, device)
     clocks = sampler.stop() if sampler else None
+    dev_rows = last["rec_dev"].wait().cpu()
     ms_e2e = _timed_steps(step_e2e, args.steps, args.warmup, world, device)
+    last["host"] = last["rec"].wait().clone()
+    d2h_bytes = int(last["rec"].host_flat.numel() * 4)
+    ms_call = _timed_steps(step_call, args.steps, args.warmup, world, device)
+    # the pipeline's rows are the blocking forward's rows (same inputs every step)
+    pipeline_equals_forward = bool(torch.equal(dev_rows, last["out"].cpu()) and torch.equal(last["host"], last["out"].cpu()))
     # detector conv stack alone (HBM-bound on tiny-12): graph of the conv launches
     plan = model.base_detector.plan_for(BATCH, SIZE, device)
     conv_ops = {i for i, k in enumerate(plan.op_kinds) if k in ("conv", "maxpool", "upsample")}
@@ -385,10 +433,16 @@ def run_fusion(args):
                                    f"score-map CNNs + PS-RoIAlign / RoIAlign + refinement / ensemble heads, batch {BATCH} per GPU, "
                                    f"{SIZE}x{SIZE}, 64 radar points per frame -> heat-maps on the device",
                           conf_thresh=CONF_THRESH, rows_last_step=int(last["out"].shape[0]),
+                          api="FusionPipeline.submit per batch (proposal / head kernels of batch i on a second stream under the "
+                              "backbone of batch i+1); blocking_forward_ms_per_step is one Network.forward call per batch",
+                          blocking_forward_ms_per_step=ms_call / args.steps,
+                          blocking_forward_fps=world * BATCH * args.steps / ms_call * 1e3,
+                          pipeline_equals_forward=pipeline_equals_forward,
                           l2="~1 GB of activations per step exceed the 126 MB L2; no explicit flush"),
               clocks=clocks,
               e2e=dict(value=fps_e2e, unit="frames/s", h2d_bytes_per_step=BATCH * 3 * SIZE * SIZE,
-                       d2h_bytes_per_step=int(last["host"].numel() * 4), ms_per_step=ms_e2e / args.steps,
+                       d2h_bytes_per_step=d2h_bytes, ms_per_step=ms_e2e / args.steps,
+                       output="rows + count of every batch in one copy to pinned host memory (the record's buffer)",
                        input="uint8 (N,3,S,S) frames in pinned host memory, ToTensor (x / 255) on the device"),
               gpu_launches=int((len(plan.ops) + len(plan.post_ops) + 14) * args.steps),
               roofline=dict(bound="hbm", achieved=achieved, peak=pk["hbm_gbs"], unit="GB/s", frac=achieved / pk["hbm_gbs"],
@@ -697,7 +751,13 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-sustained", action="store_true", help="skip the >= 2 s conv-only replay")
     ap.add_argument("--no-parity", action="store_true", help="skip the oracle check of the timed detections")
+    ap.add_argument("--obj-bias", type=float, default=None, help="synthetic head statistics: objectness bias (experiments)")
+    ap.add_argument("--head-gain", type=float, default=None, help="synthetic head statistics: head weight gain (experiments)")
     args = ap.parse_args()
+    if args.obj_bias is not None:
+        WEIGHTS["obj_bias"] = args.obj_bias
+    if args.head_gain is not None:
+        WEIGHTS["head_gain"] = args.head_gain
     quiet_stdout()
     if args.impl == "reference":
         run_reference(args)

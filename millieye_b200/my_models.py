@@ -166,8 +166,10 @@ class _FusionPlan:
         self.regress = torch.zeros((cap, 4), **f32)
         self.refine = torch.zeros((cap, 2), **f32)
         self.mask = torch.zeros((cap,), **f32)
-        self.out = torch.zeros((cap, 8), **f32)
-        self.out_count = torch.zeros((1,), **i32)
+        # rows and their count in ONE buffer: a host that wants both reads them with a single copy (FusionPipeline)
+        self.out_flat = torch.zeros((cap * 8 + 4,), **f32)
+        self.out = self.out_flat[:cap * 8].view(cap, 8)
+        self.out_count = self.out_flat[cap * 8:cap * 8 + 1].view(torch.int32)
         ws_bytes = 1
         while ws_bytes < cap:
             ws_bytes <<= 1
@@ -262,8 +264,8 @@ class Network(nn.Module):
         self._invalidate()
         self.base_detector.refresh_weights()
 
-    def _plan(self, base_plan, num_radar):
-        key = (base_plan.n, base_plan.size, base_plan.device.index, id(base_plan))
+    def _plan(self, base_plan, num_radar, slot=0):
+        key = (base_plan.n, base_plan.size, base_plan.device.index, id(base_plan), slot)
         plan = self._plans.get(key)
         need = max(num_radar, 1)
         if plan is None or plan.radar_cap < need:
@@ -435,3 +437,94 @@ class _Stage3Loss(torch.autograd.Function):
     def backward(ctx, grad_out):
         grads = ctx.model.backward_into(None)
         return (None, None) + tuple(grads[k] * grad_out for k in ctx.names)
+
+
+class FusionPipeline:
+    """Network.forward (reference my_models.py:433-640, inference branch) for STREAMS of batches: run_mp.py:300-330 and
+    test_fusion.py:70-80 call the model once per frame / batch and read the rows back before the next call, so the
+    device idles during the proposal + head kernels' short launches and the host read.  submit() enqueues one batch
+    and returns its record at once; record.wait() gives the batch's (K, 8) rows.
+
+    Stream layout per batch i:
+      main stream  backbone(i) (graph replay) -> score maps(i) (they read the backbone's single feature-map buffer, so
+                   they stay in front of backbone(i+1))
+      side stream  YOLO decode -> filter + NMS -> proposals -> RoI gathers -> refinement / ensemble heads -> finalize
+                   -> ONE device->host copy of rows + count; all of it overlaps backbone(i+1) on the main stream.
+    Each in-flight batch owns one fusion plan (score maps, proposal and head buffers) out of a ring of `depth`;
+    a plan is reused only after its previous record completed.  The rows equal Network.forward's bit for bit
+    (tests/test_gpu_models.py::test_fusion_pipeline_equals_forward)."""
+
+    class Record:
+        def __init__(self, plan):
+            self.plan = plan
+            self.host_flat = torch.empty_like(plan.out_flat, device="cpu").pin_memory()
+            self.done = torch.cuda.Event()
+            self.pending = False
+            self.readback = False
+
+        def wait(self):
+            """Blocks until the batch is complete; returns its rows — a view of the record's pinned host buffer when
+            the batch was submitted with readback=True (valid until the record is reused, `depth` submits later),
+            else a device tensor."""
+            self.done.synchronize()
+            self.pending = False
+            cap = self.plan.cap
+            if self.readback:
+                k = int(self.host_flat[cap * 8:cap * 8 + 1].view(torch.int32)[0])
+                return self.host_flat[:cap * 8].view(cap, 8)[:k]
+            return self.plan.out[:int(self.plan.out_count.item())]
+
+    def __init__(self, model, depth=3):
+        self.model = model
+        self.depth = max(2, int(depth))
+        self._records = {}     # id(fusion plan) -> Record
+        self._next = 0
+        self._side = None
+        self.launches = 0      # fusion-tail kernels launched by the last submit (the backbone's are in its plan)
+
+    def submit(self, images, maps, radar_boxes_location, model_mode=0, readback=True):
+        m = self.model
+        if model_mode == 1:
+            raise MeError("model_mode 1 is the bare detector + NMS: use millieye_b200.models.DetectPipeline")
+        if any(x.training for x in (m.img_cnn_layers, m.radar_cnn_layers, m.refinement_head)):
+            raise MeError("FusionPipeline is the inference path: call model.eval() first")
+        base = m.base_detector
+        plan_b = base.forward_device(images, decode=False)
+        dev = plan_b.device
+        n_radar = int(radar_boxes_location.shape[0]) if radar_boxes_location is not None else 0
+        slot = self._next
+        self._next = (slot + 1) % self.depth
+        plan = m._plan(plan_b, n_radar, slot=1 + slot)   # slot 0 belongs to the blocking forward()
+        with torch.cuda.device(dev):
+            if self._side is None:
+                self._side = torch.cuda.Stream(device=dev)
+            rec = self._records.get(id(plan))
+            if rec is None or rec.plan is not plan:
+                live = {id(p) for p in m._plans.values()}
+                for key in [k for k in self._records if k not in live]:
+                    del self._records[key]
+                rec = self._records[id(plan)] = FusionPipeline.Record(plan)
+            if rec.pending:
+                rec.done.synchronize()      # the plan's previous batch still runs: wait before its buffers are reused
+            rec.pending, rec.readback = True, bool(readback)
+            plan.launches = 0
+            if model_mode == 2:
+                m.refine_threshold_img = 1   # persistent, like the reference (:480)
+            if n_radar > 0:
+                radar_boxes_location[:, 1:] *= images.shape[-1]          # reference side effect (:491)
+                plan.radar_dev[:n_radar].copy_(radar_boxes_location, non_blocking=True)
+            plan.maps_in.copy_(maps, non_blocking=True)
+            plan.score_maps()
+            main = torch.cuda.current_stream()
+            self._side.wait_stream(main)
+            with torch.cuda.stream(self._side):
+                plan_b.run_decode(base.use_cuda_graph)
+                plan.proposals(m.conf_thresh, m.class_idx, n_radar)
+                plan.heads(float(m.refine_threshold_img), float(m.refine_threshold_radar), model_mode != 2)
+                if readback:
+                    rec.host_flat.copy_(plan.out_flat, non_blocking=True)
+                rec.done.record()
+            plan_b.hold_output(rec.done)
+            m.refinement_head.count += 1
+            self.launches = plan.launches
+        return rec

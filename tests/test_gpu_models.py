@@ -224,6 +224,47 @@ def test_fusion_batch32_radar_points_vs_oracle():
     assert matched >= 0.97 * len(ref)
 
 
+def test_fusion_pipeline_equals_forward():
+    """FusionPipeline.submit (tail kernels of batch i on a second stream under the backbone of batch i+1) returns the rows
+    of the blocking Network.forward bit for bit, for a stream of different batches, uint8 host frames included, with
+    records consumed late (two batches in flight) and an empty batch (no radar boxes, threshold nothing passes) in between."""
+    from millieye_b200 import radar
+    from millieye_b200.my_models import FusionPipeline
+    n, size, thr = 8, 416, 0.2
+    model = Network(define_yolo(configs.cfg_path("yolov3-tiny-12")), conf_thresh=thr).eval()
+    model.load_state_dict(synth.fill_state_dict(model.state_dict(), seed=31, obj_bias=-2.0, head_gain=0.4))
+    model.to(DEV)
+    cfg = radar.make_cfg(out_size=size // 16)
+    batches = []
+    for k in range(6):
+        rng = np.random.RandomState(50 + k)
+        pts = np.stack([rng.uniform(-3, 3, (n, 64)), rng.uniform(1, 10, (n, 64)), rng.uniform(-1.5, 1.5, (n, 64)),
+                        rng.uniform(-3, 3, (n, 64))], -1).astype(np.float32)
+        maps = radar.radar_maps(torch.from_numpy(pts).to(DEV), torch.full((n,), 64, dtype=torch.int32, device=DEV), cfg)
+        u8 = torch.randint(0, 256, (n, 3, size, size), generator=torch.Generator().manual_seed(60 + k), dtype=torch.uint8)
+        imgs = u8.pin_memory() if k % 2 else (u8.float() / 255.0).to(DEV)
+        rb = synth.synth_radar_boxes(n, seed=70 + k) if k != 3 else torch.zeros((0, 5))
+        batches.append((imgs, maps, rb))
+    want = [model(imgs, maps, rb.clone().to(DEV), 0).cpu() for imgs, maps, rb in batches]
+    assert sum(len(w) for w in want) > 50
+    pipe = FusionPipeline(model, depth=3)
+    got, recs = [], []
+    for k, (imgs, maps, rb) in enumerate(batches):
+        recs.append(pipe.submit(imgs, maps, rb.clone().to(DEV), 0, readback=(k != 4)))
+        if len(recs) == 3:                      # two further batches are in flight when a record is read
+            got.append(recs.pop(0).wait().cpu().clone())
+    got += [r.wait().cpu().clone() for r in recs]
+    for k, (a, b) in enumerate(zip(got, want)):
+        assert a.shape == b.shape and torch.equal(a, b), f"batch {k}"
+    # mode 2 (radar only) keeps the reference's persistent side effect, mode 1 is refused
+    imgs, maps, rb = batches[0]
+    w2 = model(imgs, maps, rb.clone().to(DEV), 2).cpu()
+    g2 = pipe.submit(imgs, maps, rb.clone().to(DEV), 2).wait()
+    assert torch.equal(g2, w2) and model.refine_threshold_img == 1
+    with pytest.raises(MeError):
+        pipe.submit(imgs, maps, rb.clone().to(DEV), 1)
+
+
 def test_fusion_empty_and_errors():
     model = Network(define_yolo(configs.cfg_path("yolov3-tiny-12")), conf_thresh=0.999999).eval().to(DEV)
     imgs = torch.rand(2, 3, 96, 96, device=DEV)
