@@ -145,6 +145,13 @@ int me_conv_first(const float* x_nchw, const float* w_folded, const float* bias,
 int me_conv_first_tc(const float* x_nchw, const float* w_folded, const float* bias, void* wk_scratch,
                      void* y_nhwc, int n, int h, int w, int cin, int cout, int out_pitch, int act,
                      me_stream_t stream);
+/* me_conv_first_tc followed by MaxPool2d(2, 2) (blocks 0-1 of yolov3-tiny*.cfg, models.py:22-51) in one kernel: the
+ * pool runs in the epilogue, y_nhwc is the pooled (n, h/2, w/2, out_pitch) tensor and the full-resolution activation is
+ * never written.  Bit-identical to me_conv_first_tc + me_maxpool2.  Needs w % 32 == 0, h % 4 == 0, a 16-byte aligned
+ * image and cout in {16, 32}; anything else is ME_ERR_UNSUPPORTED / ME_ERR_INVALID (run the two calls instead). */
+int me_conv_first_tc_pool(const float* x_nchw, const float* w_folded, const float* bias, void* wk_scratch,
+                          void* y_nhwc, int n, int h, int w, int cin, int cout, int out_pitch, int act,
+                          me_stream_t stream);
 
 /* ---- glue layers (A3) -------------------------------------------------------------- */
 /* MaxPool2d(2, stride) on NHWC fp16; stride 1 uses the right/bottom zero pad of

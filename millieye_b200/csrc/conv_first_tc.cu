@@ -67,7 +67,12 @@ __device__ __forceinline__ void store_row(uint8_t* tile, int row, const float (&
   }
 }
 
-template <int COUT, bool VEC>
+// POOL (VEC only; w % 32 == 0, h % 4 == 0): the 2x2 / stride-2 max-pool that follows the layer in the tiny cfgs
+// (yolov3-tiny-12.cfg blocks 0-1) runs in the epilogue.  A tile is a 4-row x 32-column block of one image; its 128 MMA
+// rows are ordered so that each epilogue warp holds 2 rows x 16 columns (lane = 16 * dy + dx): the 2x2 window is a
+// shfl_xor 1 / shfl_xor 16 away, and the 8 pooled pixels of a warp are one contiguous span of the pooled NHWC output.
+// max commutes with the fp16 rounding, so the result equals conv -> fp16 -> maxpool bit for bit.
+template <int COUT, bool VEC, bool POOL>
 __global__ void __launch_bounds__(FCfg<VEC>::THREADS, 1)
 conv_first_tc_kernel(const float* __restrict__ x, const __half* __restrict__ wk, const float* __restrict__ bias,
                      __half* __restrict__ y, int n, int h, int w, int cin, int out_pitch, int act, int tiles, int dbg) {
@@ -122,7 +127,17 @@ conv_first_tc_kernel(const float* __restrict__ x, const __half* __restrict__ wk,
     for (int tile = blockIdx.x + stage * gridDim.x; tile < tiles; tile += F::STAGES * gridDim.x) {
       uint8_t* a_tile = s_a + stage * kABytes;
       if constexpr (VEC) {
-        const int pix = tile * kTileM + lane * 4;  // 4 pixels of one image row (w % 4 == 0)
+        int pix, row0;     // 4 consecutive pixels of one image row (w % 4 == 0) and their first MMA row
+        if constexpr (POOL) {
+          const int cbs = w >> 5, rgs = h >> 2;
+          const int cb = tile % cbs, t2 = tile / cbs;
+          const int ry = lane >> 3, cx = (lane & 7) * 4;
+          pix = ((t2 / rgs) * h + (t2 % rgs) * 4 + ry) * w + cb * 32 + cx;
+          row0 = 32 * (2 * (ry >> 1) + (cx >> 4)) + 16 * (ry & 1) + (cx & 15);
+        } else {
+          pix = tile * kTileM + lane * 4;
+          row0 = lane * 4;
+        }
         float v[4][27];
 #pragma unroll
         for (int j = 0; j < 4; ++j)
@@ -156,7 +171,7 @@ conv_first_tc_kernel(const float* __restrict__ x, const __half* __restrict__ wk,
         mbar_wait_spin(&empty_bar[stage], phase ^ 1);
         if (!(dbg & 4)) {  // bit 4: no tile build either
 #pragma unroll
-          for (int j = 0; j < 4; ++j) store_row(a_tile, lane * 4 + j, v[j]);
+          for (int j = 0; j < 4; ++j) store_row(a_tile, row0 + j, v[j]);
         }
       } else {
         const int row = threadIdx.x & 127;
@@ -227,7 +242,15 @@ conv_first_tc_kernel(const float* __restrict__ x, const __half* __restrict__ wk,
       mbar_wait_spin(&tmem_full[acc], (it / F::ACCS) & 1);
       ptx::tc_fence_after();
       const uint32_t taddr = tmem_base + acc * COUT + (static_cast<uint32_t>(q * 32) << 16);
-      const int pix = tile * kTileM + row;
+      int pix = tile * kTileM + row;
+      bool writer = pix < total_px;
+      if constexpr (POOL) {
+        const int cbs = w >> 5, rgs = h >> 2;
+        const int cb = tile % cbs, t2 = tile / cbs;
+        const int prow = (t2 % rgs) * 2 + (q >> 1), pcol = cb * 16 + 8 * (q & 1) + ((lane & 15) >> 1);
+        pix = ((t2 / rgs) * (h >> 1) + prow) * (w >> 1) + pcol;     // pooled pixel of this lane's 2x2 window
+        writer = (lane & 17) == 0;
+      }
       __half* dst = y + 1LL * pix * out_pitch;
       // 32-byte sectors are written whole: one 256-bit store per 16 channels when the row pitch allows it
       const bool wide = (out_pitch & 15) == 0 && (reinterpret_cast<uintptr_t>(y) & 31) == 0;
@@ -261,7 +284,19 @@ conv_first_tc_kernel(const float* __restrict__ x, const __half* __restrict__ wk,
           oh[2 * e4] = __floats2half2_rn(v0, v1);
           oh[2 * e4 + 1] = __floats2half2_rn(v2, v3);
         }
-        if (pix < total_px && !(dbg & 1)) {  // bit 1: attribution run without the output stores
+        if constexpr (POOL) {
+#pragma unroll
+          for (int e = 0; e < 8; ++e) {
+            __half2 m = oh[e];
+            uint32_t u = *reinterpret_cast<uint32_t*>(&m);
+            uint32_t o1 = __shfl_xor_sync(0xffffffffu, u, 1);
+            m = __hmax2(m, *reinterpret_cast<__half2*>(&o1));
+            u = *reinterpret_cast<uint32_t*>(&m);
+            uint32_t o2 = __shfl_xor_sync(0xffffffffu, u, 16);
+            oh[e] = __hmax2(m, *reinterpret_cast<__half2*>(&o2));
+          }
+        }
+        if (writer && !(dbg & 1)) {  // bit 1: attribution run without the output stores
           if (wide) {
             ptx::st_global_256(dst + c, o[0], o[1]);
           } else {
@@ -288,11 +323,11 @@ __global__ void pack_first_tc_kernel(const float* __restrict__ w_folded, int cou
   wk[i] = __float2half_rn(k < per_out ? w_folded[o * per_out + k] : 0.f);
 }
 
-template <int COUT, bool VEC>
+template <int COUT, bool VEC, bool POOL = false>
 int launch_first(const float* x, const __half* wk, const float* bias, __half* y, int n, int h, int w, int cin,
                  int out_pitch, int act, int tiles, int grid, cudaStream_t stream) {
   using F = FCfg<VEC>;
-  auto kern = conv_first_tc_kernel<COUT, VEC>;
+  auto kern = conv_first_tc_kernel<COUT, VEC, POOL>;
   static bool attr_seen[64] = {false};   // per instantiation and per device
   if (first_use_on_device(attr_seen))
     ME_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, F::SMEM));
@@ -309,13 +344,11 @@ int launch_first(const float* x, const __half* wk, const float* bias, __half* y,
 }  // namespace
 }  // namespace me
 
-extern "C" {
+namespace me {
+namespace {
 
-// wk: fp16 [cout][32] scratch owned by the caller (filled here from the folded fp32 weights).
-int me_conv_first_tc(const float* x_nchw, const float* w_folded, const float* bias, void* wk_scratch, void* y_nhwc,
-                     int n, int h, int w, int cin, int cout, int out_pitch, int act, me_stream_t stream_) {
-  using namespace me;
-  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+int conv_first_tc_impl(const float* x_nchw, const float* w_folded, const float* bias, void* wk_scratch, void* y_nhwc,
+                       int n, int h, int w, int cin, int cout, int out_pitch, int act, bool pool, cudaStream_t stream) {
   ME_REQUIRE(x_nchw && w_folded && bias && wk_scratch && y_nhwc, "conv_first_tc: null argument");
   ME_REQUIRE(cin >= 1 && cin <= 3, "conv_first_tc: cin %d must be 1..3", cin);
   ME_REQUIRE(out_pitch >= cout && out_pitch % 8 == 0, "conv_first_tc: bad out_pitch %d", out_pitch);
@@ -330,6 +363,15 @@ int me_conv_first_tc(const float* x_nchw, const float* w_folded, const float* bi
   if (grid > tiles) grid = tiles;
   __half* y = static_cast<__half*>(y_nhwc);
   const bool vec = (w % 4 == 0) && ((reinterpret_cast<uintptr_t>(x_nchw) & 15) == 0);
+  if (pool) {
+    ME_REQUIRE(vec && w % 32 == 0 && h % 4 == 0, "conv_first_tc_pool: needs a 16-byte aligned image with w %% 32 == 0 and "
+               "h %% 4 == 0 (got %d x %d); run me_conv_first_tc + me_maxpool instead", h, w);
+    switch (cout) {   // tiles are exact 4 x 32 blocks: n * (h / 4) * (w / 32) == total / 128
+      case 16: return launch_first<16, true, true>(x_nchw, wk, bias, y, n, h, w, cin, out_pitch, act, tiles, grid, stream);
+      case 32: return launch_first<32, true, true>(x_nchw, wk, bias, y, n, h, w, cin, out_pitch, act, tiles, grid, stream);
+      default: return fail(ME_ERR_UNSUPPORTED, "conv_first_tc_pool: cout %d unsupported (16 or 32)", cout);
+    }
+  }
 #define ME_FIRST(C)                                                                                              \
   return vec ? launch_first<C, true>(x_nchw, wk, bias, y, n, h, w, cin, out_pitch, act, tiles, grid, stream)     \
              : launch_first<C, false>(x_nchw, wk, bias, y, n, h, w, cin, out_pitch, act, tiles, grid, stream)
@@ -340,6 +382,26 @@ int me_conv_first_tc(const float* x_nchw, const float* w_folded, const float* bi
     default: return fail(ME_ERR_UNSUPPORTED, "conv_first_tc: cout %d unsupported (16, 32 or 64)", cout);
   }
 #undef ME_FIRST
+}
+
+}  // namespace
+}  // namespace me
+
+extern "C" {
+
+// wk: fp16 [cout][32] scratch owned by the caller (filled here from the folded fp32 weights).
+int me_conv_first_tc(const float* x_nchw, const float* w_folded, const float* bias, void* wk_scratch, void* y_nhwc,
+                     int n, int h, int w, int cin, int cout, int out_pitch, int act, me_stream_t stream_) {
+  return me::conv_first_tc_impl(x_nchw, w_folded, bias, wk_scratch, y_nhwc, n, h, w, cin, cout, out_pitch, act, false,
+                                static_cast<cudaStream_t>(stream_));
+}
+
+// The same layer with the 2x2 / stride-2 max-pool that follows it applied in the epilogue: y is the POOLED
+// (n, h/2, w/2, out_pitch) NHWC tensor.
+int me_conv_first_tc_pool(const float* x_nchw, const float* w_folded, const float* bias, void* wk_scratch, void* y_nhwc,
+                          int n, int h, int w, int cin, int cout, int out_pitch, int act, me_stream_t stream_) {
+  return me::conv_first_tc_impl(x_nchw, w_folded, bias, wk_scratch, y_nhwc, n, h, w, cin, cout, out_pitch, act, true,
+                                static_cast<cudaStream_t>(stream_));
 }
 
 }  // extern "C"

@@ -224,6 +224,19 @@ class DarknetPlan:
                     nxt["_decoded_by_conv"] = True
                     views[i] = None
                     continue
+                pool_next = (i == 0 and nxt is not None and nxt["type"] == "maxpool" and nxt["size"] == 2 and nxt["stride"] == 2
+                             and fuse_res is None and readers[0] == [] and 0 not in target and 1 not in target
+                             and b["size"] == 3 and b["stride"] == 1 and b["cin"] <= 3 and cout in (16, 32)
+                             and s_out % 32 == 0 and os.environ.get("ME_FUSE_POOL", "1") != "0")
+                if pool_next:
+                    # blocks 0-1 of the tiny cfgs: the 2x2 max-pool runs in the first conv's epilogue, the full-resolution
+                    # tensor (the largest of the network) is never written
+                    pv = View(self._new(s_out // 2, s_out // 2, ops.round_up(cout, 8)), 0, ops.round_up(cout, 8),
+                              s_out // 2, s_out // 2, real_c=cout)
+                    self._add_conv(i, b, src, pv, None, views, False, pooled=True)
+                    views[i] = None
+                    self._pooled_first = pv
+                    continue
                 if out_idx in target:
                     buf, off = target[out_idx]
                     ov = View(buf, off, cout, s_out, s_out)
@@ -243,6 +256,9 @@ class DarknetPlan:
                     raise MeError("shortcut without a preceding conv; unsupported cfg")
                 views[i] = views[i - 1]
             elif t == "maxpool":
+                if i == 1 and getattr(self, "_pooled_first", None) is not None:
+                    views[i] = self._pooled_first      # already produced by the first conv's epilogue
+                    continue
                 if b["size"] != 2:
                     raise MeError("only 2x2 max-pool is supported")
                 if i in target:
@@ -419,7 +435,7 @@ class DarknetPlan:
         self._keep = getattr(self, "_keep", []) + [packed]
         return packed
 
-    def _add_conv(self, i, b, src, ov, fuse_res, views, is_head):
+    def _add_conv(self, i, b, src, ov, fuse_res, views, is_head, pooled=False):
         n = self.n
         t = self._tensors
         w = t[f"module_list.{i}.conv_{i}.weight"]
@@ -431,8 +447,8 @@ class DarknetPlan:
                 raise MeError("first layer must be a 3x3/stride-1 conv over <= 4 input channels")
             first = ops.pack_first_conv(w, bias, bn)
             self._keep = getattr(self, "_keep", []) + [first]
-            self._add(lambda b0, nb, f=first, o=ov, a=act: ops.conv_first(self.x_in[b0:b0 + nb], f, o.at(b0), o.pitch, a),
-                      "conv", i)
+            self._add(lambda b0, nb, f=first, o=ov, a=act, pl=pooled: ops.conv_first(self.x_in[b0:b0 + nb], f, o.at(b0), o.pitch, a,
+                                                                                      pool=pl), "conv", i)
             return
         packed = self._pack(i, b)
         res_v = views[fuse_res] if fuse_res is not None else None

@@ -176,11 +176,17 @@ def pack_first_conv(weight, conv_bias=None, bn=None):
     return FirstConv(wf, bias, cin, cout)
 
 
-def conv_first(x_nchw, first, out, out_pitch, act=ME_ACT_LEAKY, tensor_cores=True):
+def conv_first(x_nchw, first, out, out_pitch, act=ME_ACT_LEAKY, tensor_cores=True, pool=False):
+    """First 3x3 conv from the NCHW fp32 image; pool=True also applies the 2x2 / stride-2 max-pool that follows it in the
+    tiny cfgs (out is then the pooled (n, h/2, w/2, out_pitch) tensor)."""
     _need_cuda(x_nchw, out)
     assert x_nchw.dtype == torch.float32 and x_nchw.is_contiguous()
     n, c, h, w = x_nchw.shape
     assert c == first.cin
+    if pool:
+        check(_lib.lib().me_conv_first_tc_pool(ptr(x_nchw), ptr(first.w), ptr(first.bias), ptr(first.wk), ptr(out), n, h, w,
+                                               c, first.cout, out_pitch, act, stream_ptr()), "me_conv_first_tc_pool")
+        return out
     if tensor_cores and c <= 3 and first.cout in (16, 32, 64):
         check(_lib.lib().me_conv_first_tc(ptr(x_nchw), ptr(first.w), ptr(first.bias), ptr(first.wk), ptr(out), n, h, w,
                                           c, first.cout, out_pitch, act, stream_ptr()), "me_conv_first_tc")

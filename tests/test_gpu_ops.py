@@ -4,6 +4,7 @@ import os
 
 import numpy as np
 import pytest
+from millieye_b200._lib import MeError
 import torch
 import torch.nn.functional as F
 
@@ -146,6 +147,29 @@ def test_conv_first(cout, act, n, h, w, tensor_cores):
     # SIMT path: fp32 math, fp16 output rounding; tensor-core path also rounds inputs/weights to fp16
     tol = (4e-3 if tensor_cores else 2e-3) * max(1.0, float(ref.abs().max()))
     assert float((got - ref).abs().max()) <= tol
+
+
+@pytest.mark.parametrize("cout,n,h,w", [(16, 2, 36, 96), (32, 3, 64, 32), (16, 8, 416, 416)])
+def test_conv_first_pool_equals_two_calls(cout, n, h, w):
+    """me_conv_first_tc_pool (2x2 / stride-2 max-pool in the first conv's epilogue) == me_conv_first_tc + me_maxpool2,
+    bit for bit; shapes the tile mapping does not cover are refused, not approximated."""
+    torch.manual_seed(5)
+    x = torch.rand(n, 3, h, w).to(DEV)
+    wt = torch.randn(cout, 3, 3, 3) * 0.3
+    bn = (torch.rand(cout) + 0.5, torch.randn(cout) * 0.1, torch.randn(cout) * 0.1, torch.rand(cout) + 0.5, 1e-5)
+    first = ops.pack_first_conv(wt.to(DEV), None, tuple(t.to(DEV) if torch.is_tensor(t) else t for t in bn))
+    full = torch.zeros(n, h, w, cout, dtype=torch.float16, device=DEV)
+    ops.conv_first(x, first, full, cout, act=1)
+    want = torch.zeros(n, h // 2, w // 2, cout, dtype=torch.float16, device=DEV)
+    ops.maxpool2(full, want, n, h, w, cout, cout, cout, 2)
+    got = torch.full((n, h // 2, w // 2, cout), float("nan"), dtype=torch.float16, device=DEV)
+    ops.conv_first(x, first, got, cout, act=1, pool=True)
+    torch.cuda.synchronize()
+    assert torch.equal(got, want)
+    if (cout, h) == (16, 36):
+        bad = torch.rand(1, 3, 36, 48).to(DEV)      # w % 32 != 0
+        with pytest.raises(MeError):
+            ops.conv_first(bad, first, torch.zeros(1, 18, 24, cout, dtype=torch.float16, device=DEV), cout, act=1, pool=True)
 
 
 @pytest.mark.parametrize("stride", [1, 2])

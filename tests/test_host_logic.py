@@ -157,7 +157,7 @@ def test_plan_launch_list_on_cpu(monkeypatch):
     monkeypatch.setattr(ops, "pack_conv", fake_pack)
     monkeypatch.setattr(ops, "pack_first_conv", lambda w, b=None, bn=None: ops.FirstConv.__new__(ops.FirstConv))
     monkeypatch.setattr(ops, "conv_workspace", lambda dev: torch.zeros(1))
-    monkeypatch.setattr(ops, "conv_first", lambda x, f, out, pitch, act: calls.append(("first", out.data_ptr(), pitch, act)))
+    monkeypatch.setattr(ops, "conv_first", lambda x, f, out, pitch, act, pool=False: calls.append(("first", out.data_ptr(), pitch, act)))
     monkeypatch.setattr(ops, "conv_gemm", lambda x, p, n, h, w, in_pitch, out, out_pitch, **kw: calls.append(
         ("conv", x.data_ptr(), out.data_ptr(), h, in_pitch, out_pitch, kw)))
     monkeypatch.setattr(ops, "upsample2", lambda x, y, n, h, w, c, ip, op_: calls.append(("up", x.data_ptr(), y.data_ptr(), c, ip, op_)))
