@@ -26,12 +26,12 @@ constexpr int kTileM = 128;
 constexpr int kK = 32;                 // 27 real + 5 zero
 constexpr int kABytes = kTileM * kK * 2;
 
-template <bool VEC>
+template <bool VEC, int EPI = 2>
 struct FCfg {
   static constexpr int STAGES = VEC ? 8 : 4;
   static constexpr int PROD_WARPS = VEC ? 8 : 16;
   static constexpr int ARRIVALS = VEC ? 32 : 128;  // producer threads per tile
-  static constexpr int EPI_GROUPS = 2;             // two 4-warp epilogue groups alternate tiles
+  static constexpr int EPI_GROUPS = EPI;           // 4-warp epilogue groups taking tiles in turn
   static constexpr int ACCS = 4;                   // TMEM accumulators in flight
   static constexpr int THREADS = 32 * (PROD_WARPS + 1 + 4 * EPI_GROUPS);
   static constexpr int SMEM = STAGES * kABytes + 1024;
@@ -72,16 +72,16 @@ __device__ __forceinline__ void store_row(uint8_t* tile, int row, const float (&
 // rows are ordered so that each epilogue warp holds 2 rows x 16 columns (lane = 16 * dy + dx): the 2x2 window is a
 // shfl_xor 1 / shfl_xor 16 away, and the 8 pooled pixels of a warp are one contiguous span of the pooled NHWC output.
 // max commutes with the fp16 rounding, so the result equals conv -> fp16 -> maxpool bit for bit.
-template <int COUT, bool VEC, bool POOL>
-__global__ void __launch_bounds__(FCfg<VEC>::THREADS, 1)
+template <int COUT, bool VEC, bool POOL, int EPI>
+__global__ void __launch_bounds__(FCfg<VEC, EPI>::THREADS, 1)
 conv_first_tc_kernel(const float* __restrict__ x, const __half* __restrict__ wk, const float* __restrict__ bias,
                      __half* __restrict__ y, int n, int h, int w, int cin, int out_pitch, int act, int tiles, int dbg) {
-  using F = FCfg<VEC>;
+  using F = FCfg<VEC, EPI>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* s_a = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   __shared__ __align__(128) uint8_t s_b[COUT * kK * 2];
   __shared__ __align__(16) float s_bias[COUT];
-  __shared__ __align__(8) uint64_t full_bar[F::STAGES], empty_bar[F::STAGES], tmem_full[FCfg<VEC>::ACCS], tmem_empty[FCfg<VEC>::ACCS];
+  __shared__ __align__(8) uint64_t full_bar[F::STAGES], empty_bar[F::STAGES], tmem_full[F::ACCS], tmem_empty[F::ACCS];
   __shared__ uint32_t tmem_ptr;
   constexpr int TMEM_COLS = (F::ACCS * COUT <= 32) ? 32 : (F::ACCS * COUT <= 64) ? 64 : (F::ACCS * COUT <= 128) ? 128 : 256;
   constexpr int MMA_WARP = F::PROD_WARPS;
@@ -127,16 +127,22 @@ conv_first_tc_kernel(const float* __restrict__ x, const __half* __restrict__ wk,
     for (int tile = blockIdx.x + stage * gridDim.x; tile < tiles; tile += F::STAGES * gridDim.x) {
       uint8_t* a_tile = s_a + stage * kABytes;
       if constexpr (VEC) {
-        int pix, row0;     // 4 consecutive pixels of one image row (w % 4 == 0) and their first MMA row
+        // 4 consecutive pixels of one image row per lane (w % 4 == 0).  Their MMA rows are row0 + j * rstep: for a fixed
+        // j the 32 lanes write 32 rows whose 16-byte slots cover every bank group 4 times - the minimum (lane-major
+        // rows 4 * lane + j would hit two bank groups 16 times each).
+        int pix, row0, rstep;
         if constexpr (POOL) {
           const int cbs = w >> 5, rgs = h >> 2;
           const int cb = tile % cbs, t2 = tile / cbs;
-          const int ry = lane >> 3, cx = (lane & 7) * 4;
-          pix = ((t2 / rgs) * h + (t2 % rgs) * 4 + ry) * w + cb * 32 + cx;
-          row0 = 32 * (2 * (ry >> 1) + (cx >> 4)) + 16 * (ry & 1) + (cx & 15);
+          const int ry = lane >> 3, c4 = lane & 7;
+          pix = ((t2 / rgs) * h + (t2 % rgs) * 4 + ry) * w + cb * 32 + c4 * 4;
+          // row(ry, j) = 32 * (2 * (j >> 1) + (ry >> 1)) + 16 * (ry & 1) + 8 * (j & 1) + c4   (see the epilogue)
+          row0 = 32 * (ry >> 1) + 16 * (ry & 1) + c4;
+          rstep = 0;   // not affine in j: handled below
         } else {
           pix = tile * kTileM + lane * 4;
-          row0 = lane * 4;
+          row0 = lane;
+          rstep = 32;
         }
         float v[4][27];
 #pragma unroll
@@ -171,7 +177,8 @@ conv_first_tc_kernel(const float* __restrict__ x, const __half* __restrict__ wk,
         mbar_wait_spin(&empty_bar[stage], phase ^ 1);
         if (!(dbg & 4)) {  // bit 4: no tile build either
 #pragma unroll
-          for (int j = 0; j < 4; ++j) store_row(a_tile, row0 + j, v[j]);
+          for (int j = 0; j < 4; ++j)
+            store_row(a_tile, POOL ? row0 + 64 * (j >> 1) + 8 * (j & 1) : row0 + j * rstep, v[j]);
         }
       } else {
         const int row = threadIdx.x & 127;
@@ -242,14 +249,17 @@ conv_first_tc_kernel(const float* __restrict__ x, const __half* __restrict__ wk,
       mbar_wait_spin(&tmem_full[acc], (it / F::ACCS) & 1);
       ptx::tc_fence_after();
       const uint32_t taddr = tmem_base + acc * COUT + (static_cast<uint32_t>(q * 32) << 16);
-      int pix = tile * kTileM + row;
+      // TMEM lane q * 32 + lane holds: VEC producers -> pixel 4 * lane + q of the tile; !VEC -> pixel q * 32 + lane
+      int pix = tile * kTileM + (VEC ? 4 * lane + q : row);
       bool writer = pix < total_px;
       if constexpr (POOL) {
+        // warp q: image rows 2 * (q & 1) + {0, 1} (lane bit 4), columns 4 * c4 + 2 * (q >> 1) + {0, 1} (lane bit 3),
+        // c4 = lane & 7: the 2x2 window of pooled pixel (q & 1, 2 * c4 + (q >> 1)) sits in lanes c4 + {0, 8, 16, 24}
         const int cbs = w >> 5, rgs = h >> 2;
         const int cb = tile % cbs, t2 = tile / cbs;
-        const int prow = (t2 % rgs) * 2 + (q >> 1), pcol = cb * 16 + 8 * (q & 1) + ((lane & 15) >> 1);
-        pix = ((t2 / rgs) * (h >> 1) + prow) * (w >> 1) + pcol;     // pooled pixel of this lane's 2x2 window
-        writer = (lane & 17) == 0;
+        const int prow = (t2 % rgs) * 2 + (q & 1), pcol = cb * 16 + 2 * (lane & 7) + (q >> 1);
+        pix = ((t2 / rgs) * (h >> 1) + prow) * (w >> 1) + pcol;
+        writer = (lane & 24) == 0;
       }
       __half* dst = y + 1LL * pix * out_pitch;
       // 32-byte sectors are written whole: one 256-bit store per 16 channels when the row pitch allows it
@@ -289,7 +299,7 @@ conv_first_tc_kernel(const float* __restrict__ x, const __half* __restrict__ wk,
           for (int e = 0; e < 8; ++e) {
             __half2 m = oh[e];
             uint32_t u = *reinterpret_cast<uint32_t*>(&m);
-            uint32_t o1 = __shfl_xor_sync(0xffffffffu, u, 1);
+            uint32_t o1 = __shfl_xor_sync(0xffffffffu, u, 8);
             m = __hmax2(m, *reinterpret_cast<__half2*>(&o1));
             u = *reinterpret_cast<uint32_t*>(&m);
             uint32_t o2 = __shfl_xor_sync(0xffffffffu, u, 16);
@@ -323,11 +333,11 @@ __global__ void pack_first_tc_kernel(const float* __restrict__ w_folded, int cou
   wk[i] = __float2half_rn(k < per_out ? w_folded[o * per_out + k] : 0.f);
 }
 
-template <int COUT, bool VEC, bool POOL = false>
+template <int COUT, bool VEC, bool POOL = false, int EPI = 2>
 int launch_first(const float* x, const __half* wk, const float* bias, __half* y, int n, int h, int w, int cin,
                  int out_pitch, int act, int tiles, int grid, cudaStream_t stream) {
-  using F = FCfg<VEC>;
-  auto kern = conv_first_tc_kernel<COUT, VEC, POOL>;
+  using F = FCfg<VEC, EPI>;
+  auto kern = conv_first_tc_kernel<COUT, VEC, POOL, EPI>;
   static bool attr_seen[64] = {false};   // per instantiation and per device
   if (first_use_on_device(attr_seen))
     ME_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, F::SMEM));
@@ -366,8 +376,16 @@ int conv_first_tc_impl(const float* x_nchw, const float* w_folded, const float* 
   if (pool) {
     ME_REQUIRE(vec && w % 32 == 0 && h % 4 == 0, "conv_first_tc_pool: needs a 16-byte aligned image with w %% 32 == 0 and "
                "h %% 4 == 0 (got %d x %d); run me_conv_first_tc + me_maxpool instead", h, w);
+    static int epi3 = -1;
+    if (epi3 < 0) {
+      const char* e = getenv("ME_FIRST_EPI");
+      epi3 = e ? atoi(e) : 3;   // three epilogue groups: the pooled epilogue's latency is what bounds the kernel with two
+    }
     switch (cout) {   // tiles are exact 4 x 32 blocks: n * (h / 4) * (w / 32) == total / 128
-      case 16: return launch_first<16, true, true>(x_nchw, wk, bias, y, n, h, w, cin, out_pitch, act, tiles, grid, stream);
+      case 16:
+        if (epi3 == 3) return launch_first<16, true, true, 3>(x_nchw, wk, bias, y, n, h, w, cin, out_pitch, act, tiles, grid, stream);
+        if (epi3 == 4) return launch_first<16, true, true, 4>(x_nchw, wk, bias, y, n, h, w, cin, out_pitch, act, tiles, grid, stream);
+        return launch_first<16, true, true>(x_nchw, wk, bias, y, n, h, w, cin, out_pitch, act, tiles, grid, stream);
       case 32: return launch_first<32, true, true>(x_nchw, wk, bias, y, n, h, w, cin, out_pitch, act, tiles, grid, stream);
       default: return fail(ME_ERR_UNSUPPORTED, "conv_first_tc_pool: cout %d unsupported (16 or 32)", cout);
     }
