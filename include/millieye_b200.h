@@ -208,6 +208,14 @@ int me_psroi_align(const void* feat, int n, int h, int w, int pitch, int out_cha
 int me_roi_align(const void* feat, int n, int h, int w, int pitch, int channels, int pooled, float spatial_scale,
                  const float* rois, const int* roi_count, int cap, void* out, int out_pitch,
                  me_stream_t stream);
+/* The same two gathers in BIN-MAJOR order: output element (ph*pooled + pw)*channels + c, and for the position-sensitive
+ * variant score-map channel (ph*pooled + pw)*channels + c.  Same values as me_psroi_align / me_roi_align under that
+ * fixed permutation (the caller permutes the producing conv's output channels and the consuming layer's input columns
+ * once when packing weights); consecutive threads read consecutive channels of one pixel neighbourhood, so one
+ * 32-byte sector serves a bin's channels instead of one sector per 2-byte element. */
+int me_roi_gather_bin_major(const void* feat, int n, int h, int w, int pitch, int channels, int pooled,
+                            float spatial_scale, const float* rois, const int* roi_count, int cap, void* out,
+                            int out_pitch, int position_sensitive, me_stream_t stream);
 
 /* ---- proposal assembly, heads, output (A7, A12-A14) -------------------------------- */
 typedef struct me_head_weights {
@@ -230,6 +238,12 @@ typedef struct me_head_weights {
 int me_build_proposals(const float* det, const int* det_count, int n, int max_det, int det_cols, int class_idx,
                        const float* radar_boxes, int num_radar, float img_size, float* img_boxes, float* rois,
                        int* counts, int cap, me_stream_t stream);
+/* The same with the number of radar boxes read from DEVICE memory at run time (*num_radar_dev, clipped to
+ * [0, radar_cap]): the launch has no per-call host scalar, so a captured CUDA graph serves every batch
+ * (millieye_b200.my_models.FusionPipeline). */
+int me_build_proposals_dev(const float* det, const int* det_count, int n, int max_det, int det_cols, int class_idx,
+                           const float* radar_boxes, int radar_cap, const int* num_radar_dev, float img_size,
+                           float* img_boxes, float* rois, int* counts, int cap, me_stream_t stream);
 
 /* refinement_head tail + ensemble_head + masks (my_models.py:264-284, 498-514): from
  * hidden = leaky(net0(psroi)) [cap][hidden_pitch] fp16 and the radar crop [cap][radar_pitch]

@@ -93,7 +93,11 @@ SIGNATURES = {
                                c_int, c_void_p, c_int, c_void_p]),
     "me_roi_align": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_float, c_void_p, c_void_p,
                              c_int, c_void_p, c_int, c_void_p]),
+    "me_roi_gather_bin_major": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_float, c_void_p, c_void_p,
+                                        c_int, c_void_p, c_int, c_int, c_void_p]),
     "me_build_proposals": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_int, c_float,
+                                   c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
+    "me_build_proposals_dev": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_int, c_void_p, c_float,
                                    c_void_p, c_void_p, c_void_p, c_int, c_void_p]),
     "me_fusion_heads": (c_int, [c_void_p, c_int, c_void_p, c_int, POINTER(HeadWeights), c_void_p, c_void_p, c_int,
                                 c_void_p, c_void_p, c_void_p, c_void_p]),

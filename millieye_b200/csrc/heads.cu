@@ -35,8 +35,10 @@ __device__ __forceinline__ int block_compact(bool pass, int* s_scan, int* s_tota
 // my_models.py:459-473 + :490-492.  One block.
 __global__ void __launch_bounds__(kBlock)
 build_proposals_kernel(const float* __restrict__ det, const int* __restrict__ det_count, int n, int max_det, int det_cols,
-                       int class_idx, const float* __restrict__ radar, int num_radar, float img_size,
-                       float* __restrict__ img_boxes, float* __restrict__ rois, int* __restrict__ counts, int cap) {
+                       int class_idx, const float* __restrict__ radar, int num_radar, const int* __restrict__ num_radar_dev,
+                       float img_size, float* __restrict__ img_boxes, float* __restrict__ rois, int* __restrict__ counts,
+                       int cap) {
+  if (num_radar_dev) num_radar = max(0, min(*num_radar_dev, num_radar));   // device-side count, host value = capacity
   __shared__ int s_scan[kBlock / 32];
   __shared__ int s_total;
   if (threadIdx.x == 0) s_total = 0;
@@ -334,19 +336,34 @@ finalize_kernel(const float* __restrict__ img_boxes, const float* __restrict__ r
 
 extern "C" {
 
-int me_build_proposals(const float* det, const int* det_count, int n, int max_det, int det_cols, int class_idx,
-                       const float* radar_boxes, int num_radar, float img_size, float* img_boxes, float* rois,
-                       int* counts, int cap, me_stream_t stream_) {
+static int build_proposals_impl(const float* det, const int* det_count, int n, int max_det, int det_cols, int class_idx,
+                                const float* radar_boxes, int num_radar, const int* num_radar_dev, float img_size,
+                                float* img_boxes, float* rois, int* counts, int cap, cudaStream_t stream) {
   using namespace me;
-  cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   ME_REQUIRE(det && det_count && img_boxes && rois && counts, "build_proposals: null argument");
   ME_REQUIRE(num_radar == 0 || radar_boxes, "build_proposals: radar boxes missing");
   ME_REQUIRE(det_cols >= 8 && 7 + class_idx < det_cols, "build_proposals: bad det_cols/class_idx");
   ME_REQUIRE(cap > 0 && n > 0 && max_det > 0, "build_proposals: empty problem");
   build_proposals_kernel<<<1, kBlock, 0, stream>>>(det, det_count, n, max_det, det_cols, class_idx, radar_boxes, num_radar,
-                                                   img_size, img_boxes, rois, counts, cap);
+                                                   num_radar_dev, img_size, img_boxes, rois, counts, cap);
   ME_LAUNCH_CHECK();
   return ME_OK;
+}
+
+int me_build_proposals(const float* det, const int* det_count, int n, int max_det, int det_cols, int class_idx,
+                       const float* radar_boxes, int num_radar, float img_size, float* img_boxes, float* rois,
+                       int* counts, int cap, me_stream_t stream_) {
+  return build_proposals_impl(det, det_count, n, max_det, det_cols, class_idx, radar_boxes, num_radar, nullptr, img_size,
+                              img_boxes, rois, counts, cap, static_cast<cudaStream_t>(stream_));
+}
+
+int me_build_proposals_dev(const float* det, const int* det_count, int n, int max_det, int det_cols, int class_idx,
+                           const float* radar_boxes, int radar_cap, const int* num_radar_dev, float img_size,
+                           float* img_boxes, float* rois, int* counts, int cap, me_stream_t stream_) {
+  using namespace me;
+  ME_REQUIRE(num_radar_dev, "build_proposals_dev: null radar count");
+  return build_proposals_impl(det, det_count, n, max_det, det_cols, class_idx, radar_boxes, radar_cap, num_radar_dev, img_size,
+                              img_boxes, rois, counts, cap, static_cast<cudaStream_t>(stream_));
 }
 
 int me_fusion_heads(const void* hidden, int hidden_pitch, const void* radar_crop, int radar_pitch,

@@ -39,7 +39,12 @@ __device__ __forceinline__ float bilinear(const __half* __restrict__ plane, int 
   return hy * hx * v1 + hy * lx * v2 + ly * hx * v3 + ly * lx * v4;
 }
 
-template <bool POSITION_SENSITIVE>
+// BIN_MAJOR: the output row is ordered [bin = ph * P + pw][c] instead of the reference's [c][ph][pw], and the
+// position-sensitive score map holds channel (ph * P + pw) * C + c: consecutive threads then read consecutive channels
+// of ONE pixel neighbourhood (a single 32-byte sector serves a bin's 10 channels) instead of 2-byte loads from 10
+// different sectors.  The caller permutes the producing conv's output channels and the consuming layer's input
+// columns once at pack time, so the result is the reference's up to that fixed permutation.
+template <bool POSITION_SENSITIVE, bool BIN_MAJOR>
 __global__ void roi_gather_kernel(const __half* __restrict__ feat, int n, int h, int w, int pitch, int channels,
                                   int pooled, float scale, const float* __restrict__ rois,
                                   const int* __restrict__ roi_count, int count_index, int cap,
@@ -52,9 +57,10 @@ __global__ void roi_gather_kernel(const __half* __restrict__ feat, int n, int h,
     const int e = static_cast<int>(i - 1LL * r * out_pitch);
     float val = 0.f;
     if (r < live && e < per_roi) {
-      const int c = e / (pooled * pooled);
-      const int ph = (e / pooled) % pooled;
-      const int pw = e % pooled;
+      const int c = BIN_MAJOR ? e % channels : e / (pooled * pooled);
+      const int bin = BIN_MAJOR ? e / channels : e % (pooled * pooled);
+      const int ph = bin / pooled;
+      const int pw = bin % pooled;
       const float* roi = rois + r * 5;
       int b = static_cast<int>(roi[0]);
       b = b < 0 ? 0 : (b >= n ? n - 1 : b);
@@ -68,7 +74,7 @@ __global__ void roi_gather_kernel(const __half* __restrict__ feat, int n, int h,
       }
       const float bin_h = rh / pooled, bin_w = rw / pooled;
       const int gh = static_cast<int>(ceilf(rh / pooled)), gw = static_cast<int>(ceilf(rw / pooled));
-      const int ch = POSITION_SENSITIVE ? (c * pooled + ph) * pooled + pw : c;
+      const int ch = POSITION_SENSITIVE ? (BIN_MAJOR ? bin * channels + c : (c * pooled + ph) * pooled + pw) : c;
       const __half* plane = feat + 1LL * b * h * w * pitch + ch;
       const float hstart = ph * bin_h + sh, wstart = pw * bin_w + sw;
       float sum = 0.f;
@@ -88,7 +94,7 @@ __global__ void roi_gather_kernel(const __half* __restrict__ feat, int n, int h,
   }
 }
 
-template <bool PS>
+template <bool PS, bool BM = false>
 int launch(const void* feat, int n, int h, int w, int pitch, int channels, int pooled, float scale, const float* rois,
            const int* roi_count, int cap, void* out, int out_pitch, cudaStream_t stream) {
   ME_REQUIRE(feat && rois && roi_count && out, "roi: null argument");
@@ -98,7 +104,7 @@ int launch(const void* feat, int n, int h, int w, int pitch, int channels, int p
   const long long total = 1LL * cap * out_pitch;
   long long blocks = (total + 255) / 256;
   if (blocks > 148 * 16) blocks = 148 * 16;
-  roi_gather_kernel<PS><<<static_cast<int>(blocks), 256, 0, stream>>>(static_cast<const __half*>(feat), n, h, w, pitch,
+  roi_gather_kernel<PS, BM><<<static_cast<int>(blocks), 256, 0, stream>>>(static_cast<const __half*>(feat), n, h, w, pitch,
                                                                       channels, pooled, scale, rois, roi_count, 0, cap,
                                                                       static_cast<__half*>(out), out_pitch);
   ME_LAUNCH_CHECK();
@@ -120,6 +126,16 @@ int me_roi_align(const void* feat, int n, int h, int w, int pitch, int channels,
                  const float* rois, const int* roi_count, int cap, void* out, int out_pitch, me_stream_t stream) {
   return me::launch<false>(feat, n, h, w, pitch, channels, pooled, spatial_scale, rois, roi_count, cap, out, out_pitch,
                            static_cast<cudaStream_t>(stream));
+}
+
+int me_roi_gather_bin_major(const void* feat, int n, int h, int w, int pitch, int channels, int pooled, float spatial_scale,
+                            const float* rois, const int* roi_count, int cap, void* out, int out_pitch,
+                            int position_sensitive, me_stream_t stream) {
+  if (position_sensitive)
+    return me::launch<true, true>(feat, n, h, w, pitch, channels, pooled, spatial_scale, rois, roi_count, cap, out, out_pitch,
+                                  static_cast<cudaStream_t>(stream));
+  return me::launch<false, true>(feat, n, h, w, pitch, channels, pooled, spatial_scale, rois, roi_count, cap, out, out_pitch,
+                                 static_cast<cudaStream_t>(stream));
 }
 
 }  // extern "C"

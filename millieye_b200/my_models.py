@@ -9,6 +9,8 @@ The reference's device boundary (D2H of every decoded box for CPU NMS, H2D of th
 my_models.py:457-470) disappears; the only host synchronisation is the read of the final row count.
 The nn modules below are parameter containers (checkpoint compatibility); their forward is unused.
 """
+import os
+
 import torch
 from torch import nn
 
@@ -117,9 +119,16 @@ class _FusionPlan:
         f16 = dict(dtype=torch.float16, device=device)
         f32 = dict(dtype=torch.float32, device=device)
         i32 = dict(dtype=torch.int32, device=device)
-        # score maps
-        self.img_conv = ops.pack_conv(sd["img_cnn_layers.net.conv_0.weight"], sd["img_cnn_layers.net.conv_0.bias"],
-                                      bn("img_cnn_layers.net.batch_norm_0."), cout_pad=512)
+        # score maps.  The 490 position-sensitive channels are produced in bin-major order ((ph, pw, c) instead of the
+        # reference's (c, ph, pw)), the two RoI crops are written in that order too, and the layers that read the crops
+        # (refinement_head.net0, radar_net) get their input columns permuted the same way: same numbers, but the gathers
+        # read 10 contiguous channels per bin (ops.roi_gather_bin_major).
+        perm = ops.bin_major_perm(10, 7, device)
+        g_, b_, m_, v_, eps = bn("img_cnn_layers.net.batch_norm_0.")
+        self.img_conv = ops.pack_conv(sd["img_cnn_layers.net.conv_0.weight"][perm].contiguous(),
+                                      sd["img_cnn_layers.net.conv_0.bias"][perm].contiguous(),
+                                      (g_[perm].contiguous(), b_[perm].contiguous(), m_[perm].contiguous(), v_[perm].contiguous(), eps),
+                                      cout_pad=512)
         self.roi_score = torch.zeros((n, g, g, 512), **f16)
         self.maps_in = torch.zeros((n, 3, g, g), **f32)
         self.r1 = ops.pack_first_conv(sd["radar_cnn_layers.conv1.0.weight"], sd["radar_cnn_layers.conv1.0.bias"],
@@ -140,13 +149,14 @@ class _FusionPlan:
         cap = self.cap
         self.nms = ops.NmsBuffers(n, base_plan.rows_total, base_plan.attrs - 5, self.MAX_DET, device)
         self.radar_dev = torch.zeros((max(radar_cap, 1), 5), **f32)
+        self.radar_n_dev = torch.zeros((1,), **i32)      # radar boxes of the current batch (FusionPipeline's graphs)
         self.img_boxes = torch.zeros((cap, 9), **f32)
         self.rois = torch.zeros((cap, 5), **f32)
         self.counts = torch.zeros((2,), **i32)
         self.crop_img = torch.zeros((cap, 512), **f16)
         self.crop_radar = torch.zeros((cap, 496), **f16)
         self.hidden = torch.zeros((cap, 256), **f16)
-        w0 = sd["refinement_head.net0.0.weight"]
+        w0 = sd["refinement_head.net0.0.weight"][:, perm].contiguous()
         self.fc0 = ops.pack_conv(w0.view(w0.shape[0], w0.shape[1], 1, 1), sd["refinement_head.net0.0.bias"], None)
         # small heads stay fp32
         rw = sd["refinement_head.radar_net.0.weight"]
@@ -155,7 +165,7 @@ class _FusionPlan:
         self._hw_tensors = {
             "net1_w": sd["refinement_head.net1.0.weight"].contiguous(), "net1_b": sd["refinement_head.net1.0.bias"].contiguous(),
             "net2_w": sd["refinement_head.net2.0.weight"].contiguous(), "net2_b": sd["refinement_head.net2.0.bias"].contiguous(),
-            "radar_w": (rw.reshape(rw.shape[0], -1) * scale[:, None]).contiguous(),
+            "radar_w": (rw.reshape(rw.shape[0], -1) * scale[:, None])[:, perm].contiguous(),
             "radar_b": ((sd["refinement_head.radar_net.0.bias"] - m_) * scale + b_).contiguous(),
             "radar2_w": sd["refinement_head.radar_net.3.weight"].reshape(-1).contiguous(),
             "radar2_b": sd["refinement_head.radar_net.3.bias"].contiguous(),
@@ -205,10 +215,17 @@ class _FusionPlan:
                             1.0, self.img_boxes, self.rois, self.counts, self.cap)
         self.launches += 3
 
+    def proposals_dev(self, conf_thresh, class_idx):
+        """proposals() with the radar-box count taken from self.radar_n_dev: no per-batch host scalar in any launch."""
+        ops.filter_nms(self.base.yolo_out, conf_thresh, 0.5, self.MAX_DET, xyxy_inplace=True, buffers=self.nms)
+        ops.build_proposals_dev(self.nms.det, self.nms.count, class_idx, self.radar_dev, self.radar_n_dev, 1.0,
+                                self.img_boxes, self.rois, self.counts, self.cap)
+        self.launches += 3
+
     def heads(self, thr_img, thr_radar, regress_boxes):
         n, g, cap = self.n, self.g, self.cap
-        ops.psroi_align(self.roi_score, n, g, g, 512, 10, 7, 1.0 / 16, self.rois, self.counts, cap, self.crop_img, 512)
-        ops.roi_align(self.radar_score, n, g, g, 32, 10, 7, 1.0 / 16, self.rois, self.counts, cap, self.crop_radar, 496)
+        ops.roi_gather_bin_major(self.roi_score, n, g, g, 512, 10, 7, 1.0 / 16, self.rois, self.counts, cap, self.crop_img, 512, True)
+        ops.roi_gather_bin_major(self.radar_score, n, g, g, 32, 10, 7, 1.0 / 16, self.rois, self.counts, cap, self.crop_radar, 496, False)
         ops.conv_gemm(self.crop_img, self.fc0, cap, 1, 1, 512, self.hidden, 256, act=ME_ACT_LEAKY, cin=490)
         ops.fusion_heads(self.hidden, 256, self.crop_radar, 496, self.head_weights, self.img_boxes, self.counts, cap,
                          self.regress, self.refine, self.mask)
@@ -474,13 +491,37 @@ class FusionPipeline:
                 return self.host_flat[:cap * 8].view(cap, 8)[:k]
             return self.plan.out[:int(self.plan.out_count.item())]
 
-    def __init__(self, model, depth=3):
+    TAIL_LAUNCHES = 13        # 5 score-map convs, filter + NMS (2), proposals, 2 RoI gathers, FC GEMM, heads, finalize
+
+    def __init__(self, model, depth=4, use_cuda_graph=None):
         self.model = model
-        self.depth = max(2, int(depth))
+        # an even ring keeps every fusion plan on ONE of the detector's two output slots: one tail graph per plan
+        self.depth = max(2, int(depth) + (int(depth) & 1))
         self._records = {}     # id(fusion plan) -> Record
         self._next = 0
         self._side = None
-        self.launches = 0      # fusion-tail kernels launched by the last submit (the backbone's are in its plan)
+        self.launches = self.TAIL_LAUNCHES   # fusion-tail kernels per submit (the backbone's are in its plan)
+        # the score-map convs and the proposal / head kernels replay as two CUDA graphs per plan (13 launches -> 2):
+        # all their shapes are fixed by the plan, row counts live on the device
+        self.use_cuda_graph = (os.environ.get("ME_FUSION_GRAPHS", "1") != "0") if use_cuda_graph is None else bool(use_cuda_graph)
+
+    def _run(self, plan, name, key, fn):
+        """fn() enqueues kernels on the current stream.  First use of (name, key): run it as is (one-time initialisation
+        inside the library must not happen under capture); second use: capture it; afterwards: replay."""
+        if not self.use_cuda_graph:
+            return fn()
+        cache = plan.__dict__.setdefault("_pipe_graphs", {})
+        state = cache.get((name, key))
+        if state is None:
+            if len(cache) >= 16:        # thresholds that change every call: no point in capturing
+                return fn()
+            cache[(name, key)] = "warm"
+            return fn()
+        if state == "warm":
+            from .engine import capture_graph
+            torch.cuda.synchronize(plan.device)
+            state = cache[(name, key)] = capture_graph(fn)
+        state.replay()
 
     def submit(self, images, maps, radar_boxes_location, model_mode=0, readback=True):
         m = self.model
@@ -513,18 +554,24 @@ class FusionPipeline:
             if n_radar > 0:
                 radar_boxes_location[:, 1:] *= images.shape[-1]          # reference side effect (:491)
                 plan.radar_dev[:n_radar].copy_(radar_boxes_location, non_blocking=True)
+            plan.radar_n_dev.fill_(n_radar)
             plan.maps_in.copy_(maps, non_blocking=True)
-            plan.score_maps()
+            self._run(plan, "score", (), plan.score_maps)
             main = torch.cuda.current_stream()
             self._side.wait_stream(main)
             with torch.cuda.stream(self._side):
                 plan_b.run_decode(base.use_cuda_graph)
-                plan.proposals(m.conf_thresh, m.class_idx, n_radar)
-                plan.heads(float(m.refine_threshold_img), float(m.refine_threshold_radar), model_mode != 2)
+                thr = (float(m.conf_thresh), int(m.class_idx), float(m.refine_threshold_img), float(m.refine_threshold_radar))
+
+                def tail(thr=thr, regress=model_mode != 2):
+                    plan.proposals_dev(thr[0], thr[1])
+                    plan.heads(thr[2], thr[3], regress)
+
+                # the NMS reads the base plan's CURRENT output slot: one graph per slot and threshold set
+                self._run(plan, "tail", (plan_b._slot, model_mode != 2) + thr, tail)
                 if readback:
                     rec.host_flat.copy_(plan.out_flat, non_blocking=True)
                 rec.done.record()
             plan_b.hold_output(rec.done)
             m.refinement_head.count += 1
-            self.launches = plan.launches
         return rec

@@ -323,6 +323,23 @@ def roi_align(feat, n, h, w, pitch, channels, pooled, scale, rois, counts, cap, 
     return out
 
 
+def roi_gather_bin_major(feat, n, h, w, pitch, channels, pooled, scale, rois, counts, cap, out, out_pitch, position_sensitive):
+    """psroi_align / roi_align with output element (ph*P + pw)*C + c (and score-map channel in the same order for the
+    position-sensitive gather); see me_roi_gather_bin_major.  bin_major_perm() is the permutation the caller applies."""
+    _need_cuda(feat, rois, counts, out)
+    check(_lib.lib().me_roi_gather_bin_major(ptr(feat), n, h, w, pitch, channels, pooled, float(scale), ptr(rois),
+                                             _count_ptr(counts, 1), cap, ptr(out), out_pitch, int(bool(position_sensitive)),
+                                             stream_ptr()), "me_roi_gather_bin_major")
+    return out
+
+
+def bin_major_perm(channels, pooled, device=None):
+    """perm[j'] = j: the reference index c*P*P + bin that bin-major position j' = bin*C + c holds."""
+    bins = pooled * pooled
+    jp = torch.arange(channels * bins, device=device)
+    return (jp % channels) * bins + jp // channels
+
+
 def build_proposals(det, det_count, class_idx, radar_boxes, img_size, img_boxes, rois, counts, cap):
     _need_cuda(det, det_count, img_boxes, rois, counts)
     n, max_det, det_cols = det.shape
@@ -330,6 +347,15 @@ def build_proposals(det, det_count, class_idx, radar_boxes, img_size, img_boxes,
     check(_lib.lib().me_build_proposals(ptr(det), ptr(det_count), n, max_det, det_cols, class_idx,
                                         ptr(radar_boxes) if nr else None, nr, float(img_size), ptr(img_boxes),
                                         ptr(rois), ptr(counts), cap, stream_ptr()), "me_build_proposals")
+
+
+def build_proposals_dev(det, det_count, class_idx, radar_boxes, num_radar_dev, img_size, img_boxes, rois, counts, cap):
+    """build_proposals with the radar-box count in device memory (radar_boxes: the whole capacity buffer)."""
+    _need_cuda(det, det_count, radar_boxes, num_radar_dev, img_boxes, rois, counts)
+    n, max_det, det_cols = det.shape
+    check(_lib.lib().me_build_proposals_dev(ptr(det), ptr(det_count), n, max_det, det_cols, class_idx, ptr(radar_boxes),
+                                            int(radar_boxes.shape[0]), ptr(num_radar_dev), float(img_size), ptr(img_boxes),
+                                            ptr(rois), ptr(counts), cap, stream_ptr()), "me_build_proposals_dev")
 
 
 def fusion_heads(hidden, hidden_pitch, crop, crop_pitch, head_weights, img_boxes, counts, cap, regress, refine, mask):

@@ -247,15 +247,21 @@ def test_fusion_pipeline_equals_forward():
         batches.append((imgs, maps, rb))
     want = [model(imgs, maps, rb.clone().to(DEV), 0).cpu() for imgs, maps, rb in batches]
     assert sum(len(w) for w in want) > 50
-    pipe = FusionPipeline(model, depth=3)
-    got, recs = [], []
-    for k, (imgs, maps, rb) in enumerate(batches):
-        recs.append(pipe.submit(imgs, maps, rb.clone().to(DEV), 0, readback=(k != 4)))
-        if len(recs) == 3:                      # two further batches are in flight when a record is read
-            got.append(recs.pop(0).wait().cpu().clone())
-    got += [r.wait().cpu().clone() for r in recs]
-    for k, (a, b) in enumerate(zip(got, want)):
-        assert a.shape == b.shape and torch.equal(a, b), f"batch {k}"
+    # 18 submits over the 6 batches: every (fusion plan, detector output slot) pair is used three times - as is, under
+    # capture, and as a graph replay (FusionPipeline._run)
+    for graphs in (True, False):
+        pipe = FusionPipeline(model, depth=3, use_cuda_graph=graphs)
+        got, recs = [], []
+        for k in range(18):
+            imgs, maps, rb = batches[k % 6]
+            recs.append(pipe.submit(imgs, maps, rb.clone().to(DEV), 0, readback=(k % 6 != 4)))
+            if len(recs) == 3:                      # two further batches are in flight when a record is read
+                got.append(recs.pop(0).wait().cpu().clone())
+        got += [r.wait().cpu().clone() for r in recs]
+        assert len(got) == 18
+        for k, a in enumerate(got):
+            b = want[k % 6]
+            assert a.shape == b.shape and torch.equal(a, b), f"graphs={graphs} submit {k}"
     # mode 2 (radar only) keeps the reference's persistent side effect, mode 1 is refused
     imgs, maps, rb = batches[0]
     w2 = model(imgs, maps, rb.clone().to(DEV), 2).cpu()

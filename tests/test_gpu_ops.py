@@ -300,7 +300,19 @@ def _run_roi(feat, rfeat, rois, cap):
     out_ra = torch.full((cap, 496), 7.0, dtype=torch.float16, device=DEV)
     ops.psroi_align(f.to(DEV), n, g, g, 512, 10, 7, 1 / 16., rois_d.to(DEV), counts.to(DEV), cap, out_ps, 512)
     ops.roi_align(r.to(DEV), n, g, g, 32, 10, 7, 1 / 16., rois_d.to(DEV), counts.to(DEV), cap, out_ra, 496)
+    # bin-major variant (the layout Network's plan uses): the same numbers under ops.bin_major_perm, bit for bit
+    perm = ops.bin_major_perm(10, 7)
+    f_bm = torch.zeros_like(f)
+    f_bm[..., :490] = f[..., :490][..., perm]
+    bm_ps = torch.full((cap, 512), 7.0, dtype=torch.float16, device=DEV)
+    bm_ra = torch.full((cap, 496), 7.0, dtype=torch.float16, device=DEV)
+    ops.roi_gather_bin_major(f_bm.to(DEV), n, g, g, 512, 10, 7, 1 / 16., rois_d.to(DEV), counts.to(DEV), cap, bm_ps, 512, True)
+    ops.roi_gather_bin_major(r.to(DEV), n, g, g, 32, 10, 7, 1 / 16., rois_d.to(DEV), counts.to(DEV), cap, bm_ra, 496, False)
     torch.cuda.synchronize()
+    for std, bm in ((out_ps, bm_ps), (out_ra, bm_ra)):
+        a, b = std[:, :490][:, perm.to(DEV)], bm[:, :490]
+        assert torch.equal(torch.nan_to_num(a.float(), nan=-77.0), torch.nan_to_num(b.float(), nan=-77.0))
+        assert torch.equal(torch.nan_to_num(std[:, 490:].float()), torch.nan_to_num(bm[:, 490:].float()))
     # oracle on the same fp16-rounded maps
     ref_ps = oroi.ps_roi_align(f[..., :490].float().permute(0, 3, 1, 2).numpy(), rois)
     ref_ra = oroi.roi_align(r[..., :10].float().permute(0, 3, 1, 2).numpy(), rois)
