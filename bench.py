@@ -579,7 +579,10 @@ def run_gpu(args):
     resident = [h.to(device).float() / 255.0 for h in host]
     plan = net.plan_for(BATCH, SIZE, device)
     from millieye_b200.models import DetectPipeline
-    pipe = DetectPipeline(net, CONF_THRESH, 0.5, 200, gather=world > 1)
+    # every rank reads its own shard back; the gathered batch goes to the host on rank 0 only (the consumer of the whole
+    # batch) - the other ranks keep it on the device
+    pipe = DetectPipeline(net, CONF_THRESH, 0.5, 200, gather=world > 1 and os.environ.get("ME_BENCH_GATHER", "1") != "0",
+                          host_all=rank == 0 and os.environ.get("ME_BENCH_HOSTALL", "1") != "0")
     last = {}
 
     def step(x, e2e):
@@ -683,7 +686,9 @@ def run_gpu(args):
     achieved_burst = flops_frame * BATCH / (conv_ms * 1e-3) / 1e12
     achieved_long = flops_frame * BATCH / (conv_ms_long * 1e-3) / 1e12 if conv_ms_long else None
     h2d = BATCH * 3 * SIZE * SIZE     # uint8 frames
-    d2h = rec.host_det.numel() * 4 + rec.host_cnt.numel() * 4
+    d2h = rec.host_det.numel() * 4 + rec.host_cnt.numel() * 4      # this rank's shard (every rank reads its own)
+    if rec.host_all is not None:                                      # + the gathered batch, on rank 0 only
+        d2h += rec.host_all[0].numel() * 4 + rec.host_all[1].numel() * 4
 
     cpu = None
     if world == 1 and not args.no_cpu_baseline:

@@ -260,8 +260,9 @@ class DetectPipeline:
             self.pending = False
             return self
 
-    def __init__(self, net, conf_thresh, nms_thresh=0.5, max_det=200, gather=False, depth=4):
+    def __init__(self, net, conf_thresh, nms_thresh=0.5, max_det=200, gather=False, depth=4, host_all=True):
         self.net, self.conf_thresh, self.nms_thresh, self.max_det, self.gather = net, conf_thresh, nms_thresh, max_det, gather
+        self.host_all = host_all    # readback=True also copies the gathered batch of every rank to this rank's host
         self.depth = max(2, int(depth))
         self._rings = {}     # plan -> [records], round robin
         self._next = {}
@@ -306,7 +307,7 @@ class DetectPipeline:
                                                            out=rec.gather_out)
                 if readback:
                     rec.host_flat.copy_(rec.nms.flat, non_blocking=True)      # this rank's shard: one copy
-                    if self.gather:
+                    if self.gather and self.host_all:
                         if rec.host_all is None:
                             rec.host_all = (torch.empty_like(rec.det, device="cpu").pin_memory(),
                                             torch.empty_like(rec.count, device="cpu").pin_memory())
