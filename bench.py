@@ -579,10 +579,24 @@ def run_gpu(args):
     resident = [h.to(device).float() / 255.0 for h in host]
     plan = net.plan_for(BATCH, SIZE, device)
     from millieye_b200.models import DetectPipeline
-    # every rank reads its own shard back; the gathered batch goes to the host on rank 0 only (the consumer of the whole
-    # batch) - the other ranks keep it on the device
-    pipe = DetectPipeline(net, CONF_THRESH, 0.5, 200, gather=world > 1 and os.environ.get("ME_BENCH_GATHER", "1") != "0",
-                          host_all=rank == 0 and os.environ.get("ME_BENCH_HOSTALL", "1") != "0")
+    # N > 1: every rank's detections are gathered on every GPU each step with ONE all_gather_into_tensor (ME_BENCH_GATHER=0:
+    # none; =peer: dist.PeerGather, copy engines + stream memory operations - measured slower).  Every
+    # rank reads its own shard back in the e2e arm; ME_BENCH_HOSTALL=1 also copies the gathered batch to rank 0's host.
+    mode = os.environ.get("ME_BENCH_GATHER", "nccl")
+    gather = False if world == 1 or mode == "0" else ("peer" if mode == "peer" else True)
+    pipe = DetectPipeline(net, CONF_THRESH, 0.5, 200, gather=gather,
+                          host_all=rank == 0 and os.environ.get("ME_BENCH_HOSTALL", "0") == "1")
+    if gather == "peer":
+        try:       # CUDA IPC between the ranks' processes; fall back to the NCCL collective where it is not permitted
+            pipe.submit(plan.next_input()).wait()
+            ok = torch.ones(1, device=device)
+        except Exception as e:  # noqa: BLE001
+            print(f"[bench] rank {rank}: PeerGather unavailable ({e}); using all_gather_into_tensor", file=sys.stderr)
+            ok = torch.zeros(1, device=device)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        if float(ok.item()) == 0:
+            pipe = DetectPipeline(net, CONF_THRESH, 0.5, 200, gather=True, host_all=pipe.host_all)
+    gather_impl = {False: "none", True: "nccl all_gather_into_tensor", "peer": "PeerGather (copy engines + stream memory ops)"}[pipe.gather]
     last = {}
 
     def step(x, e2e):
@@ -734,7 +748,7 @@ def run_gpu(args):
                 config=dict(workload=f"Darknet-53 YOLOv3 inference (forward + decode + conf filter + NMS), batch {BATCH} per GPU, "
                                      f"{SIZE}x{SIZE}, fp16 compute / fp32 accumulate",
                             conf_thresh=CONF_THRESH, parallelism=f"frames sharded over {world} GPU(s), weights replicated"
-                            + (", one all_gather of detections per step" if world > 1 else ""),
+                            + (f", detections gathered on every GPU each step: {gather_impl}" if world > 1 else ""),
                             l2="2 alternating resident input batches (64 MB each; 3 rotating pinned host batches in the e2e arm) and "
                                "~4 GB of activations per step exceed the 126 MB L2; no explicit flush",
                             pipeline="DetectPipeline: filter+NMS (+all_gather, +D2H read in the e2e arm) of batch i run on a "

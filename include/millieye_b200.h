@@ -420,6 +420,19 @@ int me_stage3_tail_bwd(const float* rc, const float* refine, const float* cls, i
 int me_adam_step(float* params, const float* grads, float* exp_avg, float* exp_avg_sq, long long n, float lr, float beta1,
                  float beta2, float eps, int step, me_stream_t stream);
 
+/* ---- copy-engine collective plumbing (millieye_b200/dist.py::PeerGather) ------------------------------------------ */
+/* The detection path has no exchange step (frames are independent); when a caller wants every rank's
+ * detections on every GPU, the shards are PUSHED into the peers' buffers (opened through CUDA IPC) with copy engines and
+ * completion is signalled / awaited with stream memory operations - no kernel, so nothing competes with the persistent
+ * convolution kernels for SMs (an NCCL all-gather kernel has to wait until they leave).
+ * me_stream_wait_value32: blocks `stream` until *(uint32*)addr >= value.  me_stream_write_value32: stream-ordered store.
+ * me_peer_copy: cudaMemcpyAsync between device allocations of (possibly) different GPUs, ordered on `stream`. */
+int me_stream_wait_value32(const void* addr, unsigned int value, me_stream_t stream);
+int me_stream_write_value32(void* addr, unsigned int value, me_stream_t stream);
+int me_peer_copy(void* dst, const void* src, size_t bytes, me_stream_t stream);
+/* cudaDeviceEnablePeerAccess(current device -> peer_device); ME_OK when already enabled or the same device. */
+int me_peer_enable(int peer_device);
+
 #ifdef __cplusplus
 }
 #endif

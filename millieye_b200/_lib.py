@@ -6,7 +6,7 @@ with the library's message on a non-zero return code.
 """
 import ctypes
 import os
-from ctypes import (POINTER, Structure, byref, c_char_p, c_double, c_float, c_int, c_longlong, c_size_t,
+from ctypes import (POINTER, Structure, byref, c_char_p, c_double, c_float, c_int, c_longlong, c_size_t, c_uint,
                     c_ulonglong, c_void_p)
 
 from . import build as _build
@@ -93,6 +93,10 @@ SIGNATURES = {
                                c_int, c_void_p, c_int, c_void_p]),
     "me_roi_align": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_float, c_void_p, c_void_p,
                              c_int, c_void_p, c_int, c_void_p]),
+    "me_stream_wait_value32": (c_int, [c_void_p, c_uint, c_void_p]),
+    "me_stream_write_value32": (c_int, [c_void_p, c_uint, c_void_p]),
+    "me_peer_copy": (c_int, [c_void_p, c_void_p, c_size_t, c_void_p]),
+    "me_peer_enable": (c_int, [c_int]),
     "me_roi_gather_bin_major": (c_int, [c_void_p, c_int, c_int, c_int, c_int, c_int, c_int, c_float, c_void_p, c_void_p,
                                         c_int, c_void_p, c_int, c_int, c_void_p]),
     "me_build_proposals": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p, c_int, c_float,

@@ -142,3 +142,62 @@ int me_device_info(int* sm_count, int* cc_major, int* cc_minor) {
 }
 
 }  // extern "C"
+
+// ---- stream memory operations + peer copies (millieye_b200/dist.py::PeerGather) ----------------------------------------
+extern "C" {
+
+// Blocks `stream` (no SM is used) until *(volatile uint32*)addr >= value.  addr: 4-byte aligned device memory of the current
+// device.  The flag is typically written by another GPU (me_peer_copy / me_stream_write_value32 on the peer's stream).
+int me_stream_wait_value32(const void* addr, unsigned int value, me_stream_t stream) {
+  using namespace me;
+  typedef CUresult (*wait_fn)(CUstream, CUdeviceptr, cuuint32_t, unsigned int);
+  static wait_fn fn = reinterpret_cast<wait_fn>(driver_symbol("cuStreamWaitValue32"));
+  if (!fn) return fail(ME_ERR_CUDA, "cuStreamWaitValue32 entry point not available");
+  ME_REQUIRE(addr && (reinterpret_cast<uintptr_t>(addr) & 3) == 0, "stream_wait_value32: bad address");
+  const CUresult r = fn(static_cast<CUstream>(stream), reinterpret_cast<CUdeviceptr>(addr), value, CU_STREAM_WAIT_VALUE_GEQ);
+  if (r != CUDA_SUCCESS) return fail(ME_ERR_CUDA, "cuStreamWaitValue32 failed (%d)", static_cast<int>(r));
+  return ME_OK;
+}
+
+// Stream-ordered 4-byte store without a kernel.
+int me_stream_write_value32(void* addr, unsigned int value, me_stream_t stream) {
+  using namespace me;
+  typedef CUresult (*write_fn)(CUstream, CUdeviceptr, cuuint32_t, unsigned int);
+  static write_fn fn = reinterpret_cast<write_fn>(driver_symbol("cuStreamWriteValue32"));
+  if (!fn) return fail(ME_ERR_CUDA, "cuStreamWriteValue32 entry point not available");
+  ME_REQUIRE(addr && (reinterpret_cast<uintptr_t>(addr) & 3) == 0, "stream_write_value32: bad address");
+  const CUresult r = fn(static_cast<CUstream>(stream), reinterpret_cast<CUdeviceptr>(addr), value, CU_STREAM_WRITE_VALUE_DEFAULT);
+  if (r != CUDA_SUCCESS) return fail(ME_ERR_CUDA, "cuStreamWriteValue32 failed (%d)", static_cast<int>(r));
+  return ME_OK;
+}
+
+// Lets the CURRENT device read and write allocations of `peer_device` directly (NVLink / PCIe peer-to-peer).  Without it a
+// copy into a peer's IPC-mapped buffer is staged through the host.  Already enabled / same device: ME_OK.
+int me_peer_enable(int peer_device) {
+  using namespace me;
+  int cur = -1;
+  ME_CUDA(cudaGetDevice(&cur));
+  if (cur == peer_device) return ME_OK;
+  int can = 0;
+  ME_CUDA(cudaDeviceCanAccessPeer(&can, cur, peer_device));
+  if (!can) return fail(ME_ERR_UNSUPPORTED, "device %d cannot access device %d directly", cur, peer_device);
+  const cudaError_t e = cudaDeviceEnablePeerAccess(peer_device, 0);
+  if (e == cudaErrorPeerAccessAlreadyEnabled) {
+    (void)cudaGetLastError();
+    return ME_OK;
+  }
+  ME_CUDA(e);
+  return ME_OK;
+}
+
+// cudaMemcpyAsync between two device allocations that may live on different GPUs (unified addressing + peer access, e.g. a
+// buffer of another process opened through CUDA IPC): a copy-engine transfer over NVLink, ordered on `stream` only.
+int me_peer_copy(void* dst, const void* src, size_t bytes, me_stream_t stream) {
+  using namespace me;
+  ME_REQUIRE(dst && src, "peer_copy: null argument");
+  if (bytes == 0) return ME_OK;
+  ME_CUDA(cudaMemcpyAsync(dst, src, bytes, cudaMemcpyDefault, static_cast<cudaStream_t>(stream)));
+  return ME_OK;
+}
+
+}  // extern "C"

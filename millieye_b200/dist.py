@@ -138,3 +138,74 @@ def all_reduce_gradients(params, group=None, average=False):
             p.grad.copy_(g)
         off += n
     return off
+
+
+class PeerGather:
+    """All-gather of equal-sized flat fp32 shards over NVLink peer memory WITHOUT a kernel.
+
+    The persistent convolution kernels hold every SM (one 227 KB CTA each), so an NCCL all-gather kernel launched next to
+    them waits until they leave and then delays the next one: ~90 us per step at any N > 1 (profiles/round2).  Here every
+    rank owns `depth` receive buffers of world x numel floats and one arrival flag per source rank, exposes them to its
+    peers through CUDA IPC once, and per step k (all on the caller's stream, copy engines and stream memory operations
+    only):
+        1. waits until every peer has pushed step k - depth + 1 (its reads of the slot about to be overwritten are
+           behind that push in its stream order),
+        2. copies its shard into slot k % depth of its own buffer and of every peer's (me_peer_copy),
+        3. stores k + 1 into a local word and copies that word onto flag[rank] of every peer (stream order = arrival order),
+        4. waits until its own flags of all peers are >= k + 1 (me_stream_wait_value32).
+    gather() returns a (world, numel) view of the slot; it stays valid for depth - 1 further calls.  Pushes precede
+    waits on every rank, so the exchange cannot deadlock; a rank can run at most `depth` steps ahead of the slowest.
+
+    MEASURED (2 x B200, tools/peer_probe.py, 2.2 MB shards): correct, but NOT faster - a blocked cuStreamWaitValue32 is
+    re-polled at a coarse interval (0.37 ms per exchange against 0.03 ms for ncclAllGather) and delays work queued on the
+    process's other streams (a matmul loop next to it went from 0.67 to 1.29 ms per step).  DetectPipeline therefore keeps
+    the NCCL collective as its default and offers this class as gather="peer" only."""
+
+    def __init__(self, numel, depth, device, group=None):
+        from torch.multiprocessing.reductions import reduce_tensor
+        self.group = group
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        self.numel, self.depth, self.device = int(numel), max(2, int(depth)), torch.device(device)
+        self.step = 0
+        with torch.cuda.device(self.device):
+            self.data = torch.zeros((self.depth, self.world, self.numel), dtype=torch.float32, device=self.device)
+            self.flags = torch.zeros((self.world,), dtype=torch.int32, device=self.device)
+            self.ticks = torch.zeros((2 * self.depth,), dtype=torch.int32, device=self.device)
+            torch.cuda.synchronize(self.device)
+        mine = (reduce_tensor(self.data), reduce_tensor(self.flags))
+        every = [None] * self.world
+        dist.all_gather_object(every, mine, group=group)
+        self.peer_data, self.peer_flags = {}, {}
+        for p, (d, f) in enumerate(every):
+            if p != self.rank:
+                self.peer_data[p] = d[0](*d[1])       # rebuild_cuda_tensor: opens the peer's allocation (cudaIpcOpenMemHandle)
+                self.peer_flags[p] = f[0](*f[1])
+        from . import _lib
+        with torch.cuda.device(self.device):           # direct NVLink access from this GPU to every peer's buffers
+            for p, buf in self.peer_data.items():
+                _lib.check(_lib.lib().me_peer_enable(int(buf.device.index)), "me_peer_enable")
+        dist.barrier(group=group)                      # nobody pushes before every rank has opened every buffer
+
+    def gather(self, shard):
+        from . import _lib
+        from ._lib import check, ptr, stream_ptr
+        L = _lib.lib()
+        assert shard.is_cuda and shard.dtype == torch.float32 and shard.is_contiguous() and shard.numel() == self.numel
+        k, st = self.step, stream_ptr()
+        self.step += 1
+        slot = k % self.depth
+        nbytes = self.numel * 4
+        if k >= self.depth:
+            for p in self.peer_flags:
+                # step j stores j + 1: the peer has pushed step k - depth + 1, i.e. is done with step k - depth's slot
+                check(L.me_stream_wait_value32(self.flags[p:p + 1].data_ptr(), k - self.depth + 2, st), "me_stream_wait_value32")
+        check(L.me_peer_copy(self.data[slot, self.rank].data_ptr(), ptr(shard), nbytes, st), "me_peer_copy")
+        for p, buf in self.peer_data.items():
+            check(L.me_peer_copy(buf[slot, self.rank].data_ptr(), ptr(shard), nbytes, st), "me_peer_copy")
+        tick = self.ticks[k % (2 * self.depth):k % (2 * self.depth) + 1]
+        check(L.me_stream_write_value32(tick.data_ptr(), k + 1, st), "me_stream_write_value32")
+        for p, fl in self.peer_flags.items():
+            check(L.me_peer_copy(fl[self.rank:self.rank + 1].data_ptr(), tick.data_ptr(), 4, st), "me_peer_copy")
+        for p in self.peer_flags:
+            check(L.me_stream_wait_value32(self.flags[p:p + 1].data_ptr(), k + 1, st), "me_stream_wait_value32")
+        return self.data[slot]

@@ -240,7 +240,12 @@ class DetectPipeline:
 
     Records live in a ring of `depth` (default 4) per plan: a record's buffers are reused by the depth-th submit after
     it, and that submit first waits (on the host) until the record has completed, so a caller may keep up to `depth`
-    batches in flight; a record must be consumed before `depth` further submits are made."""
+    batches in flight; a record must be consumed before `depth` further submits are made.
+
+    gather: False | True (one all_gather_into_tensor per batch) | "peer" (dist.PeerGather: the shards are pushed into the
+    peers' buffers with copy engines over NVLink, no kernel competes with the convolutions for SMs).  With gather the
+    record's det / count are views of the gathered buffer, shaped (world, n_local, max_det, 7 + C) / (world, n_local)
+    and read on the pipeline's second stream (record.wait() first when reading from another stream)."""
 
     class Record:
         def __init__(self, nms):
@@ -250,9 +255,11 @@ class DetectPipeline:
             body = nms.det.numel()
             self.host_det = self.host_flat[:body].view(nms.det.shape)
             self.host_cnt = self.host_flat[body:].view(torch.int32)
-            self.host_all = None          # gathered detections of every rank (gather=True, readback=True)
+            self.host_all = None          # gathered detections of every rank (gather, readback=True): (det, count) views
+            self.host_all_flat = None     # of this pinned (world, rows + counts) buffer
             self.gather_out = None
             self.done = torch.cuda.Event()
+            self.nms_done = torch.cuda.Event()   # the detector's output slot is free again (before gather / read-back)
             self.pending = False
 
         def wait(self):
@@ -264,6 +271,7 @@ class DetectPipeline:
         self.net, self.conf_thresh, self.nms_thresh, self.max_det, self.gather = net, conf_thresh, nms_thresh, max_det, gather
         self.host_all = host_all    # readback=True also copies the gathered batch of every rank to this rank's host
         self.depth = max(2, int(depth))
+        self._peer = {}      # plan -> dist.PeerGather (gather="peer")
         self._rings = {}     # plan -> [records], round robin
         self._next = {}
         self._side = None
@@ -284,6 +292,13 @@ class DetectPipeline:
         rec.pending = True
         return rec
 
+    def _peer_gather(self, plan, numel, dev):
+        pg = self._peer.get(id(plan))
+        if pg is None or pg.numel != numel:
+            from .dist import PeerGather
+            pg = self._peer[id(plan)] = PeerGather(numel, self.depth, dev)
+        return pg
+
     def submit(self, x, readback=False):
         plan = self.net.forward_device(x, decode=False)
         dev = plan.device
@@ -297,22 +312,29 @@ class DetectPipeline:
                 ops.filter_nms(plan.yolo_out, self.conf_thresh, self.nms_thresh, self.max_det, xyxy_inplace=True,
                                buffers=rec.nms)
                 rec.det, rec.count = rec.nms.det, rec.nms.count
-                if self.gather:
-                    from .dist import gather_detections
+                rec.nms_done.record()     # later forwards only wait for this: the collective and the host copies read
+                if self.gather:           # the record's own buffers and stay off the convolutions' critical path
                     import torch.distributed as tdist
-                    if rec.gather_out is None:     # the record owns its gather output: nothing is copied or concatenated
-                        rec.gather_out = torch.empty((tdist.get_world_size() * rec.nms.flat.numel(),), dtype=torch.float32,
-                                                     device=dev)
-                    rec.det, rec.count = gather_detections(rec.nms.det, rec.nms.count, packed=rec.nms.flat,
-                                                           out=rec.gather_out)
+                    world, flat = tdist.get_world_size(), rec.nms.flat
+                    if self.gather == "peer":      # copy engines + stream memory operations over peer memory: no kernel
+                        g = self._peer_gather(plan, flat.numel(), dev).gather(flat)
+                    else:                          # one NCCL / gloo collective into the record's own output buffer
+                        if rec.gather_out is None:
+                            rec.gather_out = torch.empty((world * flat.numel(),), dtype=torch.float32, device=dev)
+                        tdist.all_gather_into_tensor(rec.gather_out, flat)
+                        g = rec.gather_out.view(world, flat.numel())
+                    body = rec.nms.det.numel()
+                    # views of the gathered buffer (rank-major; a rank's rows are followed by its counts): no copy
+                    rec.det = g[:, :body].view(world, *rec.nms.det.shape)
+                    rec.count = g[:, body:].view(torch.int32)
                 if readback:
                     rec.host_flat.copy_(rec.nms.flat, non_blocking=True)      # this rank's shard: one copy
                     if self.gather and self.host_all:
-                        if rec.host_all is None:
-                            rec.host_all = (torch.empty_like(rec.det, device="cpu").pin_memory(),
-                                            torch.empty_like(rec.count, device="cpu").pin_memory())
-                        rec.host_all[0].copy_(rec.det, non_blocking=True)      # and the whole batch
-                        rec.host_all[1].copy_(rec.count, non_blocking=True)
+                        if rec.host_all_flat is None:
+                            rec.host_all_flat = torch.empty(tuple(g.shape), dtype=torch.float32).pin_memory()
+                            rec.host_all = (rec.host_all_flat[:, :body].view(world, *rec.nms.det.shape),
+                                            rec.host_all_flat[:, body:].view(torch.int32))
+                        rec.host_all_flat.copy_(g, non_blocking=True)          # and the whole batch: one copy
                 rec.done.record()
-            plan.hold_output(rec.done)
+            plan.hold_output(rec.nms_done)
         return rec
