@@ -41,6 +41,7 @@ struct ThinParams {
   const float* bias;
   int M, H, W, Ho, Wo, in_pitch, stride;
   int tiles, act, has_res;
+  int dbg;              // ME_THIN_DBG attribution bits: 1 no output stores, 2 no input copies, 4 no MMAs
   unsigned long long* debug;
 };
 
@@ -182,7 +183,8 @@ conv_thin_kernel(const __grid_constant__ CUtensorMap tmC, const __grid_constant_
             const bool ok = yok && ix >= 0 && ix < p.W;
             // cp.async: the copies of up to STAGES filter rows are in flight per thread, no registers held; a pixel
             // outside the image is zero-filled (the source address is then only a placeholder)
-            ptx::cp_async_16(dst + s * (kBM * ROWB), ok ? line + static_cast<size_t>(ix) * p.in_pitch : p.x, ok);
+            if (!(p.dbg & 2))
+              ptx::cp_async_16(dst + s * (kBM * ROWB), ok ? line + static_cast<size_t>(ix) * p.in_pitch : p.x, ok);
           }
         }
         ptx::cp_async_mbar_arrive_noinc(&full_bar[stage]);
@@ -213,7 +215,7 @@ conv_thin_kernel(const __grid_constant__ CUtensorMap tmC, const __grid_constant_
             for (int k = 0; k < CIN / 16; ++k) {
               const uint64_t adesc = ptx::make_kmajor_desc(a_addr + s * (kBM * ROWB) + k * 32, ROWB);
               const uint64_t bdesc = ptx::make_kmajor_desc(w_addr + (r * 3 + s) * (COUT * ROWB) + k * 32, ROWB);
-              ptx::umma_f16_ss(d_tmem, adesc, bdesc, idesc, (r | s | k) != 0 ? 1u : 0u);
+              if (!(p.dbg & 4)) ptx::umma_f16_ss(d_tmem, adesc, bdesc, idesc, (r | s | k) != 0 ? 1u : 0u);
             }
           }
           ptx::umma_commit(&empty_bar[stage]);
@@ -301,7 +303,7 @@ conv_thin_kernel(const __grid_constant__ CUtensorMap tmC, const __grid_constant_
       ptx::fence_proxy_async_smem();
       ptx::named_bar_sync(bar_id, kEpiThreads);
       if (leader) {
-        ptx::tma_store_2d(&tmC, stg, 0, tile * kBM);
+        if (!(p.dbg & 1)) ptx::tma_store_2d(&tmC, stg, 0, tile * kBM);
         ptx::tma_store_commit();
         const int next = tile + 2 * gridDim.x;
         if (p.has_res && next < p.tiles) {
@@ -339,6 +341,12 @@ int launch_thin(const me_conv_desc* d, const void* x, const void* w, const float
   p.tiles = ceil_div(p.M, kBM);
   p.act = d->act;
   p.has_res = (d->res_pitch > 0 && residual != nullptr) ? 1 : 0;
+  static int dbg = -1;
+  if (dbg < 0) {
+    const char* e = getenv("ME_THIN_DBG");
+    dbg = e ? atoi(e) : 0;
+  }
+  p.dbg = dbg;
   int rc = conv_ensure_debug_word();
   if (rc != ME_OK) return rc;
   p.debug = conv_debug_word();

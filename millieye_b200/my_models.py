@@ -222,6 +222,37 @@ class _FusionPlan:
                                 self.img_boxes, self.rois, self.counts, self.cap)
         self.launches += 3
 
+    def run_graphed(self, name, key, fn, enabled=True):
+        """fn() enqueues kernels of this plan on the current stream.  First use of (name, key): run it as is (one-time
+        initialisation inside the library must not happen under capture); second use: capture it into a CUDA graph;
+        afterwards: replay.  Every shape is fixed by the plan and row counts live on the device, so a graph serves
+        every batch; `key` holds the host scalars baked into the launches (thresholds, detector output slot)."""
+        if not enabled:
+            return fn()
+        cache = self.__dict__.setdefault("_graphs", {})
+        state = cache.get((name, key))
+        if state is None:
+            if len(cache) >= 16:        # thresholds that change every call: no point in capturing
+                return fn()
+            cache[(name, key)] = "warm"
+            return fn()
+        if state == "warm":
+            from .engine import capture_graph
+            torch.cuda.synchronize(self.device)
+            state = cache[(name, key)] = capture_graph(fn)
+        state.replay()
+
+    def tail(self, conf_thresh, class_idx, thr_img, thr_radar, regress_boxes, graphs=True):
+        """NMS -> proposals (radar-box count from self.radar_n_dev) -> RoI gathers -> heads -> output rows, as one graph
+        per (detector output slot, thresholds)."""
+        key = (self.base._slot, bool(regress_boxes), float(conf_thresh), int(class_idx), float(thr_img), float(thr_radar))
+
+        def body():
+            self.proposals_dev(key[2], key[3])
+            self.heads(key[4], key[5], key[1])
+
+        self.run_graphed("tail", key, body, graphs)
+
     def heads(self, thr_img, thr_radar, regress_boxes):
         n, g, cap = self.n, self.g, self.cap
         ops.roi_gather_bin_major(self.roi_score, n, g, g, 512, 10, 7, 1.0 / 16, self.rois, self.counts, cap, self.crop_img, 512, True)
@@ -322,9 +353,13 @@ class Network(nn.Module):
             if heads_training:
                 return self._train_branch(plan, images, maps, n_radar, targets)
             plan.maps_in.copy_(maps, non_blocking=True)
-            plan.score_maps()
-            plan.proposals(self.conf_thresh, self.class_idx, n_radar)
-            plan.heads(float(self.refine_threshold_img), float(self.refine_threshold_radar), model_mode != 2)
+            plan.radar_n_dev.fill_(n_radar)
+            # the blocking call is bound by the kernels themselves (0.85 ms at batch 32 with or without graphs,
+            # tools/fusion_block_probe.py), so it only replays graphs on request; FusionPipeline always does
+            graphs = os.environ.get("ME_FUSION_GRAPHS_BLOCKING", "0") == "1"
+            plan.run_graphed("score", (), plan.score_maps, graphs)
+            plan.tail(self.conf_thresh, self.class_idx, self.refine_threshold_img, self.refine_threshold_radar, model_mode != 2,
+                      graphs)
             self.refinement_head.count += 1
             k = int(plan.out_count.item())                               # the forward's only host sync
             output = plan.out[:k].clone()
@@ -505,24 +540,6 @@ class FusionPipeline:
         # all their shapes are fixed by the plan, row counts live on the device
         self.use_cuda_graph = (os.environ.get("ME_FUSION_GRAPHS", "1") != "0") if use_cuda_graph is None else bool(use_cuda_graph)
 
-    def _run(self, plan, name, key, fn):
-        """fn() enqueues kernels on the current stream.  First use of (name, key): run it as is (one-time initialisation
-        inside the library must not happen under capture); second use: capture it; afterwards: replay."""
-        if not self.use_cuda_graph:
-            return fn()
-        cache = plan.__dict__.setdefault("_pipe_graphs", {})
-        state = cache.get((name, key))
-        if state is None:
-            if len(cache) >= 16:        # thresholds that change every call: no point in capturing
-                return fn()
-            cache[(name, key)] = "warm"
-            return fn()
-        if state == "warm":
-            from .engine import capture_graph
-            torch.cuda.synchronize(plan.device)
-            state = cache[(name, key)] = capture_graph(fn)
-        state.replay()
-
     def submit(self, images, maps, radar_boxes_location, model_mode=0, readback=True):
         m = self.model
         if model_mode == 1:
@@ -556,19 +573,13 @@ class FusionPipeline:
                 plan.radar_dev[:n_radar].copy_(radar_boxes_location, non_blocking=True)
             plan.radar_n_dev.fill_(n_radar)
             plan.maps_in.copy_(maps, non_blocking=True)
-            self._run(plan, "score", (), plan.score_maps)
+            plan.run_graphed("score", (), plan.score_maps, self.use_cuda_graph)
             main = torch.cuda.current_stream()
             self._side.wait_stream(main)
             with torch.cuda.stream(self._side):
                 plan_b.run_decode(base.use_cuda_graph)
-                thr = (float(m.conf_thresh), int(m.class_idx), float(m.refine_threshold_img), float(m.refine_threshold_radar))
-
-                def tail(thr=thr, regress=model_mode != 2):
-                    plan.proposals_dev(thr[0], thr[1])
-                    plan.heads(thr[2], thr[3], regress)
-
-                # the NMS reads the base plan's CURRENT output slot: one graph per slot and threshold set
-                self._run(plan, "tail", (plan_b._slot, model_mode != 2) + thr, tail)
+                plan.tail(m.conf_thresh, m.class_idx, m.refine_threshold_img, m.refine_threshold_radar, model_mode != 2,
+                          self.use_cuda_graph)
                 if readback:
                     rec.host_flat.copy_(plan.out_flat, non_blocking=True)
                 rec.done.record()
