@@ -87,6 +87,15 @@ typedef struct me_conv_desc {
 int me_conv_gemm(const me_conv_desc* d, const void* x, const void* w_packed, const float* bias,
                  const void* residual, void* y, me_stream_t stream);
 
+/* me_conv_gemm for a thin 3x3 / stride-1 layer FOLLOWED BY MaxPool2d(2, 2) (blocks 2-3, 4-5 of yolov3-tiny*.cfg,
+ * models.py:22-51) in one kernel: the pool runs on the epilogue's registers, y is the pooled (n, h/2, w/2, out_pitch)
+ * tensor and the full-resolution activation is never written.  Bit-identical to me_conv_gemm + me_maxpool2.
+ * me_conv_pool_supported: 1 if the layer qualifies (cin 16 / 32, cout 32 / 64, no residual, fp16 output, w % 8 == 0,
+ * h even), else 0 and me_conv_pool returns ME_ERR_UNSUPPORTED. */
+int me_conv_pool_supported(const me_conv_desc* d);
+int me_conv_pool(const me_conv_desc* d, const void* x, const void* w_packed, const float* bias, void* y_pooled,
+                 me_stream_t stream);
+
 /* me_conv_gemm with a workspace for the split-K tail: layers whose last wave of 256 x 256 tiles would leave most SM pairs
  * idle cut those tiles along K; partial sums and arrival counters live in `workspace` (zero-filled by the caller once,
  * me_conv_workspace_bytes() long, 256-byte aligned; NULL: no split).  The workspace belongs to the call, not to the

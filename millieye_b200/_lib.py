@@ -77,6 +77,8 @@ SIGNATURES = {
     "me_fold_first_weights": (c_int, [c_void_p] * 6 + [c_float, c_int, c_int, c_void_p, c_void_p, c_void_p]),
     "me_conv_first": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p] + [c_int] * 7 + [c_void_p]),
     "me_conv_first_tc": (c_int, [c_void_p] * 5 + [c_int] * 7 + [c_void_p]),
+    "me_conv_pool_supported": (c_int, [POINTER(ConvDesc)]),
+    "me_conv_pool": (c_int, [POINTER(ConvDesc), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "me_conv_first_tc_pool": (c_int, [c_void_p] * 5 + [c_int] * 7 + [c_void_p]),
     "me_maxpool2": (c_int, [c_void_p, c_void_p] + [c_int] * 7 + [c_void_p]),
     "me_upsample2": (c_int, [c_void_p, c_void_p] + [c_int] * 6 + [c_void_p]),

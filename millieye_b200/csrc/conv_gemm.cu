@@ -26,6 +26,8 @@ int conv_gemm_pair(int bn, const me_conv_desc* d, const void* x, const void* w, 
 size_t conv_pair_workspace_bytes();
 bool conv_thin_enabled();                          // conv_thin.cu
 bool conv_thin_supported(const me_conv_desc* d);
+bool conv_thin_pool_supported(const me_conv_desc* d);
+int conv_thin_pool(const me_conv_desc* d, const void* x, const void* w, const float* bias, void* y, cudaStream_t stream);
 int conv_thin(const me_conv_desc* d, const void* x, const void* w, const float* bias, const void* residual, void* y,
               cudaStream_t stream);
 
@@ -701,6 +703,21 @@ int me_conv_set_trace(unsigned long long* dev_words) {
 int me_debug_status(unsigned long long* host_word) {
   if (host_word) *host_word = me::g_debug_host ? *me::g_debug_host : 0ull;
   return ME_OK;
+}
+
+int me_conv_pool_supported(const me_conv_desc* d) { return (d && me::conv_thin_pool_supported(d)) ? 1 : 0; }
+
+// 3x3 / stride-1 conv + bias + activation followed by MaxPool2d(2, 2) in one kernel (thin layers: 16 / 32 input channels,
+// 32 / 64 filters); y is the pooled (n, h/2, w/2, out_pitch) tensor.
+int me_conv_pool(const me_conv_desc* d, const void* x, const void* w_packed, const float* bias, void* y, me_stream_t stream_) {
+  using namespace me;
+  ME_REQUIRE(d && x && w_packed && bias && y, "conv_pool: null argument");
+  ME_REQUIRE(d->n > 0 && d->h > 0 && d->w > 0, "conv_pool: empty input");
+  if (!conv_thin_pool_supported(d))
+    return fail(ME_ERR_UNSUPPORTED, "conv_pool: unsupported layer (3x3 stride 1, cin 16/32, cout 32/64, no residual, "
+                "w %% 8 == 0, h even); run me_conv_gemm + me_maxpool2");
+  ME_REQUIRE(d->out_pitch >= d->cout && d->out_pitch % 8 == 0, "conv_pool: bad out_pitch %d", d->out_pitch);
+  return conv_thin_pool(d, x, w_packed, bias, y, static_cast<cudaStream_t>(stream_));
 }
 
 static int conv_dispatch(const me_conv_desc* d, const void* x, const void* w_packed, const float* bias,

@@ -12,8 +12,14 @@
 // The layer's whole weight slab (<= 36 KB) stays in shared memory, one swizzled [COUT][CIN] tile per tap.  Warp roles:
 //   warps 0-7   producers (256 threads: lanes run over a pixel's 16-byte chunks first, then over tile rows)
 //   warp 8      TMEM owner + MMA issuer: 3 x CIN/16 tcgen05.mma (M=128, N=COUT, K=16) per stage, commit per stage
-//   warps 9-16  two epilogue groups alternating tiles, as in conv_gemm.cu: tcgen05.ld -> +bias -> activation ->
-//               (+ residual, TMA-prefetched into the staging tile) -> fp16 -> swizzled staging -> TMA store
+//   warps 9-16  two epilogue groups alternating tiles over FOUR TMEM accumulators: tcgen05.ld -> +bias -> activation ->
+//               (+ residual, loaded straight from global memory before the accumulator is awaited) -> fp16 -> 32-byte
+//               global stores, a lane per output pixel (a warp's rows are one contiguous span).  No staging tile, no
+//               block barrier, no TMA store: with 3 K stages per tile the per-tile hand-shakes of the staged epilogue
+//               were half of the kernel's time (ME_THIN_DBG attribution, tools/thin_probe2.py).
+//   POOL        (stride 1, the 2x2 / stride-2 max-pool that follows the layer in the tiny cfgs): a tile is a block of
+//               bw x 128/bw pixels (bw = 16 or 8), so a warp's 32 rows hold whole 2x2 windows (shfl_xor 1 and bw); the
+//               pooled pixels are written instead of the conv output.  max commutes with the fp16 rounding.
 // Replaces the same reference lines as conv_gemm.cu (yolov3/models.py:22-41,252,258-260) for modules 1 and 3 of
 // Darknet-53 and the first two 3x3 layers after the pools of the tiny cfgs.
 #include "common.cuh"
@@ -41,24 +47,28 @@ struct ThinParams {
   const float* bias;
   int M, H, W, Ho, Wo, in_pitch, stride;
   int tiles, act, has_res;
+  const __half* res;    // residual rows (res_pitch halves apart) or nullptr
+  __half* y;            // output rows (out_pitch halves apart); POOL: the pooled tensor
+  int out_pitch, res_pitch;
+  int pool_bw;          // POOL: tile block width (16 or 8); 0 otherwise
   int dbg;              // ME_THIN_DBG attribution bits: 1 no output stores, 2 no input copies, 4 no MMAs
   unsigned long long* debug;
 };
 
 template <int CIN, int COUT>
 struct TCfg {
-  static constexpr int KROW = 3 * CIN;                 // K of one stage (one filter row)
+  static constexpr int RPS = CIN == 16 ? 3 : 1;        // filter rows per pipeline stage: the whole 3x3 window when it is
+                                                       // 36 KB (16 channels) - one barrier round trip per tile, not three
+  static constexpr int KROW = RPS * 3 * CIN;           // K of one stage
   static constexpr int CHUNKS = KROW / 8;              // 16-byte chunks per tile row and stage
   static constexpr int STAGE_BYTES = CHUNKS * kBM * 16;
   static constexpr int W_BYTES = COUT * 9 * CIN * 2;
-  static constexpr int STAGING_BYTES = kBM * COUT * 2;  // per epilogue group; rows of 64 (COUT=32) or 128 bytes
-  static constexpr int ROW_BYTES = COUT * 2;
-  static constexpr int SWZ_BITS = ROW_BYTES == 128 ? 3 : 2;
-  static constexpr int TAIL_BYTES = 2 * COUT * 4 + 32 * 8 + 16;
-  static constexpr int FIXED = 1024 + W_BYTES + 2 * STAGING_BYTES + TAIL_BYTES;
+  static constexpr int ACCS = 4;                        // TMEM accumulators in flight
+  static constexpr int TAIL_BYTES = COUT * 4 + 32 * 8 + 16;
+  static constexpr int FIXED = 1024 + W_BYTES + TAIL_BYTES;
   static constexpr int STAGES = (227 * 1024 - FIXED) / STAGE_BYTES > 8 ? 8 : (227 * 1024 - FIXED) / STAGE_BYTES;
   static constexpr int SMEM = FIXED + STAGES * STAGE_BYTES;
-  static constexpr int TMEM_COLS = 2 * COUT <= 64 ? 64 : 128;
+  static constexpr int TMEM_COLS = ACCS * COUT <= 128 ? 128 : 256;
   static_assert(CIN == 16 || CIN == 32, "thin conv: 16 or 32 input channels");
   static_assert(COUT == 32 || COUT == 64, "thin conv: 32 or 64 filters");
   static_assert(STAGES >= 3, "thin conv: pipeline too shallow");
@@ -88,39 +98,62 @@ __device__ __forceinline__ uint32_t swz_off(int row, int c8) {
   return off;
 }
 
-template <int CIN, int COUT>
+// Output pixel of one tile row, advanced from tile to tile without divisions (17 warps doing four runtime div/mod per tile
+// were a third of the kernel's instruction issue).  Flat tiles: pixel index tile * 128 + i decomposed over (Wo, Ho).
+// POOL tiles: the BLOCK index decomposed over (blocks per row, block rows per image); the row's offset inside the block
+// is added by the caller.
+struct PixIter {
+  int a, b, c;        // flat: ox, oy, img;  pool: bx, by, img
+  int sa, sb, sc, A, B;
+  __device__ __forceinline__ void init(int first, int step, int A_, int B_) {
+    A = A_;
+    B = B_;
+    a = first % A;
+    int t = first / A;
+    b = t % B;
+    c = t / B;
+    sa = step % A;
+    t = step / A;
+    sb = t % B;
+    sc = t / B;
+  }
+  __device__ __forceinline__ void next() {
+    a += sa;
+    if (a >= A) { a -= A; ++b; }
+    b += sb;
+    if (b >= B) { b -= B; ++c; }
+    c += sc;
+  }
+};
+
+template <int CIN, int COUT, bool POOL>
 __global__ void __launch_bounds__(kThreads, 1)
-conv_thin_kernel(const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmR, const ThinParams p) {
+conv_thin_kernel(const ThinParams p) {
   using C = TCfg<CIN, COUT>;
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   constexpr int ROWB = CIN * 2;                          // bytes of one tile row (one pixel's channels / one filter's tap)
   uint8_t* s_w = smem;                                   // 9 taps x [COUT][ROWB] swizzled
   uint8_t* s_a = s_w + C::W_BYTES;                        // STAGES x 3 taps x [128][ROWB] swizzled
-  uint8_t* staging = s_a + C::STAGES * C::STAGE_BYTES;    // 2 x [128][ROW_BYTES] swizzled
-  float* s_bias = reinterpret_cast<float*>(staging + 2 * C::STAGING_BYTES);  // [2][COUT]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(s_bias + 2 * COUT);
+  float* s_bias = reinterpret_cast<float*>(s_a + C::STAGES * C::STAGE_BYTES);  // [COUT]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_bias + COUT);
   uint64_t* full_bar = bars;            // [8]
   uint64_t* empty_bar = bars + 8;       // [8]
-  uint64_t* tmem_full = bars + 16;      // [2]
-  uint64_t* tmem_empty = bars + 18;     // [2]
-  uint64_t* res_full = bars + 20;       // [2]
-  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 22);
+  uint64_t* tmem_full = bars + 16;      // [4]
+  uint64_t* tmem_empty = bars + 20;     // [4]
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(bars + 24);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   ptx::pdl_launch_dependents();
   if (warp == kMmaWarp) {
     if (ptx::elect_one()) {
-      ptx::prefetch_tmap(&tmC);
-      if (p.has_res) ptx::prefetch_tmap(&tmR);
       for (int s = 0; s < C::STAGES; ++s) {
-        ptx::mbar_init(&full_bar[s], kProdThreads);
+        ptx::mbar_init(&full_bar[s], kProdThreads / 32);   // one arrival per producer warp
         ptx::mbar_init(&empty_bar[s], 1);
       }
-      for (int a = 0; a < 2; ++a) {
+      for (int a = 0; a < C::ACCS; ++a) {
         ptx::mbar_init(&tmem_full[a], 1);
         ptx::mbar_init(&tmem_empty[a], 4);
-        ptx::mbar_init(&res_full[a], 1);
       }
       ptx::fence_mbar_init();
     }
@@ -135,12 +168,37 @@ conv_thin_kernel(const __grid_constant__ CUtensorMap tmC, const __grid_constant_
     *reinterpret_cast<uint4*>(s_w + tap * (COUT * ROWB) + swz_off<ROWB>(o, c8)) =
         __ldg(reinterpret_cast<const uint4*>(p.w + static_cast<size_t>(o) * 9 * CIN + k8 * 8));
   }
+  for (int i = threadIdx.x; i < COUT; i += kThreads) s_bias[i] = p.bias[i];
   ptx::fence_proxy_async_smem();
   ptx::tc_fence_before();
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
   ptx::pdl_wait();
+
+  // Tile row i of a tile -> output pixel.  Flat tiles: pixel tile * 128 + i.  POOL tiles: block (img, by, bx) of
+  // bw x 128/bw pixels, row i = (i / bw, i % bw) inside it (W % bw == 0; the last block row of an image may be partial).
+  const int n_img = p.M / (p.Ho * p.Wo);
+  const int bw_log = p.pool_bw == 16 ? 4 : 3;
+  auto iter_init = [&](PixIter& it, int first_tile, int tile_step, int i) {
+    if constexpr (POOL) {
+      it.init(first_tile, tile_step, p.Wo >> bw_log, (p.Ho + (kBM >> bw_log) - 1) / (kBM >> bw_log));
+    } else {
+      it.init(first_tile * kBM + i, tile_step * kBM, p.Wo, p.Ho);
+    }
+  };
+  auto iter_pixel = [&](const PixIter& it, int i, int& ox, int& oy, int& img) -> bool {
+    img = it.c;
+    if constexpr (POOL) {
+      ox = (it.a << bw_log) + (i & (p.pool_bw - 1));
+      oy = it.b * (kBM >> bw_log) + (i >> bw_log);
+      return oy < p.Ho;
+    } else {
+      ox = it.a;
+      oy = it.b;
+      return img < n_img;
+    }
+  };
 
   if (warp < kMmaWarp) {
     // ------------------------------------------------------------------ im2col producers
@@ -151,45 +209,71 @@ conv_thin_kernel(const __grid_constant__ CUtensorMap tmC, const __grid_constant_
     constexpr int PASSES = kBM / PIX_PER_PASS;        // 2 (CIN 32) or 1 (CIN 16)
     const int c8 = threadIdx.x % CPP;
     const int p0 = threadIdx.x / CPP;
-    uint32_t stage = 0, phase = 0;
+    uint32_t stage = 0, phase = 0, ann = 0;
+    int issued = 0;
+    constexpr int LAG = C::STAGES >= 6 ? 3 : (C::STAGES >= 4 ? 2 : 1);
+    PixIter pit[PASSES];
+#pragma unroll
+    for (int q = 0; q < PASSES; ++q) iter_init(pit[q], blockIdx.x, gridDim.x, p0 + q * PIX_PER_PASS);
     for (int tile = blockIdx.x; tile < p.tiles; tile += gridDim.x) {
       const __half* base[PASSES];
       int ix0[PASSES], iy0[PASSES];
       bool live[PASSES];
 #pragma unroll
       for (int q = 0; q < PASSES; ++q) {
-        const int m = tile * kBM + p0 + q * PIX_PER_PASS;
-        live[q] = m < p.M;
-        const int ox = m % p.Wo;
-        const int t = m / p.Wo;
-        const int oy = t % p.Ho, img = t / p.Ho;
+        int ox, oy, img;
+        live[q] = iter_pixel(pit[q], p0 + q * PIX_PER_PASS, ox, oy, img);
+        pit[q].next();
         ix0[q] = ox * p.stride - 1;
         iy0[q] = oy * p.stride - 1;
         base[q] = p.x + (static_cast<size_t>(img) * p.H * p.W) * p.in_pitch + c8 * 8;
       }
 #pragma unroll 1
-      for (int r = 0; r < 3; ++r) {
+      for (int r0 = 0; r0 < 3; r0 += C::RPS) {
         mbar_wait(&empty_bar[stage], phase ^ 1, p.debug, 0x100u + stage);
         const uint32_t dst0 = ptx::smem_u32(s_a + stage * C::STAGE_BYTES);
 #pragma unroll
-        for (int q = 0; q < PASSES; ++q) {
-          const int iy = iy0[q] + r;
-          const bool yok = live[q] && iy >= 0 && iy < p.H;
-          const __half* line = base[q] + static_cast<size_t>(iy) * p.W * p.in_pitch;
-          const uint32_t dst = dst0 + swz_off<ROWB>(p0 + q * PIX_PER_PASS, c8);
+        for (int rr = 0; rr < C::RPS; ++rr) {
 #pragma unroll
-          for (int s = 0; s < 3; ++s) {
-            const int ix = ix0[q] + s;
-            const bool ok = yok && ix >= 0 && ix < p.W;
-            // cp.async: the copies of up to STAGES filter rows are in flight per thread, no registers held; a pixel
-            // outside the image is zero-filled (the source address is then only a placeholder)
-            if (!(p.dbg & 2))
-              ptx::cp_async_16(dst + s * (kBM * ROWB), ok ? line + static_cast<size_t>(ix) * p.in_pitch : p.x, ok);
+          for (int q = 0; q < PASSES; ++q) {
+            const int iy = iy0[q] + r0 + rr;
+            const bool yok = live[q] && iy >= 0 && iy < p.H;
+            const __half* line = base[q] + static_cast<size_t>(iy) * p.W * p.in_pitch;
+            const uint32_t dst = dst0 + rr * 3 * (kBM * ROWB) + swz_off<ROWB>(p0 + q * PIX_PER_PASS, c8);
+#pragma unroll
+            for (int s = 0; s < 3; ++s) {
+              const int ix = ix0[q] + s;
+              const bool ok = yok && ix >= 0 && ix < p.W;
+              // cp.async: the copies of several stages are in flight per thread, no registers held; a pixel outside the
+              // image is zero-filled (the source address is then only a placeholder)
+              if (!(p.dbg & 2))
+                ptx::cp_async_16(dst + s * (kBM * ROWB), ok ? line + static_cast<size_t>(ix) * p.in_pitch : p.x, ok);
+            }
           }
         }
-        ptx::cp_async_mbar_arrive_noinc(&full_bar[stage]);
+        // A stage is announced LAG stages after its copies were issued: every lane waits until its own copies of that
+        // stage have landed (cp.async.wait_group), makes them visible to the tensor core's proxy (writer-side fence), and
+        // one lane per warp arrives: 8 arrivals per stage instead of 256 cp.async.mbarrier.arrive (measured neutral in
+        // time; kept for the writer-side fence).
+        ptx::cp_async_commit_group();
+        ++issued;
+        if (issued > LAG) {
+          ptx::cp_async_wait_group<LAG>();
+          ptx::fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) ptx::mbar_arrive(&full_bar[ann]);
+          if (++ann == (uint32_t)C::STAGES) ann = 0;
+        }
         if (++stage == (uint32_t)C::STAGES) { stage = 0; phase ^= 1; }
       }
+    }
+    // drain: the last LAG stages
+    ptx::cp_async_wait_group<0>();
+    ptx::fence_proxy_async_smem();
+    __syncwarp();
+    for (int k = issued > LAG ? LAG : issued; k > 0; --k) {
+      if (lane == 0) ptx::mbar_arrive(&full_bar[ann]);
+      if (++ann == (uint32_t)C::STAGES) ann = 0;
     }
   } else if (warp == kMmaWarp) {
     // ------------------------------------------------------------------ MMA issuer
@@ -199,23 +283,23 @@ conv_thin_kernel(const __grid_constant__ CUtensorMap tmC, const __grid_constant_
       uint32_t stage = 0, phase = 0;
       int it = 0;
       for (int tile = blockIdx.x; tile < p.tiles; tile += gridDim.x, ++it) {
-        const int acc = it & 1;
-        mbar_wait(&tmem_empty[acc], ((it >> 1) & 1) ^ 1, p.debug, 0x200u + acc);
+        const int acc = it & (C::ACCS - 1);
+        mbar_wait(&tmem_empty[acc], ((it / C::ACCS) & 1) ^ 1, p.debug, 0x200u + acc);
         ptx::tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * COUT;
 #pragma unroll 1
-        for (int r = 0; r < 3; ++r) {
+        for (int r0 = 0; r0 < 3; r0 += C::RPS) {
           mbar_wait(&full_bar[stage], phase, p.debug, 0x300u + stage);
-          ptx::fence_proxy_async_smem();   // the producers' cp.async writes (generic proxy) -> visible to the tensor core
+          ptx::fence_proxy_async_smem();
           ptx::tc_fence_after();
           const uint32_t a_addr = ptx::smem_u32(s_a + stage * C::STAGE_BYTES);
 #pragma unroll
-          for (int s = 0; s < 3; ++s) {
+          for (int rs = 0; rs < C::RPS * 3; ++rs) {
 #pragma unroll
             for (int k = 0; k < CIN / 16; ++k) {
-              const uint64_t adesc = ptx::make_kmajor_desc(a_addr + s * (kBM * ROWB) + k * 32, ROWB);
-              const uint64_t bdesc = ptx::make_kmajor_desc(w_addr + (r * 3 + s) * (COUT * ROWB) + k * 32, ROWB);
-              if (!(p.dbg & 4)) ptx::umma_f16_ss(d_tmem, adesc, bdesc, idesc, (r | s | k) != 0 ? 1u : 0u);
+              const uint64_t adesc = ptx::make_kmajor_desc(a_addr + rs * (kBM * ROWB) + k * 32, ROWB);
+              const uint64_t bdesc = ptx::make_kmajor_desc(w_addr + (r0 * 3 + rs) * (COUT * ROWB) + k * 32, ROWB);
+              if (!(p.dbg & 4)) ptx::umma_f16_ss(d_tmem, adesc, bdesc, idesc, (r0 | rs | k) != 0 ? 1u : 0u);
             }
           }
           ptx::umma_commit(&empty_bar[stage]);
@@ -229,28 +313,30 @@ conv_thin_kernel(const __grid_constant__ CUtensorMap tmC, const __grid_constant_
     const int g = (warp - (kMmaWarp + 1)) >> 2;
     const int q = warp & 3;                 // TMEM lane quarter (warp index % 4)
     const int row = q * 32 + lane;
-    const int etid = (threadIdx.x - (kProdThreads + 32)) & (kEpiThreads - 1);
-    const bool leader = etid == 0;
-    uint8_t* stg = staging + g * C::STAGING_BYTES;
-    float* bias_s = s_bias + g * COUT;
-    uint64_t* res_bar = &res_full[g];
-    const uint32_t bar_id = kEpiBarrierId + g;
-    auto load_residual = [&](int tile) {
-      ptx::mbar_arrive_expect_tx(res_bar, C::STAGING_BYTES);
-      ptx::tma_load_2d(&tmR, res_bar, stg, 0, tile * kBM);
-    };
-    for (int i = etid; i < COUT; i += kEpiThreads) bias_s[i] = p.bias[i];
-    int tile = blockIdx.x + g * gridDim.x;
-    if (p.has_res && leader && tile < p.tiles) load_residual(tile);
-    for (int lit = 0; tile < p.tiles; ++lit, tile += 2 * gridDim.x) {
-      if (leader && !p.has_res) ptx::tma_store_wait_read0();  // previous store has drained the staging tile
-      ptx::named_bar_sync(bar_id, kEpiThreads);
-      mbar_wait(&tmem_full[g], lit & 1, p.debug, 0x400u + g);
+    constexpr int NV = COUT / 8;            // 16-byte vectors per output row
+    const bool wide = (p.out_pitch & 15) == 0 && (reinterpret_cast<uintptr_t>(p.y) & 31) == 0;
+    int it = g;
+    PixIter eit;
+    iter_init(eit, blockIdx.x + g * gridDim.x, 2 * gridDim.x, row);
+    for (int tile = blockIdx.x + g * gridDim.x; tile < p.tiles; tile += 2 * gridDim.x, it += 2) {
+      const int acc = it & (C::ACCS - 1);
+      int ox, oy, img;
+      const bool live = iter_pixel(eit, row, ox, oy, img);
+      eit.next();
+      const long long pix = (static_cast<long long>(img) * p.Ho + oy) * p.Wo + ox;
+      // the residual row travels while the MMAs of this tile are still running
+      uint4 res[NV];
+      if (p.has_res && live) {
+        const uint4* rp = reinterpret_cast<const uint4*>(p.res + pix * p.res_pitch);
+#pragma unroll
+        for (int j = 0; j < NV; ++j) res[j] = __ldg(rp + j);
+      }
+      mbar_wait(&tmem_full[acc], (it / C::ACCS) & 1, p.debug, 0x400u + acc);
       ptx::tc_fence_after();
-      if (p.has_res) mbar_wait(res_bar, lit & 1, p.debug, 0x500u + g);
-      const uint32_t t_row = tmem_base + g * COUT + (static_cast<uint32_t>(q * 32) << 16);
+      const uint32_t t_row = tmem_base + acc * COUT + (static_cast<uint32_t>(q * 32) << 16);
       constexpr int NCH = COUT / 32;
       uint32_t r[2][32];
+      uint4 o[NV];
       ptx::tmem_ld_32x32b_x32(t_row, r[0]);
 #pragma unroll
       for (int ci = 0; ci < NCH; ++ci) {
@@ -260,7 +346,7 @@ conv_thin_kernel(const __grid_constant__ CUtensorMap tmC, const __grid_constant_
         float v[32];
 #pragma unroll
         for (int j4 = 0; j4 < 8; ++j4) {
-          const float4 b4 = *reinterpret_cast<const float4*>(bias_s + c + 4 * j4);
+          const float4 b4 = *reinterpret_cast<const float4*>(s_bias + c + 4 * j4);
           v[4 * j4 + 0] = __uint_as_float(r[ci & 1][4 * j4 + 0]) + b4.x;
           v[4 * j4 + 1] = __uint_as_float(r[ci & 1][4 * j4 + 1]) + b4.y;
           v[4 * j4 + 2] = __uint_as_float(r[ci & 1][4 * j4 + 2]) + b4.z;
@@ -273,16 +359,11 @@ conv_thin_kernel(const __grid_constant__ CUtensorMap tmC, const __grid_constant_
 #pragma unroll
           for (int j = 0; j < 32; ++j) v[j] = 1.f / (1.f + __expf(-v[j]));
         }
-        const uint32_t rbase = row * C::ROW_BYTES + c * 2;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          uint32_t off = rbase + j * 16;
-          off ^= ((off >> 7) & ((1u << C::SWZ_BITS) - 1)) << 4;
-          uint4* dst = reinterpret_cast<uint4*>(stg + off);
           float* vv = v + 8 * j;
-          if (p.has_res) {
-            const uint4 rr = *dst;
-            const __half2* rh = reinterpret_cast<const __half2*>(&rr);
+          if (p.has_res && live) {
+            const __half2* rh = reinterpret_cast<const __half2*>(&res[ci * 4 + j]);
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
               const float2 f = __half22float2(rh[e]);
@@ -290,29 +371,49 @@ conv_thin_kernel(const __grid_constant__ CUtensorMap tmC, const __grid_constant_
               vv[2 * e + 1] += f.y;
             }
           }
-          uint4 o;
-          __half2* oh = reinterpret_cast<__half2*>(&o);
+          __half2* oh = reinterpret_cast<__half2*>(&o[ci * 4 + j]);
 #pragma unroll
           for (int e = 0; e < 4; ++e) oh[e] = __floats2half2_rn(vv[2 * e], vv[2 * e + 1]);
-          *dst = o;
         }
       }
+      // the accumulator is in registers: hand it back before the stores
       ptx::tc_fence_before();
       __syncwarp();
-      if (lane == 0) ptx::mbar_arrive(&tmem_empty[g]);
-      ptx::fence_proxy_async_smem();
-      ptx::named_bar_sync(bar_id, kEpiThreads);
-      if (leader) {
-        if (!(p.dbg & 1)) ptx::tma_store_2d(&tmC, stg, 0, tile * kBM);
-        ptx::tma_store_commit();
-        const int next = tile + 2 * gridDim.x;
-        if (p.has_res && next < p.tiles) {
-          ptx::tma_store_wait_read0();
-          load_residual(next);
+      if (lane == 0) ptx::mbar_arrive(&tmem_empty[acc]);
+      long long opix = pix;
+      bool writer = live;
+      if constexpr (POOL) {
+        // a warp's 32 rows are 32/bw image rows x bw columns of the block: the 2x2 window of an even (row, column) lane
+        // is lanes +1, +bw, +bw+1
+        const int bw = p.pool_bw;
+#pragma unroll
+        for (int j = 0; j < NV; ++j) {
+          uint32_t* w4 = reinterpret_cast<uint32_t*>(&o[j]);
+#pragma unroll
+          for (int e = 0; e < 4; ++e) {
+            uint32_t u = w4[e];
+            uint32_t n1 = __shfl_xor_sync(0xffffffffu, u, 1);
+            __half2 m2 = __hmax2(*reinterpret_cast<__half2*>(&u), *reinterpret_cast<__half2*>(&n1));
+            u = *reinterpret_cast<uint32_t*>(&m2);
+            uint32_t n2 = __shfl_xor_sync(0xffffffffu, u, bw);
+            m2 = __hmax2(m2, *reinterpret_cast<__half2*>(&n2));
+            w4[e] = *reinterpret_cast<uint32_t*>(&m2);
+          }
+        }
+        writer = live && ((ox | oy) & 1) == 0;
+        opix = (static_cast<long long>(img) * (p.Ho >> 1) + (oy >> 1)) * (p.Wo >> 1) + (ox >> 1);
+      }
+      if (writer && !(p.dbg & 1)) {
+        __half* dst = p.y + opix * p.out_pitch;
+        if (wide) {
+#pragma unroll
+          for (int j = 0; j < NV; j += 2) ptx::st_global_256(dst + j * 8, o[j], o[j + 1]);
+        } else {
+#pragma unroll
+          for (int j = 0; j < NV; ++j) *reinterpret_cast<uint4*>(dst + j * 8) = o[j];
         }
       }
     }
-    if (leader) ptx::tma_store_wait_all0();
   }
   ptx::tc_fence_before();
   __syncthreads();
@@ -320,9 +421,10 @@ conv_thin_kernel(const __grid_constant__ CUtensorMap tmC, const __grid_constant_
   if (warp == kMmaWarp) ptx::tmem_dealloc(tmem_base, C::TMEM_COLS);
 }
 
-template <int CIN, int COUT>
+// pool_bw: 0 = plain conv; 16 / 8 = fused 2x2 max-pool with bw-wide tile blocks (y is the pooled tensor)
+template <int CIN, int COUT, bool POOL>
 int launch_thin(const me_conv_desc* d, const void* x, const void* w, const float* bias, const void* residual, void* y,
-                cudaStream_t stream) {
+                int pool_bw, cudaStream_t stream) {
   using C = TCfg<CIN, COUT>;
   const int Ho = (d->h + 2 - 3) / d->stride + 1, Wo = (d->w + 2 - 3) / d->stride + 1;
   const long long M64 = 1LL * d->n * Ho * Wo;
@@ -338,9 +440,17 @@ int launch_thin(const me_conv_desc* d, const void* x, const void* w, const float
   p.Wo = Wo;
   p.in_pitch = d->in_pitch;
   p.stride = d->stride;
-  p.tiles = ceil_div(p.M, kBM);
+  p.tiles = POOL ? d->n * ceil_div(Ho, kBM / pool_bw) * (Wo / pool_bw) : ceil_div(p.M, kBM);
   p.act = d->act;
   p.has_res = (d->res_pitch > 0 && residual != nullptr) ? 1 : 0;
+  p.res = static_cast<const __half*>(residual);
+  p.res_pitch = d->res_pitch;
+  p.y = static_cast<__half*>(y);
+  p.out_pitch = d->out_pitch;
+  p.pool_bw = pool_bw;
+  ME_REQUIRE(d->out_pitch % 8 == 0 && (!p.has_res || d->res_pitch % 8 == 0), "conv(thin): pitches must be multiples of 8");
+  ME_REQUIRE((reinterpret_cast<uintptr_t>(y) & 15) == 0 && (reinterpret_cast<uintptr_t>(residual) & 15) == 0,
+             "conv(thin): output / residual must be 16-byte aligned");
   static int dbg = -1;
   if (dbg < 0) {
     const char* e = getenv("ME_THIN_DBG");
@@ -350,17 +460,7 @@ int launch_thin(const me_conv_desc* d, const void* x, const void* w, const float
   int rc = conv_ensure_debug_word();
   if (rc != ME_OK) return rc;
   p.debug = conv_debug_word();
-  CUtensorMap tmC, tmR;
-  const CUtensorMapSwizzle swz = swizzle_for_row_bytes(C::ROW_BYTES);
-  rc = encode_tiled_2d(&tmC, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, y, COUT, p.M, d->out_pitch, COUT, kBM, swz);
-  if (rc != ME_OK) return rc;
-  if (p.has_res) {
-    rc = encode_tiled_2d(&tmR, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, residual, COUT, p.M, d->res_pitch, COUT, kBM, swz);
-    if (rc != ME_OK) return rc;
-  } else {
-    tmR = tmC;
-  }
-  auto kern = conv_thin_kernel<CIN, COUT>;
+  auto kern = conv_thin_kernel<CIN, COUT, POOL>;
   static bool attr_seen[64] = {false};   // per instantiation and per device
   if (first_use_on_device(attr_seen))
     ME_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, C::SMEM));
@@ -377,9 +477,17 @@ int launch_thin(const me_conv_desc* d, const void* x, const void* w, const float
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr;
   cfg.numAttrs = conv_pdl_enabled() ? 1 : 0;
-  ME_CUDA(cudaLaunchKernelEx(&cfg, kern, tmC, tmR, p));
+  ME_CUDA(cudaLaunchKernelEx(&cfg, kern, p));
   ME_LAUNCH_CHECK();
   return ME_OK;
+}
+
+// Block width of the fused-pool tiles for an output of Ho x Wo pixels (0: the shape has none).
+int pool_block_width(int Ho, int Wo) {
+  if (Ho % 2 != 0) return 0;
+  if (Wo % 16 == 0) return 16;   // blocks of 8 rows x 16 columns
+  if (Wo % 8 == 0) return 8;     // 16 rows x 8 columns
+  return 0;
 }
 
 }  // namespace
@@ -407,10 +515,24 @@ bool conv_thin_supported(const me_conv_desc* d) {
 
 int conv_thin(const me_conv_desc* d, const void* x, const void* w, const float* bias, const void* residual, void* y,
               cudaStream_t stream) {
-  if (d->cin == 16 && d->cout == 32) return launch_thin<16, 32>(d, x, w, bias, residual, y, stream);
-  if (d->cin == 16 && d->cout == 64) return launch_thin<16, 64>(d, x, w, bias, residual, y, stream);
-  if (d->cin == 32 && d->cout == 32) return launch_thin<32, 32>(d, x, w, bias, residual, y, stream);
-  return launch_thin<32, 64>(d, x, w, bias, residual, y, stream);
+  if (d->cin == 16 && d->cout == 32) return launch_thin<16, 32, false>(d, x, w, bias, residual, y, 0, stream);
+  if (d->cin == 16 && d->cout == 64) return launch_thin<16, 64, false>(d, x, w, bias, residual, y, 0, stream);
+  if (d->cin == 32 && d->cout == 32) return launch_thin<32, 32, false>(d, x, w, bias, residual, y, 0, stream);
+  return launch_thin<32, 64, false>(d, x, w, bias, residual, y, 0, stream);
+}
+
+// conv (3x3, stride 1, 16 / 32 input channels, 32 / 64 filters) + MaxPool2d(2, 2): y is the pooled tensor.
+bool conv_thin_pool_supported(const me_conv_desc* d) {
+  return d->ksize == 3 && d->stride == 1 && !d->out_f32 && d->res_pitch == 0 && (d->cin == 16 || d->cin == 32) &&
+         (d->cout == 32 || d->cout == 64) && d->in_pitch % 8 == 0 && pool_block_width(d->h, d->w) != 0;
+}
+
+int conv_thin_pool(const me_conv_desc* d, const void* x, const void* w, const float* bias, void* y, cudaStream_t stream) {
+  const int bw = pool_block_width(d->h, d->w);
+  if (d->cin == 16 && d->cout == 32) return launch_thin<16, 32, true>(d, x, w, bias, nullptr, y, bw, stream);
+  if (d->cin == 16 && d->cout == 64) return launch_thin<16, 64, true>(d, x, w, bias, nullptr, y, bw, stream);
+  if (d->cin == 32 && d->cout == 32) return launch_thin<32, 32, true>(d, x, w, bias, nullptr, y, bw, stream);
+  return launch_thin<32, 64, true>(d, x, w, bias, nullptr, y, bw, stream);
 }
 
 }  // namespace me

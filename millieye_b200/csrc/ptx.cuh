@@ -75,6 +75,11 @@ __device__ __forceinline__ void cp_async_16(uint32_t dst_smem, const void* src, 
 }
 // The mbarrier gets one arrival from this thread once all its earlier cp.async copies have landed (the arrival was
 // counted at mbarrier.init time: .noinc).
+__device__ __forceinline__ void cp_async_commit_group() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait_group() {
+  asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
 __device__ __forceinline__ void cp_async_mbar_arrive_noinc(uint64_t* bar) {
   asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
 }

@@ -199,6 +199,7 @@ class DarknetPlan:
                            for _ in range(2)]
 
         views = [None] * nb
+        self._pooled = {}      # max-pool block index -> view written by the conv in front of it (fused pool)
         row_off = 0
         self.feature_view = None
         for i, b in enumerate(blocks):
@@ -235,8 +236,26 @@ class DarknetPlan:
                               s_out // 2, s_out // 2, real_c=cout)
                     self._add_conv(i, b, src, pv, None, views, False, pooled=True)
                     views[i] = None
-                    self._pooled_first = pv
+                    self._pooled[1] = pv
                     continue
+                if (i > 0 and nxt is not None and nxt["type"] == "maxpool" and nxt["size"] == 2 and nxt["stride"] == 2
+                        and fuse_res is None and not is_head and readers[i] == [] and i not in target and i + 1 not in target
+                        and b["size"] == 3 and b["stride"] == 1 and self.device.type == "cuda"
+                        and b["cin"] in (16, 32) and cout in (32, 64) and i != self.feature_tap
+                        and os.environ.get("ME_FUSE_POOL", "1") != "0"):
+                    packed = self._pack(i, b)
+                    cin_real = src.real_c if src.real_c != src.c else src.c
+                    cpad = packed.cout_pad
+                    if ops.conv_pool_supported(packed, self.n, src.h, src.w, src.pitch, cpad,
+                                               ME_ACT_LEAKY if b["leaky"] else ME_ACT_LINEAR, cin=cin_real, cout=cpad):
+                        # thin 3x3 layer + 2x2 max-pool (tiny cfgs, blocks 2-3 / 4-5): pooled in the conv's epilogue
+                        pv = View(self._new(s_out // 2, s_out // 2, cpad), 0, cpad, s_out // 2, s_out // 2, real_c=cout)
+                        self._add(lambda b0, nb, sv=src, p=packed, o=pv, a=ME_ACT_LEAKY if b["leaky"] else ME_ACT_LINEAR,
+                                  ci=cin_real: ops.conv_pool(sv.at(b0), p, nb, sv.h, sv.w, sv.pitch, o.at(b0), o.pitch, act=a,
+                                                             cin=ci, cout=p.cout_pad), "conv", i)
+                        views[i] = None
+                        self._pooled[i + 1] = pv
+                        continue
                 if out_idx in target:
                     buf, off = target[out_idx]
                     ov = View(buf, off, cout, s_out, s_out)
@@ -256,8 +275,8 @@ class DarknetPlan:
                     raise MeError("shortcut without a preceding conv; unsupported cfg")
                 views[i] = views[i - 1]
             elif t == "maxpool":
-                if i == 1 and getattr(self, "_pooled_first", None) is not None:
-                    views[i] = self._pooled_first      # already produced by the first conv's epilogue
+                if i in self._pooled:
+                    views[i] = self._pooled[i]         # already produced by the preceding conv's epilogue
                     continue
                 if b["size"] != 2:
                     raise MeError("only 2x2 max-pool is supported")

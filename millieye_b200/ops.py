@@ -81,6 +81,21 @@ def conv_gemm(x, packed, n, h, w, in_pitch, out, out_pitch, stride=1, act=ME_ACT
     return out
 
 
+def conv_pool_supported(packed, n, h, w, in_pitch, out_pitch, act=ME_ACT_LEAKY, cin=None, cout=None):
+    """True if conv_pool() can run this 3x3 / stride-1 layer with the 2x2 / stride-2 max-pool behind it in one kernel."""
+    d = conv_desc(packed, n, h, w, in_pitch, out_pitch, 1, act, 0, cin, cout)
+    return bool(_lib.lib().me_conv_pool_supported(byref(d)))
+
+
+def conv_pool(x, packed, n, h, w, in_pitch, out, out_pitch, act=ME_ACT_LEAKY, cin=None, cout=None):
+    """conv_gemm (3x3, stride 1, thin layer) + maxpool2(stride 2) in one kernel; out is the pooled (n, h/2, w/2, out_pitch)
+    tensor.  Bit-identical to the two calls (me_conv_pool)."""
+    _need_cuda(x, out)
+    d = conv_desc(packed, n, h, w, in_pitch, out_pitch, 1, act, 0, cin, cout)
+    check(_lib.lib().me_conv_pool(byref(d), ptr(x), ptr(packed.w), ptr(packed.bias), ptr(out), stream_ptr()), "me_conv_pool")
+    return out
+
+
 def conv_gemm_yolo(x, packed, n, h, w, in_pitch, pred, g, anchors, num_classes, yolo_stride, rows_total, row_offset,
                    cin=None, cout=None):
     """Head conv (1x1, linear, bias) with the YOLO decode fused into its epilogue: writes decoded rows into

@@ -172,6 +172,32 @@ def test_conv_first_pool_equals_two_calls(cout, n, h, w):
             ops.conv_first(bad, first, torch.zeros(1, 18, 24, cout, dtype=torch.float16, device=DEV), cout, act=1, pool=True)
 
 
+@pytest.mark.parametrize("cin,cout,n,h,w", [(16, 32, 2, 48, 48), (32, 64, 3, 32, 24), (16, 32, 4, 208, 208), (32, 64, 4, 104, 104),
+                                             (16, 64, 1, 16, 8), (32, 32, 2, 10, 16), (16, 32, 1, 6, 24)])
+def test_conv_pool_equals_two_calls(cin, cout, n, h, w):
+    """me_conv_pool (thin 3x3 conv with the 2x2 / stride-2 max-pool in its epilogue) == me_conv_gemm + me_maxpool2 bit for
+    bit, for both tile-block widths (16 columns x 8 rows when w % 16 == 0, else 8 x 16; the last block row of an image may
+    be partial); other shapes are refused."""
+    torch.manual_seed(7)
+    x = (torch.randn(n, h, w, cin) * 0.5).half().to(DEV)
+    wt = torch.randn(cout, cin, 3, 3) / (cin * 9) ** 0.5
+    bn = (torch.rand(cout) + 0.5, torch.randn(cout) * 0.1, torch.randn(cout) * 0.1, torch.rand(cout) + 0.5, 1e-5)
+    packed = ops.pack_conv(wt.to(DEV), None, tuple(t.to(DEV) if torch.is_tensor(t) else t for t in bn), cout_pad=cout)
+    assert ops.conv_pool_supported(packed, n, h, w, cin, cout)
+    full = torch.zeros(n, h, w, cout, dtype=torch.float16, device=DEV)
+    ops.conv_gemm(x, packed, n, h, w, cin, full, cout, stride=1, act=1)
+    want = torch.zeros(n, h // 2, w // 2, cout, dtype=torch.float16, device=DEV)
+    ops.maxpool2(full, want, n, h, w, cout, cout, cout, 2)
+    got = torch.full((n, h // 2, w // 2, cout), float("nan"), dtype=torch.float16, device=DEV)
+    ops.conv_pool(x, packed, n, h, w, cin, got, cout, act=1)
+    torch.cuda.synchronize()
+    assert torch.equal(got, want)
+    if (h, w) == (48, 48):
+        assert not ops.conv_pool_supported(packed, n, 20, 20, cin, cout)
+        with pytest.raises(MeError):
+            ops.conv_pool(x[:, :20, :20].contiguous(), packed, n, 20, 20, cin, got, cout, act=1)
+
+
 @pytest.mark.parametrize("stride", [1, 2])
 def test_maxpool(stride):
     torch.manual_seed(2)
