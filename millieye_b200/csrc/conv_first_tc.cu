@@ -390,6 +390,15 @@ int conv_first_tc_impl(const float* x_nchw, const float* w_folded, const float* 
       default: return fail(ME_ERR_UNSUPPORTED, "conv_first_tc_pool: cout %d unsupported (16 or 32)", cout);
     }
   }
+  static int epi_plain = -1;
+  if (epi_plain < 0) {
+    const char* e = getenv("ME_FIRST_EPI_PLAIN");
+    epi_plain = e ? atoi(e) : 2;
+  }
+  if (vec && epi_plain == 3 && cout == 32)
+    return launch_first<32, true, false, 3>(x_nchw, wk, bias, y, n, h, w, cin, out_pitch, act, tiles, grid, stream);
+  if (vec && epi_plain == 3 && cout == 16)
+    return launch_first<16, true, false, 3>(x_nchw, wk, bias, y, n, h, w, cin, out_pitch, act, tiles, grid, stream);
 #define ME_FIRST(C)                                                                                              \
   return vec ? launch_first<C, true>(x_nchw, wk, bias, y, n, h, w, cin, out_pitch, act, tiles, grid, stream)     \
              : launch_first<C, false>(x_nchw, wk, bias, y, n, h, w, cin, out_pitch, act, tiles, grid, stream)

@@ -6,7 +6,7 @@ if len(sys.argv) > 1:
     import torch
     from millieye_b200 import ops
     pool = sys.argv[1] == "pool"
-    n, s, cout = 32, 416, 16
+    n, s, cout = 32, 416, int(os.environ.get("FIRST_COUT", "16"))
     x = torch.rand(n, 3, s, s, device="cuda")
     wt = torch.randn(cout, 3, 3, 3, device="cuda") * 0.3
     first = ops.pack_first_conv(wt, torch.zeros(cout, device="cuda"), None)
@@ -20,10 +20,10 @@ if len(sys.argv) > 1:
     for _ in range(20):
         ops.conv_first(x, first, out, cout, act=1, pool=pool)
     e1.record(); torch.cuda.synchronize()
-    print(f"{sys.argv[1]:5s} DBG={os.environ.get('ME_FIRST_DBG','0')} EPI={os.environ.get('ME_FIRST_EPI','2')}: {e0.elapsed_time(e1)/20*1e3:7.1f} us")
+    print(f"{sys.argv[1]:5s} DBG={os.environ.get('ME_FIRST_DBG','0')} COUT={os.environ.get('FIRST_COUT','16')} EPI={os.environ.get('ME_FIRST_EPI_PLAIN','2')}: {e0.elapsed_time(e1)/20*1e3:7.1f} us")
 else:
-    for mode in ("plain", "pool"):
+    for cout in ("16", "32"):
         for dbg in ("0", "7"):
-            for epi in (("2", "3") if mode == "pool" else ("2",)):
-                env = dict(os.environ, ME_FIRST_DBG=dbg, ME_FIRST_EPI=epi)
-                subprocess.run([sys.executable, __file__, mode], env=env)
+            for epi in ("2", "3"):
+                env = dict(os.environ, ME_FIRST_DBG=dbg, ME_FIRST_EPI_PLAIN=epi, FIRST_COUT=cout)
+                subprocess.run([sys.executable, __file__, "plain"], env=env)
