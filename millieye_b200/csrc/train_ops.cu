@@ -12,6 +12,7 @@
 // The op-by-op derivation these kernels transcribe is oracle/stage3_backward.py (checked against torch.autograd and
 // the reference's own gradients).  All matrices are row-major [rows][channels] ("NHWC flattened").
 #include "common.cuh"
+#include <cooperative_groups.h>
 
 namespace me {
 namespace {
@@ -95,22 +96,130 @@ gemm_f32_kernel(int M, int N, int K, const float* __restrict__ A, long long sai,
   }
 }
 
+// The same product for the large shapes (pixels x channels forward / input-gradient products, split-K weight gradients):
+// 128 x 128 x 8 tiles, 256 threads, an 8 x 8 micro-tile per thread read from shared memory as float4 (16 FMAs per shared
+// load instead of 2), the next K slab prefetched into registers while the current one is multiplied.
+__global__ void __launch_bounds__(256, 2)
+gemm_f32_big_kernel(int M, int N, int K, const float* __restrict__ A, long long sai, long long sak,
+                    const float* __restrict__ B, long long sbk, long long sbj, float* __restrict__ C, long long ldc,
+                    const float* __restrict__ bias, int act, int accumulate, int k_chunk) {
+  constexpr int BM = 128, BN = 128, BK = 8;
+  __shared__ __align__(16) float As[2][BK][BM];
+  __shared__ __align__(16) float Bs[2][BK][BN];
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  const int i0 = blockIdx.y * BM, j0 = blockIdx.x * BN;
+  const bool a_k_fast = sak == 1, b_j_fast = sbj == 1;
+  const bool split = gridDim.z > 1;
+  const int k_begin = blockIdx.z * k_chunk;
+  if (split) K = min(K, k_begin + k_chunk);
+  // element e (0..1023) of a slab handled by this thread: 4 per operand; the faster index follows the unit stride
+  int ai[4], ak[4], bj[4], bk[4];
+#pragma unroll
+  for (int u = 0; u < 4; ++u) {
+    const int e = threadIdx.x + 256 * u;
+    ai[u] = a_k_fast ? e / BK : e % BM;
+    ak[u] = a_k_fast ? e % BK : e / BM;
+    bj[u] = b_j_fast ? e % BN : e / BK;
+    bk[u] = b_j_fast ? e / BN : e % BK;
+  }
+  float ra[4], rb[4];
+  auto fetch = [&](int k0) {
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const int gi = i0 + ai[u], gk = k0 + ak[u];
+      ra[u] = (gi < M && gk < K) ? A[gi * sai + gk * sak] : 0.f;
+      const int gj = j0 + bj[u], gk2 = k0 + bk[u];
+      rb[u] = (gj < N && gk2 < K) ? B[gk2 * sbk + gj * sbj] : 0.f;
+    }
+  };
+  auto stash = [&](int buf) {
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      As[buf][ak[u]][ai[u]] = ra[u];
+      Bs[buf][bk[u]][bj[u]] = rb[u];
+    }
+  };
+  float acc[8][8];
+#pragma unroll
+  for (int a = 0; a < 8; ++a)
+#pragma unroll
+    for (int b = 0; b < 8; ++b) acc[a][b] = 0.f;
+  int buf = 0;
+  if (k_begin < K) {
+    fetch(k_begin);
+    stash(0);
+  }
+  __syncthreads();
+  for (int k0 = k_begin; k0 < K; k0 += BK) {
+    const bool more = k0 + BK < K;
+    if (more) fetch(k0 + BK);
+#pragma unroll
+    for (int k = 0; k < BK; ++k) {
+      const float4 a0 = *reinterpret_cast<const float4*>(&As[buf][k][ty * 4]);
+      const float4 a1 = *reinterpret_cast<const float4*>(&As[buf][k][64 + ty * 4]);
+      const float4 b0 = *reinterpret_cast<const float4*>(&Bs[buf][k][tx * 4]);
+      const float4 b1 = *reinterpret_cast<const float4*>(&Bs[buf][k][64 + tx * 4]);
+      const float av[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
+      const float bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+      for (int a = 0; a < 8; ++a)
+#pragma unroll
+        for (int b = 0; b < 8; ++b) acc[a][b] = fmaf(av[a], bv[b], acc[a][b]);
+    }
+    if (more) stash(buf ^ 1);
+    __syncthreads();
+    buf ^= 1;
+  }
+#pragma unroll
+  for (int a = 0; a < 8; ++a) {
+    const int gi = i0 + (a < 4 ? ty * 4 + a : 64 + ty * 4 + a - 4);
+    if (gi >= M) continue;
+#pragma unroll
+    for (int b = 0; b < 8; ++b) {
+      const int gj = j0 + (b < 4 ? tx * 4 + b : 64 + tx * 4 + b - 4);
+      if (gj >= N) continue;
+      float v = acc[a][b];
+      float* c = C + gi * ldc + gj;
+      if (split) {
+        atomicAdd(c, v);
+      } else if (accumulate) {
+        *c += v;
+      } else {
+        if (bias) v += bias[gj];
+        if (act == ME_ACT_LEAKY) v = v > 0.f ? v : kSlope * v;
+        else if (act == ME_ACT_SIGMOID) v = sigmoid_f(v);
+        *c = v;
+      }
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------------ column sums
 // out[c] = sum_r X[r][c] * (Y ? Y[r][c] : 1), double accumulation.  One block of 32 x 32 threads per 32 columns: a warp
 // reads 32 consecutive columns of one row (128 bytes), the 32 warps take rows r, r+32, ... four at a time (memory-level
 // parallelism: with 8 row lanes and one load in flight the 43 264-row sums of a batch-64 step took ~0.3 ms each).
 // Fixed reduction order: deterministic.
 constexpr int kColsumLanes = 32;
-__global__ void __launch_bounds__(32 * kColsumLanes)
+constexpr int kRowSplit = 8;     // CTAs of one thread-block cluster share a 32-column group, each takes an eighth of the rows
+// Column sums over [rows][cols] matrices have cols / 32 column groups - 1 to 16 blocks for the head layers, i.e. 1 to 16 of
+// 148 SMs reading tens of MB.  A cluster of 8 CTAs per column group splits the rows; the partial sums meet in CTA 0 through
+// distributed shared memory and are added in rank order: still a fixed reduction order (deterministic), no workspace.
+__global__ void __cluster_dims__(kRowSplit, 1, 1) __launch_bounds__(32 * kColsumLanes)
 colsum_kernel(const float* __restrict__ X, const float* __restrict__ Y, long long rows, int cols, long long ldx,
               long long ldy, float* __restrict__ out) {
+  namespace cg = cooperative_groups;
+  cg::cluster_group cluster = cg::this_cluster();
   __shared__ double s[kColsumLanes][33];
-  const int c = blockIdx.x * 32 + (threadIdx.x & 31);
+  __shared__ double s_tot[32];
+  const int rank = static_cast<int>(cluster.block_rank());
+  const int c = (blockIdx.x / kRowSplit) * 32 + (threadIdx.x & 31);
   const int lane_r = threadIdx.x >> 5;
+  const long long per = (rows + kRowSplit - 1) / kRowSplit;
+  const long long r_end = min(rows, (rank + 1) * per);
   double acc = 0.0;
   if (c < cols) {
-    long long r = lane_r;
-    for (; r + 3 * kColsumLanes < rows; r += 4 * kColsumLanes) {
+    long long r = rank * per + lane_r;
+    for (; r + 3 * kColsumLanes < r_end; r += 4 * kColsumLanes) {
       float x[4], y[4];
 #pragma unroll
       for (int u = 0; u < 4; ++u) x[u] = X[(r + u * kColsumLanes) * ldx + c];
@@ -121,19 +230,26 @@ colsum_kernel(const float* __restrict__ X, const float* __restrict__ Y, long lon
 #pragma unroll
       for (int u = 0; u < 4; ++u) acc += Y ? static_cast<double>(x[u]) * static_cast<double>(y[u]) : static_cast<double>(x[u]);
     }
-    for (; r < rows; r += kColsumLanes) {
+    for (; r < r_end; r += kColsumLanes) {
       const float x = X[r * ldx + c];
       acc += Y ? static_cast<double>(x) * static_cast<double>(Y[r * ldy + c]) : static_cast<double>(x);
     }
   }
   s[lane_r][threadIdx.x & 31] = acc;
   __syncthreads();
-  if (lane_r == 0 && c < cols) {
+  if (lane_r == 0) {
     double t = 0.0;
 #pragma unroll
     for (int k = 0; k < kColsumLanes; ++k) t += s[k][threadIdx.x & 31];
+    s_tot[threadIdx.x & 31] = t;
+  }
+  cluster.sync();
+  if (rank == 0 && lane_r == 0 && c < cols) {
+    double t = 0.0;
+    for (int k = 0; k < kRowSplit; ++k) t += cluster.map_shared_rank(s_tot, k)[threadIdx.x & 31];
     out[c] = static_cast<float>(t);
   }
+  cluster.sync();   // the peers' shared memory stays alive until CTA 0 has read it
 }
 
 // ------------------------------------------------------------------------------------------------ layout / im2col
@@ -196,15 +312,21 @@ __global__ void col2im3_kernel(const float* __restrict__ dcols, int n, int h, in
 //   partial : sums[c] = sum_r z[r][c], sums[cols + c] = sum_r z[r][c]^2 (double), sums[2 cols] = rows
 //   finalize: mean, biased variance -> inv_std; running statistics updated like nn.BatchNorm2d in training mode
 //             (momentum m, unbiased variance into running_var).  The row count is read from device memory.
-__global__ void __launch_bounds__(32 * kColsumLanes)
+__global__ void __cluster_dims__(kRowSplit, 1, 1) __launch_bounds__(32 * kColsumLanes)
 bn_partial_kernel(const float* __restrict__ z, long long rows, int cols, double* __restrict__ sums) {
+  namespace cg = cooperative_groups;
+  cg::cluster_group cluster = cg::this_cluster();
   __shared__ double s1[kColsumLanes][33], s2[kColsumLanes][33];
-  const int c = blockIdx.x * 32 + (threadIdx.x & 31);
+  __shared__ double t1s[32], t2s[32];
+  const int rank = static_cast<int>(cluster.block_rank());
+  const int c = (blockIdx.x / kRowSplit) * 32 + (threadIdx.x & 31);
   const int lr = threadIdx.x >> 5;
+  const long long per = (rows + kRowSplit - 1) / kRowSplit;
+  const long long r_end = min(rows, (rank + 1) * per);
   double a = 0.0, b = 0.0;
   if (c < cols) {
-    long long r = lr;
-    for (; r + 3 * kColsumLanes < rows; r += 4 * kColsumLanes) {
+    long long r = rank * per + lr;
+    for (; r + 3 * kColsumLanes < r_end; r += 4 * kColsumLanes) {
       float x[4];
 #pragma unroll
       for (int u = 0; u < 4; ++u) x[u] = z[(r + u * kColsumLanes) * cols + c];
@@ -215,7 +337,7 @@ bn_partial_kernel(const float* __restrict__ z, long long rows, int cols, double*
         b += v * v;
       }
     }
-    for (; r < rows; r += kColsumLanes) {
+    for (; r < r_end; r += kColsumLanes) {
       const double v = static_cast<double>(z[r * cols + c]);
       a += v;
       b += v * v;
@@ -224,17 +346,28 @@ bn_partial_kernel(const float* __restrict__ z, long long rows, int cols, double*
   s1[lr][threadIdx.x & 31] = a;
   s2[lr][threadIdx.x & 31] = b;
   __syncthreads();
-  if (lr == 0 && c < cols) {
+  if (lr == 0) {
     double t1 = 0.0, t2 = 0.0;
 #pragma unroll
     for (int k = 0; k < kColsumLanes; ++k) {
       t1 += s1[k][threadIdx.x & 31];
       t2 += s2[k][threadIdx.x & 31];
     }
+    t1s[threadIdx.x & 31] = t1;
+    t2s[threadIdx.x & 31] = t2;
+  }
+  cluster.sync();
+  if (rank == 0 && lr == 0 && c < cols) {
+    double t1 = 0.0, t2 = 0.0;
+    for (int k = 0; k < kRowSplit; ++k) {     // rank order: deterministic
+      t1 += cluster.map_shared_rank(t1s, k)[threadIdx.x & 31];
+      t2 += cluster.map_shared_rank(t2s, k)[threadIdx.x & 31];
+    }
     sums[c] = t1;
     sums[cols + c] = t2;
   }
   if (blockIdx.x == 0 && threadIdx.x == 0) sums[2 * cols] = static_cast<double>(rows);
+  cluster.sync();
 }
 
 __global__ void bn_finalize_kernel(const double* __restrict__ sums, int cols, float eps, float momentum,
@@ -531,6 +664,7 @@ int me_gemm_f32(int M, int N, int K, const float* A, long long sai, long long sa
   ME_REQUIRE(A && B && C && K >= 0, "gemm_f32: null argument");
   ME_REQUIRE(!accumulate || (!bias && act == ME_ACT_LINEAR), "gemm_f32: accumulate excludes bias / activation");
   const long long tiles64 = 1LL * ((M + 63) / 64) * ((N + 63) / 64);
+  const long long tiles128 = 1LL * ((M + 127) / 128) * ((N + 127) / 128);
   // Few output tiles and a long reduction (the weight gradients dW = dZ^T x over all pixels / proposals of the batch):
   // split K over blockIdx.z so that ~4 waves of CTAs work, partial tiles added with atomicAdd into a zero-filled C.
   int splits = 1, k_chunk = K;
@@ -543,8 +677,21 @@ int me_gemm_f32(int M, int N, int K, const float* A, long long sai, long long sa
   }
   if (splits > 1) {
     if (!accumulate) ME_CUDA(cudaMemset2DAsync(C, static_cast<size_t>(ldc) * sizeof(float), 0, static_cast<size_t>(N) * sizeof(float), M, stream));
-    dim3 grid((N + 63) / 64, (M + 63) / 64, splits);
-    gemm_f32_kernel<64, 64><<<grid, 256, 0, stream>>>(M, N, K, A, sai, sak, B, sbk, sbj, C, ldc, nullptr, ME_ACT_LINEAR, 0, k_chunk);
+    if (M >= 96 && N >= 96) {   // 128 x 128 tiles, K split so that ~4 waves of them work
+      int sp = static_cast<int>((4 * 148 + tiles128 - 1) / tiles128);
+      if (sp > K / 256) sp = K / 256;
+      if (sp < 1) sp = 1;
+      const int kc = (((K + sp - 1) / sp) + 7) / 8 * 8;
+      sp = (K + kc - 1) / kc;
+      dim3 grid((N + 127) / 128, (M + 127) / 128, sp);
+      gemm_f32_big_kernel<<<grid, 256, 0, stream>>>(M, N, K, A, sai, sak, B, sbk, sbj, C, ldc, nullptr, ME_ACT_LINEAR, 0, kc);
+    } else {
+      dim3 grid((N + 63) / 64, (M + 63) / 64, splits);
+      gemm_f32_kernel<64, 64><<<grid, 256, 0, stream>>>(M, N, K, A, sai, sak, B, sbk, sbj, C, ldc, nullptr, ME_ACT_LINEAR, 0, k_chunk);
+    }
+  } else if (tiles128 >= 120 && N >= 64) {
+    dim3 grid((N + 127) / 128, (M + 127) / 128);
+    gemm_f32_big_kernel<<<grid, 256, 0, stream>>>(M, N, K, A, sai, sak, B, sbk, sbj, C, ldc, bias, act, accumulate, K);
   } else if (tiles64 >= 148) {
     dim3 grid((N + 63) / 64, (M + 63) / 64);
     gemm_f32_kernel<64, 64><<<grid, 256, 0, stream>>>(M, N, K, A, sai, sak, B, sbk, sbj, C, ldc, bias, act, accumulate, K);
@@ -562,7 +709,7 @@ int me_colsum_f32(const float* X, const float* Y, long long rows, int cols, long
   using namespace me;
   if (cols <= 0) return ME_OK;
   ME_REQUIRE(X && out, "colsum_f32: null argument");
-  colsum_kernel<<<(cols + 31) / 32, 32 * kColsumLanes, 0, static_cast<cudaStream_t>(stream)>>>(X, Y, rows, cols, ldx, ldy, out);
+  colsum_kernel<<<kRowSplit * ((cols + 31) / 32), 32 * kColsumLanes, 0, static_cast<cudaStream_t>(stream)>>>(X, Y, rows, cols, ldx, ldy, out);
   ME_LAUNCH_CHECK();
   return ME_OK;
 }
@@ -604,7 +751,7 @@ int me_col2im3_f32(const float* dcols, int n, int h, int w, int c, float* dx, me
 int me_bn_partial_stats(const float* z, long long rows, int cols, double* sums, me_stream_t stream) {
   using namespace me;
   ME_REQUIRE(sums && cols > 0 && rows >= 0 && (rows == 0 || z), "bn_partial_stats: bad argument");
-  bn_partial_kernel<<<(cols + 31) / 32, 32 * kColsumLanes, 0, static_cast<cudaStream_t>(stream)>>>(z, rows, cols, sums);
+  bn_partial_kernel<<<kRowSplit * ((cols + 31) / 32), 32 * kColsumLanes, 0, static_cast<cudaStream_t>(stream)>>>(z, rows, cols, sums);
   ME_LAUNCH_CHECK();
   return ME_OK;
 }
@@ -646,8 +793,8 @@ int me_bn_bwd_sums(float* da_inout, const float* a, const float* xhat, long long
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   ME_REQUIRE(dgamma && dbeta && cols > 0 && rows >= 0 && (rows == 0 || (da_inout && a && xhat)), "bn_bwd_sums: bad argument");
   if (rows > 0) leaky_bwd_kernel<<<grid_for(rows * cols), 256, 0, stream>>>(da_inout, a, rows * cols);
-  colsum_kernel<<<(cols + 31) / 32, 32 * kColsumLanes, 0, stream>>>(da_inout, xhat, rows, cols, cols, cols, dgamma);
-  colsum_kernel<<<(cols + 31) / 32, 32 * kColsumLanes, 0, stream>>>(da_inout, nullptr, rows, cols, cols, cols, dbeta);
+  colsum_kernel<<<kRowSplit * ((cols + 31) / 32), 32 * kColsumLanes, 0, stream>>>(da_inout, xhat, rows, cols, cols, cols, dgamma);
+  colsum_kernel<<<kRowSplit * ((cols + 31) / 32), 32 * kColsumLanes, 0, stream>>>(da_inout, nullptr, rows, cols, cols, cols, dbeta);
   ME_LAUNCH_CHECK();
   return ME_OK;
 }

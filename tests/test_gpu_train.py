@@ -97,6 +97,38 @@ def test_head_training_kernels_match_reference_gradients(golden_dir):
     print("worst relative gradient error", worst)
 
 
+@pytest.mark.parametrize("m,n,k", [(21632, 490, 256), (5000, 131, 27), (2400, 256, 490), (300, 70, 40)])
+def test_gemm_f32_all_paths_vs_torch(m, n, k):
+    """me_gemm_f32 through its three layouts (x W^T with bias + LeakyReLU, dZ W, and the split-K weight gradient dZ^T x) on
+    shapes that take the 128 x 128 tiles, the 64 x 64 / 32 x 32 tiles and the split-K paths, against torch in float64;
+    column sums (cluster-split reduction) on the same matrices."""
+    torch.backends.cuda.matmul.allow_tf32 = False
+    g = torch.Generator(device="cpu").manual_seed(m + n)
+    x = torch.randn(m, k, generator=g).to(DEV)
+    w = (torch.randn(n, k, generator=g) / k ** 0.5).to(DEV)
+    b = torch.randn(n, generator=g).to(DEV)
+    out = torch.full((m, n), float("nan"), device=DEV)
+    st.gemm_nt(x, w, out, b, 1)
+    ref = torch.nn.functional.leaky_relu(x.double() @ w.double().t() + b.double(), 0.1)
+    assert float((out.double() - ref).abs().max()) <= 2e-5 * max(1.0, float(ref.abs().max()))
+    dz = torch.randn(m, n, generator=g).to(DEV)
+    dx = torch.full((m, k), float("nan"), device=DEV)
+    st.gemm_nn(dz, w, dx)
+    ref = dz.double() @ w.double()
+    assert float((dx.double() - ref).abs().max()) <= 2e-5 * max(1.0, float(ref.abs().max()))
+    dw = torch.full((n, k), float("nan"), device=DEV)
+    st.gemm_tn(dz, x, dw)
+    ref = dz.double().t() @ x.double()
+    assert float((dw.double() - ref).abs().max()) <= 2e-5 * max(1.0, float(ref.abs().max()))
+    cs = torch.full((n,), float("nan"), device=DEV)
+    st.colsum(dz, cs)
+    assert float((cs.double() - dz.double().sum(0)).abs().max()) <= 1e-5 * max(1.0, float(dz.double().sum(0).abs().max()))
+    cs2 = torch.full((n,), float("nan"), device=DEV)
+    st.colsum(dz, cs2, y=out)
+    ref = (dz.double() * out.double()).sum(0)
+    assert float((cs2.double() - ref).abs().max()) <= 1e-5 * max(1.0, float(ref.abs().max()))
+
+
 def test_adam_kernel_matches_torch():
     torch.manual_seed(0)
     p0 = torch.randn(5000, device=DEV)
