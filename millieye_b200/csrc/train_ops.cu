@@ -668,9 +668,11 @@ int me_gemm_f32(int M, int N, int K, const float* A, long long sai, long long sa
   // Few output tiles and a long reduction (the weight gradients dW = dZ^T x over all pixels / proposals of the batch):
   // split K over blockIdx.z so that ~4 waves of CTAs work, partial tiles added with atomicAdd into a zero-filled C.
   int splits = 1, k_chunk = K;
-  if (tiles64 < 148 && K >= 4096 && !bias && act == ME_ACT_LINEAR) {
+  if (tiles64 < 148 && K >= 1024 && !bias && act == ME_ACT_LINEAR) {
+    // chunks of >= 128 (K < 8192: the proposals' products, a few thousand rows) or >= 512 reduction steps
+    const int min_chunk = K >= 8192 ? 512 : 128;
     splits = static_cast<int>((4 * 148 + tiles64 - 1) / tiles64);
-    if (splits > K / 512) splits = K / 512;
+    if (splits > K / min_chunk) splits = K / min_chunk;
     if (splits < 1) splits = 1;
     k_chunk = (((K + splits - 1) / splits) + 15) / 16 * 16;
     splits = (K + k_chunk - 1) / k_chunk;
