@@ -32,9 +32,17 @@ struct FCfg {
   static constexpr int PROD_WARPS = VEC ? 8 : 16;
   static constexpr int ARRIVALS = VEC ? 32 : 128;  // producer threads per tile
   static constexpr int EPI_GROUPS = EPI;           // 4-warp epilogue groups taking tiles in turn
-  static constexpr int ACCS = 4;                   // TMEM accumulators in flight
+  // TMEM accumulators in flight.  They form ACCS / TPS sets (one per stage in flight); the number of sets must be a
+  // multiple of the number of epilogue groups so that a group meets each set's barrier phases in order (a group that
+  // skips a phase would pass a parity wait on a phase that has not started)
+  static constexpr int ACCS = VEC ? 2 * EPI : 4;   // (TPS = 1: 4 or 6 sets for 2 or 3 groups)
   static constexpr int THREADS = 32 * (PROD_WARPS + 1 + 4 * EPI_GROUPS);
-  static constexpr int SMEM = STAGES * kABytes + 1024;
+  // Tiles per pipeline stage / barrier round trip.  With everything but the barriers stripped the kernel takes 330 clocks
+  // per 128-pixel tile (ME_FIRST_DBG=31), and TPS = 2 halves that floor (49 -> 29 us at 416^2 x 32) - but the whole
+  // kernel does not gain (16 channels 100 -> 94 us, 32 channels 134 -> 143 us, pooled 95 -> 95 us): the epilogue then
+  // owns two accumulators per wake-up and the MMAs run less far ahead of it.  Kept at 1; the loops are written for any TPS.
+  static constexpr int TPS = 1;
+  static constexpr int SMEM = STAGES * TPS * kABytes + 1024;
 };
 
 __device__ __forceinline__ void mbar_wait_spin(uint64_t* bar, uint32_t parity) {
@@ -83,7 +91,10 @@ conv_first_tc_kernel(const float* __restrict__ x, const __half* __restrict__ wk,
   __shared__ __align__(16) float s_bias[COUT];
   __shared__ __align__(8) uint64_t full_bar[F::STAGES], empty_bar[F::STAGES], tmem_full[F::ACCS], tmem_empty[F::ACCS];
   __shared__ uint32_t tmem_ptr;
-  constexpr int TMEM_COLS = (F::ACCS * COUT <= 32) ? 32 : (F::ACCS * COUT <= 64) ? 64 : (F::ACCS * COUT <= 128) ? 128 : 256;
+  constexpr int TMEM_COLS = (F::ACCS * COUT <= 32) ? 32 : (F::ACCS * COUT <= 64) ? 64 : (F::ACCS * COUT <= 128) ? 128
+                            : (F::ACCS * COUT <= 256) ? 256 : 512;
+  static_assert(F::ACCS * COUT <= 512, "first conv: accumulators exceed TMEM");
+  static_assert((F::ACCS / F::TPS) % F::EPI_GROUPS == 0, "first conv: accumulator sets must be a multiple of the epilogue groups");
   constexpr int MMA_WARP = F::PROD_WARPS;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -124,8 +135,11 @@ conv_first_tc_kernel(const float* __restrict__ x, const __half* __restrict__ wk,
     // producer unit u (a warp when VEC, a 4-warp group otherwise) owns stage u and every STAGES-th tile
     const uint32_t stage = VEC ? warp : (warp >> 2);
     uint32_t phase = 0;
-    for (int tile = blockIdx.x + stage * gridDim.x; tile < tiles; tile += F::STAGES * gridDim.x) {
-      uint8_t* a_tile = s_a + stage * kABytes;
+    const int supers = (tiles + F::TPS - 1) / F::TPS;
+    for (int st = blockIdx.x + stage * gridDim.x; st < supers; st += F::STAGES * gridDim.x) {
+     for (int h2 = 0; h2 < F::TPS; ++h2) {
+      const int tile = st * F::TPS + h2;
+      uint8_t* a_tile = s_a + (stage * F::TPS + h2) * kABytes;
       if constexpr (VEC) {
         // 4 consecutive pixels of one image row per lane (w % 4 == 0).  Their MMA rows are row0 + j * rstep: for a fixed
         // j the 32 lanes write 32 rows whose 16-byte slots cover every bank group 4 times - the minimum (lane-major
@@ -210,6 +224,7 @@ conv_first_tc_kernel(const float* __restrict__ x, const __half* __restrict__ wk,
         mbar_wait_spin(&empty_bar[stage], phase ^ 1);
         store_row(a_tile, row, v);
       }
+     }
       ptx::fence_proxy_async_smem();
       ptx::mbar_arrive(&full_bar[stage]);
       phase ^= 1;
@@ -221,20 +236,26 @@ conv_first_tc_kernel(const float* __restrict__ x, const __half* __restrict__ wk,
       const uint32_t b_addr = ptx::smem_u32(s_b);
       uint32_t stage = 0, phase = 0;
       int it = 0;
-      for (int tile = blockIdx.x; tile < tiles; tile += gridDim.x, ++it) {
-        const int acc = it & (F::ACCS - 1);
-        mbar_wait_spin(&tmem_empty[acc], ((it / F::ACCS) & 1) ^ 1);
+      constexpr int SETS = F::ACCS / F::TPS;      // accumulator sets: one per super tile in flight
+      const int supers = (tiles + F::TPS - 1) / F::TPS;
+      for (int st = blockIdx.x; st < supers; st += gridDim.x, ++it) {
+        const int set = it % SETS;
+        mbar_wait_spin(&tmem_empty[set], ((it / SETS) & 1) ^ 1);
         mbar_wait_spin(&full_bar[stage], phase);
         ptx::tc_fence_after();
-        const uint32_t a_addr = ptx::smem_u32(s_a + stage * kABytes);
 #pragma unroll
-        for (int k = 0; k < 2; ++k) {
-          const uint64_t adesc = make_nosw_desc(a_addr + k * 2 * (kTileM * 16), kTileM * 16, 128);
-          const uint64_t bdesc = make_nosw_desc(b_addr + k * 2 * (COUT * 16), COUT * 16, 128);
-          ptx::umma_f16_ss(tmem_base + acc * COUT, adesc, bdesc, idesc, k);
+        for (int h2 = 0; h2 < F::TPS; ++h2) {
+          const uint32_t a_addr = ptx::smem_u32(s_a + (stage * F::TPS + h2) * kABytes);
+#pragma unroll
+          for (int k = 0; k < 2; ++k) {
+            const uint64_t adesc = make_nosw_desc(a_addr + k * 2 * (kTileM * 16), kTileM * 16, 128);
+            const uint64_t bdesc = make_nosw_desc(b_addr + k * 2 * (COUT * 16), COUT * 16, 128);
+            if (!(dbg & 16))   // bit 16: no MMAs
+              ptx::umma_f16_ss(tmem_base + (set * F::TPS + h2) * COUT, adesc, bdesc, idesc, k);
+          }
         }
         ptx::umma_commit(&empty_bar[stage]);
-        ptx::umma_commit(&tmem_full[acc]);
+        ptx::umma_commit(&tmem_full[set]);
         if (++stage == F::STAGES) { stage = 0; phase ^= 1; }
       }
     }
@@ -243,11 +264,16 @@ conv_first_tc_kernel(const float* __restrict__ x, const __half* __restrict__ wk,
     const int q = warp & 3;
     const int row = q * 32 + lane;
     const int group = (warp - (MMA_WARP + 1)) >> 2;  // this group takes tiles it = group, group + 2, ...
-    for (int it = group; blockIdx.x + it * gridDim.x < tiles; it += F::EPI_GROUPS) {
-      const int tile = blockIdx.x + it * gridDim.x;
-      const int acc = it & (F::ACCS - 1);
-      mbar_wait_spin(&tmem_full[acc], (it / F::ACCS) & 1);
-      ptx::tc_fence_after();
+    constexpr int SETS = F::ACCS / F::TPS;
+    const int supers = (tiles + F::TPS - 1) / F::TPS;
+    for (int it = group; blockIdx.x + it * gridDim.x < supers; it += F::EPI_GROUPS) {
+     const int set = it % SETS;
+     mbar_wait_spin(&tmem_full[set], (it / SETS) & 1);
+     ptx::tc_fence_after();
+     for (int h2 = 0; h2 < F::TPS; ++h2) {
+      const int tile = (blockIdx.x + it * gridDim.x) * F::TPS + h2;
+      if (tile >= tiles || (dbg & 8)) continue;   // bit 8: the epilogue only hands the accumulators back
+      const int acc = set * F::TPS + h2;
       const uint32_t taddr = tmem_base + acc * COUT + (static_cast<uint32_t>(q * 32) << 16);
       // TMEM lane q * 32 + lane holds: VEC producers -> pixel 4 * lane + q of the tile; !VEC -> pixel q * 32 + lane
       int pix = tile * kTileM + (VEC ? 4 * lane + q : row);
@@ -315,9 +341,10 @@ conv_first_tc_kernel(const float* __restrict__ x, const __half* __restrict__ wk,
           }
         }
       }
-      ptx::tc_fence_before();
-      __syncwarp();
-      if (lane == 0) ptx::mbar_arrive(&tmem_empty[acc]);
+     }
+     ptx::tc_fence_before();
+     __syncwarp();
+     if (lane == 0) ptx::mbar_arrive(&tmem_empty[set]);
     }
   }
   ptx::tc_fence_before();

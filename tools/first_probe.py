@@ -23,7 +23,7 @@ if len(sys.argv) > 1:
     print(f"{sys.argv[1]:5s} DBG={os.environ.get('ME_FIRST_DBG','0')} COUT={os.environ.get('FIRST_COUT','16')} EPI={os.environ.get('ME_FIRST_EPI_PLAIN','2')}: {e0.elapsed_time(e1)/20*1e3:7.1f} us")
 else:
     for cout in ("16", "32"):
-        for dbg in ("0", "7"):
-            for epi in ("2", "3"):
+        for dbg in ("0", "7", "31"):
+            for epi in ("2",):
                 env = dict(os.environ, ME_FIRST_DBG=dbg, ME_FIRST_EPI_PLAIN=epi, FIRST_COUT=cout)
                 subprocess.run([sys.executable, __file__, "plain"], env=env)
