@@ -241,7 +241,8 @@ class DarknetPlan:
                 if (i > 0 and nxt is not None and nxt["type"] == "maxpool" and nxt["size"] == 2 and nxt["stride"] == 2
                         and fuse_res is None and not is_head and readers[i] == [] and i not in target and i + 1 not in target
                         and b["size"] == 3 and b["stride"] == 1 and self.device.type == "cuda"
-                        and b["cin"] in (16, 32) and cout in (32, 64) and i != self.feature_tap
+                        and b["cin"] == 16 and cout in (32, 64) and i != self.feature_tap   # 32-channel inputs: the TMA
+                        # kernel + a separate pool is 7 us faster at 104^2 x 32 (profiles/round2/launches_fusion_r2z_summary.txt)
                         and os.environ.get("ME_FUSE_POOL", "1") != "0"):
                     packed = self._pack(i, b)
                     cin_real = src.real_c if src.real_c != src.c else src.c
