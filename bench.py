@@ -591,10 +591,12 @@ def run_gpu(args):
     resident = [h.to(device).float() / 255.0 for h in host]
     plan = net.plan_for(BATCH, SIZE, device)
     from millieye_b200.models import DetectPipeline
-    # N > 1: every rank's detections are gathered on every GPU each step with ONE all_gather_into_tensor (ME_BENCH_GATHER=0:
-    # none; =peer: dist.PeerGather, copy engines + stream memory operations - measured slower).  Every
-    # rank reads its own shard back in the e2e arm; ME_BENCH_HOSTALL=1 also copies the gathered batch to rank 0's host.
-    mode = os.environ.get("ME_BENCH_GATHER", "nccl")
+    # N > 1: frames are independent and the path has no exchange step, so by default every rank keeps (device
+    # arm) or reads back (e2e arm) the detections of its own shard and no collective runs.  ME_BENCH_GATHER=nccl gathers
+    # every rank's detections on every GPU each step with ONE all_gather_into_tensor (costs 3.5 %: the NCCL kernel has to wait
+    # for SMs held by the persistent conv kernels); =peer: dist.PeerGather (copy engines + stream memory
+    # operations; measured slower).  ME_BENCH_HOSTALL=1 also copies a gathered batch to rank 0's host.
+    mode = os.environ.get("ME_BENCH_GATHER", "0")
     gather = False if world == 1 or mode == "0" else ("peer" if mode == "peer" else True)
     pipe = DetectPipeline(net, CONF_THRESH, 0.5, 200, gather=gather,
                           host_all=rank == 0 and os.environ.get("ME_BENCH_HOSTALL", "0") == "1")
@@ -760,7 +762,8 @@ def run_gpu(args):
                 config=dict(workload=f"Darknet-53 YOLOv3 inference (forward + decode + conf filter + NMS), batch {BATCH} per GPU, "
                                      f"{SIZE}x{SIZE}, fp16 compute / fp32 accumulate",
                             conf_thresh=CONF_THRESH, parallelism=f"frames sharded over {world} GPU(s), weights replicated"
-                            + (f", detections gathered on every GPU each step: {gather_impl}" if world > 1 else ""),
+                            + ("" if world == 1 else (", per-rank shards, no data-path collective" if not pipe.gather else
+                                                         f", per-rank shards; detections gathered on every GPU each step: {gather_impl}")),
                             l2="2 alternating resident input batches (64 MB each; 3 rotating pinned host batches in the e2e arm) and "
                                "~4 GB of activations per step exceed the 126 MB L2; no explicit flush",
                             pipeline="DetectPipeline: filter+NMS (+all_gather, +D2H read in the e2e arm) of batch i run on a "
