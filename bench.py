@@ -91,6 +91,20 @@ def measured_traffic():
                 write=t["dram_write_bytes"], launches=t["conv_launches"], source=t["source"])
 
 
+def l2_feed():
+    """What actually bounds the dominant kernel: L2 -> SM operand bytes per clock of the conv chain kernel against the
+    L2 slices' throughput cap, from the committed ncu capture (profiles/round2/l2_feed.json).  None if not in the tree."""
+    path = os.path.join(ROOT, "profiles", "round2", "l2_feed.json")
+    if not os.path.exists(path):
+        return None
+    with open(path) as fh:
+        d = json.load(fh)
+    top = d["launches"][0]
+    return dict(kernel=d["kernel"], bytes_per_clk=top["bytes_per_clk"], cap_bytes_per_clk=d["cap_bytes_per_clk"],
+                frac=top["frac_of_lts_cap"], tensor_pipe_active_pct=top["tensor_pipe_active_pct"], source=d["source"],
+                cap_source=d["cap_source"])
+
+
 class ClockSampler:
     FIELDS = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
               "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
@@ -748,13 +762,15 @@ def run_gpu(args):
                     frac_sustained=(achieved_long / pk["sustained"]) if achieved_long else None,
                     clocks_sustained=clocks_long,
                     traffic=(measured_traffic() or {}).get("dram_bytes_per_step"), traffic_detail=measured_traffic(),
-                    peak_source=pk["src"],
+                    peak_source=pk["src"], l2_feed=l2_feed(),
                     kernel="conv_chain_kernel / conv_gemm_kernel / conv_gemm_pair_kernel / conv_first_tc_kernel (tcgen05 implicit GEMM)",
                     launches=n_conv, conv_ms_per_step=conv_ms, conv_ms_per_step_sustained=conv_ms_long,
                     note="achieved = 65.864 GFLOP/frame x 32 frames / device time of the step's conv launches (all 75 conv "
                          "layers: per-layer tcgen05 GEMMs, the tensor-core first conv and the persistent multi-layer chain "
                          "kernels), CUDA events around replays of a graph holding only those launches; traffic = DRAM bytes "
-                         "(read + write) of the conv launches per step from the committed ncu capture")
+                         "(read + write) of the conv launches per step from the committed ncu capture; l2_feed = the 52-layer chain "
+                         "kernel's L2->SM operand bytes per clock against the L2 slices' cap (ncu): the tensor pipe waits for "
+                         "operands, the kernel sits at 94% of that cap")
 
     line = dict(metric=METRIC, value=fps, unit="frames/s", n_gpus=world, steps=args.steps, warmup=max(args.warmup, 3),
                 ms_per_step=ms_dev / args.steps, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f16",

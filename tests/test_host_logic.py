@@ -209,6 +209,45 @@ def test_plan_launch_list_on_cpu(monkeypatch):
     assert [d[5] for d in dec] == [32.0, 16.0, 8.0]
 
 
+def test_tiny_plan_fuses_first_pool_on_cpu(monkeypatch):
+    """yolov3-tiny-12 at 64 x 64 without a GPU: block 1 (MaxPool 2/2) has no launch of its own - the first conv is asked to
+    pool and writes the 32 x 32 tensor; the stride-1 pool of block 11 and the other four pools stay separate launches;
+    ME_FUSE_POOL=0 restores the six pools; a 48 x 48 input (width % 32 != 0) is not fused either."""
+    import torch
+    from millieye_b200 import engine, ops
+    first_calls = []
+
+    def fake_pack(weight, conv_bias=None, bn=None, cout_pad=None):
+        cout, cin, k, _ = weight.shape
+        return ops.PackedConv(torch.zeros(1), torch.zeros(1), cin, cout, cout_pad or ops.round_up(cout, 32), k)
+
+    monkeypatch.setattr(ops, "pack_conv", fake_pack)
+    monkeypatch.setattr(ops, "pack_first_conv", lambda w, b=None, bn=None: ops.FirstConv.__new__(ops.FirstConv))
+    monkeypatch.setattr(ops, "conv_workspace", lambda dev: torch.zeros(1))
+    monkeypatch.setattr(ops, "conv_first", lambda x, f, out, pitch, act, pool=False: first_calls.append((tuple(out.shape), pitch, pool)))
+    for name in ("conv_gemm", "maxpool2", "upsample2", "yolo_decode"):
+        monkeypatch.setattr(ops, name, lambda *a, **k: None)
+    net = __import__("millieye_b200.models", fromlist=["Darknet"]).Darknet(configs.cfg_path("yolov3-tiny-12"))
+    tensors = {k: v.detach().float() for k, v in net.state_dict().items() if v.is_floating_point()}
+
+    def build(size):
+        first_calls.clear()
+        plan = engine.DarknetPlan(net._blocks, tensors, 1, size, torch.device("cpu"), 8)
+        plan.enqueue()
+        return plan
+
+    monkeypatch.delenv("ME_FUSE_POOL", raising=False)
+    plan = build(64)
+    assert plan.op_kinds.count("maxpool") == 5 and plan.op_kinds.count("conv") == 13
+    assert first_calls[0][2] is True and first_calls[0][1] == 16
+    assert plan.feature_view is not None and plan.feature_view.real_c == 256 and plan.feature_view.h == 4
+    plan = build(48)
+    assert plan.op_kinds.count("maxpool") == 6 and first_calls[0][2] is False
+    monkeypatch.setenv("ME_FUSE_POOL", "0")
+    plan = build(64)
+    assert plan.op_kinds.count("maxpool") == 6 and first_calls[0][2] is False
+
+
 def test_chain_formation_on_cpu(monkeypatch):
     """DarknetPlan._form_chains without a GPU: Darknet-53's launch list becomes 8 per-layer launches (the 416^2 .. 104^2
     layers with fewer than 128 filters, and the 3x3 layers between them), three chains (the trunk from the last 104^2
