@@ -39,7 +39,7 @@ def main():
     steps = int(sys.argv[1]) if len(sys.argv) > 1 else 30
     dev = torch.device("cuda:0")
     model = Network(define_yolo(configs.cfg_path("yolov3-tiny-12")), conf_thresh=0.2).eval()
-    model.load_state_dict(synth.fill_state_dict(model.state_dict(), seed=0, obj_bias=-3.0, head_gain=1.0))
+    model.load_state_dict(synth.fill_state_dict(model.state_dict(), seed=0, obj_bias=-2.0, head_gain=0.3)   # bench.FUSION_WEIGHTS)
     model.to(dev)
     imgs = torch.rand(N, 3, S, S, device=dev)
     host_imgs = imgs.cpu().pin_memory()
