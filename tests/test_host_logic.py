@@ -209,6 +209,22 @@ def test_plan_launch_list_on_cpu(monkeypatch):
     assert [d[5] for d in dec] == [32.0, 16.0, 8.0]
 
 
+def test_bin_major_permutation():
+    """ops.bin_major_perm: position bin * C + c of the bin-major order holds reference element c * P * P + bin (the flatten
+    order of my_models.py:262), and permuting a producer's rows and a consumer's columns with it leaves the product
+    unchanged - what _FusionPlan relies on when it packs img_cnn_layers / refinement_head.net0 / radar_net."""
+    from millieye_b200 import ops
+    perm = ops.bin_major_perm(10, 7)
+    assert perm.shape == (490,) and sorted(perm.tolist()) == list(range(490))
+    for c in (0, 3, 9):
+        for b in (0, 17, 48):
+            assert int(perm[b * 10 + c]) == c * 49 + b
+    g = torch.Generator().manual_seed(0)
+    feat = torch.randn(5, 490, generator=g)            # a crop in reference order
+    w = torch.randn(8, 490, generator=g)               # a layer that reads it
+    assert torch.allclose(feat[:, perm] @ w[:, perm].t(), feat @ w.t(), atol=1e-4)
+
+
 def test_tiny_plan_fuses_first_pool_on_cpu(monkeypatch):
     """yolov3-tiny-12 at 64 x 64 without a GPU: block 1 (MaxPool 2/2) has no launch of its own - the first conv is asked to
     pool and writes the 32 x 32 tensor; the stride-1 pool of block 11 and the other four pools stay separate launches;
