@@ -237,11 +237,79 @@ def run_reference(args):
     emit(line)
 
 
+def match_detections(ref, det, cnt, frames, conf_thresh, tol=1e-3):
+    """Row-by-row comparison of NMS survivors: ref[f] = oracle rows (k, 7+) or None, det (n, max_det, 7+) / cnt (n,) = the
+    rows under test; columns x1, y1, x2, y2, conf, class_conf, class.  Rows are matched by class and IoU >= 0.9 (each
+    oracle row once); a row that only one side reports must be explained by a score difference <= tol: its confidence
+    is within tol of the threshold, it overlaps (IoU > 0.5 - tol) a same-class row of the other side whose score is
+    within tol of its own (the NMS order of the two flipped), or it overlaps an unmatched row of the other side (the row
+    that suppressed it there is itself such a flip)."""
+    import numpy as np
+    rows_ref = rows_gpu = matched = exact_order = 0
+    near_threshold = near_tie = unexplained = 0
+    box_err = score_err = 0.0
+
+    def iou(a, b):
+        ix = max(0.0, min(a[2], b[2]) - max(a[0], b[0]))
+        iy = max(0.0, min(a[3], b[3]) - max(a[1], b[1]))
+        inter = ix * iy
+        u = (a[2] - a[0]) * (a[3] - a[1]) + (b[2] - b[0]) * (b[3] - b[1]) - inter
+        return inter / u if u > 0 else 0.0
+
+    def explain(row, other, other_only):
+        if abs(row[4] - conf_thresh) <= tol:
+            return "threshold"
+        for o in other:
+            if o[6] == row[6] and abs(o[4] * o[5] - row[4] * row[5]) <= tol and iou(row, o) > 0.5 - tol:
+                return "tie"
+        for o in other_only:
+            if o[6] == row[6] and iou(row, o) > 0.5 - tol:
+                return "tie"
+        return None
+
+    for f in range(frames):
+        r = ref[f] if ref[f] is not None else np.zeros((0, det.shape[2]), np.float32)
+        r = np.asarray(r)
+        g = det[f, :cnt[f]]
+        rows_ref += len(r)
+        rows_gpu += len(g)
+        used = np.zeros(len(r), bool)
+        got_used = np.zeros(len(g), bool)
+        for i, row in enumerate(g):
+            best, bj = 0.0, -1
+            for j, rr in enumerate(r):
+                if used[j] or rr[6] != row[6]:
+                    continue
+                v = iou(row, rr)
+                if v > best:
+                    best, bj = v, j
+            if bj >= 0 and best >= 0.9:
+                used[bj] = got_used[i] = True
+                matched += 1
+                exact_order += int(bj == i)
+                rr = r[bj]
+                scale = max(abs(rr[2] - rr[0]), abs(rr[3] - rr[1]), 1.0)
+                box_err = max(box_err, float(np.abs(row[:4] - rr[:4]).max() / scale))
+                score_err = max(score_err, float(np.abs(row[4:6] - rr[4:6]).max()))
+        for rows, flags, other, oflags in ((g, got_used, r, used), (r, used, g, got_used)):
+            for row in rows[~flags]:
+                why = explain(row, other, other[~oflags])
+                near_threshold += int(why == "threshold")
+                near_tie += int(why == "tie")
+                unexplained += int(why is None)
+    return dict(checked=True, frames=frames, rows_oracle=rows_ref, rows_gpu=rows_gpu, rows_matched=matched,
+                rows_same_rank=exact_order, rows_only_one_side=dict(conf_within_tol_of_threshold=near_threshold,
+                                                                    nms_order_flip_within_tol=near_tie, unexplained=unexplained),
+                max_box_err_rel=box_err, max_score_err_abs=score_err, tolerance=tol,
+                within_tolerance=bool(unexplained == 0 and matched > 0 and box_err <= tol and score_err <= tol),
+                how="oracle (CPU fp32 restatement of the reference) on the same images / weights; rows matched by class and "
+                    "IoU >= 0.9; a row only one side reports must be explained by a score difference <= tolerance (at the "
+                    "confidence threshold, or an NMS order flip between two overlapping rows)")
+
+
 def check_parity(host_batch, rec, frames):
     """Detections of the first `frames` frames of a timed batch (as read back by the e2e arm) against the CPU oracle on
-    the same images and weights: survivors are matched row by row (same class, IoU >= 0.9 with an unused oracle row);
-    reports how many rows match and the box / score errors over the matched rows (north_star: 1e-3 relative)."""
-    import numpy as np
+    the same images and weights (north_star: 1e-3 relative); see match_detections."""
     from millieye_b200 import configs
     from millieye_b200.models import Darknet
     from oracle import boxes as obox
@@ -257,72 +325,7 @@ def check_parity(host_batch, rec, frames):
         with torch.no_grad():
             _, y = odark.darknet_forward(md, sd, x)
         ref, _ = obox.non_max_suppression_cpp(y.clone().numpy(), CONF_THRESH, use_torchvision=True)
-        det = rec.host_det.numpy()
-        cnt = rec.host_cnt.numpy()
-        rows_ref = rows_gpu = matched = exact_order = 0
-        near_threshold = near_tie = unexplained = 0
-        box_err = score_err = 0.0
-        tol = 1e-3
-
-        def iou(a, b):
-            ix = max(0.0, min(a[2], b[2]) - max(a[0], b[0]))
-            iy = max(0.0, min(a[3], b[3]) - max(a[1], b[1]))
-            inter = ix * iy
-            u = (a[2] - a[0]) * (a[3] - a[1]) + (b[2] - b[0]) * (b[3] - b[1]) - inter
-            return inter / u if u > 0 else 0.0
-
-        def explain(row, other, other_only):
-            """A row only one side reports is within tolerance if a score error <= tol explains it: its confidence is
-            within tol of the threshold, or it overlaps (IoU > nms threshold - tol) a same-class row the other side kept
-            whose score is within tol of its own (the NMS order of the two flipped)."""
-            if abs(row[4] - CONF_THRESH) <= tol:
-                return "threshold"
-            for o in other:
-                if o[6] == row[6] and abs(o[4] * o[5] - row[4] * row[5]) <= tol and iou(row, o) > 0.5 - tol:
-                    return "tie"
-            for o in other_only:     # second order: the row that suppressed it on the other side is itself such a flip
-                if o[6] == row[6] and iou(row, o) > 0.5 - tol:
-                    return "tie"
-            return None
-
-        for f in range(frames):
-            r = ref[f] if ref[f] is not None else np.zeros((0, det.shape[2]), np.float32)
-            r = np.asarray(r)
-            g = det[f, :cnt[f]]
-            rows_ref += len(r)
-            rows_gpu += len(g)
-            used = np.zeros(len(r), bool)
-            got_used = np.zeros(len(g), bool)
-            for i, row in enumerate(g):
-                best, bj = 0.0, -1
-                for j, rr in enumerate(r):
-                    if used[j] or rr[6] != row[6]:
-                        continue
-                    v = iou(row, rr)
-                    if v > best:
-                        best, bj = v, j
-                if bj >= 0 and best >= 0.9:
-                    used[bj] = got_used[i] = True
-                    matched += 1
-                    exact_order += int(bj == i)
-                    rr = r[bj]
-                    scale = max(abs(rr[2] - rr[0]), abs(rr[3] - rr[1]), 1.0)
-                    box_err = max(box_err, float(np.abs(row[:4] - rr[:4]).max() / scale))
-                    score_err = max(score_err, float(np.abs(row[4:6] - rr[4:6]).max()))
-            for rows, flags, other, oflags in ((g, got_used, r, used), (r, used, g, got_used)):
-                for row in rows[~flags]:
-                    why = explain(row, other, other[~oflags])
-                    near_threshold += int(why == "threshold")
-                    near_tie += int(why == "tie")
-                    unexplained += int(why is None)
-        return dict(checked=True, frames=frames, rows_oracle=rows_ref, rows_gpu=rows_gpu, rows_matched=matched,
-                    rows_same_rank=exact_order, rows_only_one_side=dict(conf_within_tol_of_threshold=near_threshold,
-                                                                        nms_order_flip_within_tol=near_tie, unexplained=unexplained),
-                    max_box_err_rel=box_err, max_score_err_abs=score_err, tolerance=tol,
-                    within_tolerance=bool(unexplained == 0 and matched > 0 and box_err <= tol and score_err <= tol),
-                    how="oracle (CPU fp32 restatement of the reference) on the same images / weights; rows matched by class and "
-                        "IoU >= 0.9; a row only one side reports must be explained by a score difference <= tolerance (at the "
-                        "confidence threshold, or an NMS order flip between two overlapping rows)")
+        return match_detections(ref, rec.host_det.numpy(), rec.host_cnt.numpy(), frames, CONF_THRESH)
     except Exception as e:  # noqa: BLE001
         return dict(checked=False, error=str(e)[:200])
 

@@ -329,3 +329,29 @@ def test_chain_formation_on_cpu(monkeypatch):
     assert first[51]["dep"] == 48 and first[51]["desc"].cout == 256      # route -4: the 1x1 in front of the upsample
     assert sum(1 for l in first if l["residual"] is not None) == 21      # 1 + 8 + 8 + 4 residual blocks
     assert all(l["dep"] == -1 for l in (chains[2].layers[0], chains[4].layers[0]))   # they read concat buffers
+
+
+def test_bench_detection_matcher():
+    """bench.match_detections (the in-bench parity check): equal rows match; a row at the confidence threshold or an NMS
+    order flip between two overlapping, equally scored rows is explained; anything else fails the check."""
+    import bench
+    base = np.array([[10, 10, 60, 60, 0.90, 0.8, 3], [100, 100, 180, 150, 0.50, 0.9, 1], [200, 40, 260, 90, 0.2004, 0.7, 5]],
+                    np.float32)
+
+    def run(ref_rows, got_rows):
+        det = np.zeros((1, 8, 7), np.float32)
+        det[0, :len(got_rows)] = got_rows
+        return bench.match_detections([ref_rows], det, np.array([len(got_rows)]), 1, 0.2)
+
+    r = run(base, base + np.array([0.01, -0.01, 0.02, 0.0, 1e-4, -1e-4, 0], np.float32))
+    assert r["rows_matched"] == 3 and r["within_tolerance"] and r["max_box_err_rel"] < 1e-3
+    r = run(base, base[:2])                              # the third row's confidence is within 1e-3 of the threshold
+    assert r["rows_only_one_side"]["conf_within_tol_of_threshold"] == 1 and r["within_tolerance"]
+    flip_a = np.array([[300, 300, 360, 360, 0.6000, 0.5, 2]], np.float32)     # two overlapping boxes, scores 1e-4 apart:
+    flip_b = np.array([[310, 300, 370, 360, 0.6001, 0.5, 2]], np.float32)     # each side kept the other one
+    r = run(np.concatenate([base, flip_a]), np.concatenate([base, flip_b]))
+    assert r["rows_only_one_side"]["nms_order_flip_within_tol"] == 2 and r["within_tolerance"]
+    r = run(base, np.concatenate([base, np.array([[5, 300, 50, 380, 0.7, 0.9, 4]], np.float32)]))
+    assert r["rows_only_one_side"]["unexplained"] == 1 and not r["within_tolerance"]
+    r = run(base, base + np.array([0.5, 0, 0, 0, 0, 0, 0], np.float32))   # 0.5 px on a 50 px box: 1e-2 > tolerance
+    assert r["rows_matched"] == 3 and not r["within_tolerance"]
