@@ -131,6 +131,13 @@ int me_conv_chain_eligible(const me_conv_desc* d);
 size_t me_conv_chain_blob_bytes(const me_chain_layer* layers, int n_layers);
 int me_conv_chain_build(const me_chain_layer* layers, int n_layers, void* host_blob, size_t blob_bytes);
 int me_conv_chain_run(const void* host_blob, void* dev_blob, me_stream_t stream);
+/* me_conv_chain_verify: replays a blob's work lists under the rules the kernel waits by (every pair takes its items in
+ * order; an item runs once the m tiles it reads and its residual tile are complete) and returns ME_ERR_ARG with the
+ * blocked item if the schedule cannot complete, lists a tile twice or not at all; me_conv_chain_build runs it on every
+ * blob it writes.  me_conv_chain_plan: me_conv_chain_build without tensor maps - needs no CUDA driver (tests,
+ * inspection of the schedule); me_conv_chain_run refuses such a blob. */
+int me_conv_chain_plan(const me_chain_layer* layers, int n_layers, void* host_blob, size_t blob_bytes);
+int me_conv_chain_verify(const void* host_blob);
 
 /* YOLO head: the linear 1x1 head conv (models.py:252, blocks followed by a [yolo] block) with YOLOLayer.forward's
  * decode (models.py:142-177, see me_yolo_decode) fused into its epilogue: the fp32 logits never go to memory, the
@@ -157,7 +164,7 @@ int me_conv_first_tc(const float* x_nchw, const float* w_folded, const float* bi
 /* me_conv_first_tc followed by MaxPool2d(2, 2) (blocks 0-1 of yolov3-tiny*.cfg, models.py:22-51) in one kernel: the
  * pool runs in the epilogue, y_nhwc is the pooled (n, h/2, w/2, out_pitch) tensor and the full-resolution activation is
  * never written.  Bit-identical to me_conv_first_tc + me_maxpool2.  Needs w % 32 == 0, h % 4 == 0, a 16-byte aligned
- * image and cout in {16, 32}; anything else is ME_ERR_UNSUPPORTED / ME_ERR_INVALID (run the two calls instead). */
+ * image and cout in {16, 32}; anything else is ME_ERR_UNSUPPORTED / ME_ERR_ARG (run the two calls instead). */
 int me_conv_first_tc_pool(const float* x_nchw, const float* w_folded, const float* bias, void* wk_scratch,
                           void* y_nhwc, int n, int h, int w, int cin, int cout, int out_pitch, int act,
                           me_stream_t stream);

@@ -68,6 +68,8 @@ SIGNATURES = {
     "me_conv_chain_eligible": (c_int, [POINTER(ConvDesc)]),
     "me_conv_chain_blob_bytes": (c_size_t, [POINTER(ChainLayer), c_int]),
     "me_conv_chain_build": (c_int, [POINTER(ChainLayer), c_int, c_void_p, c_size_t]),
+    "me_conv_chain_plan": (c_int, [POINTER(ChainLayer), c_int, c_void_p, c_size_t]),
+    "me_conv_chain_verify": (c_int, [c_void_p]),
     "me_conv_chain_run": (c_int, [c_void_p, c_void_p, c_void_p]),
     "me_conv_workspace_bytes": (c_size_t, []),
     "me_conv_gemm_ws": (c_int, [POINTER(ConvDesc), c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_size_t,

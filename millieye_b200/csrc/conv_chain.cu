@@ -81,6 +81,7 @@ struct ChainHeader {
   long long layers_off, work_off, counters_off, total_bytes;
 };
 constexpr unsigned long long kMagic = 0x4d45434841494e31ull;  // "MECHAIN1"
+constexpr unsigned long long kMagicPlan = 0x4d45434841494e50ull;  // "MECHAINP": schedule only, no tensor maps
 constexpr size_t kHeaderBytes = 256;
 
 struct ChainParams {
@@ -143,7 +144,7 @@ __device__ __forceinline__ void publish_counter(int* ctr) {
 }
 
 // Rows [lo, hi] of the producer layer that the consumer rows [m0, m1] read.
-__device__ __forceinline__ void dep_rows(const ChainLayer& L, int m0, int m1, int* lo, int* hi) {
+__host__ __device__ __forceinline__ void dep_rows(const ChainLayer& L, int m0, int m1, int* lo, int* hi) {
   if (L.dep_kind == 0) {
     *lo = m0;
     *hi = m1;
@@ -619,7 +620,9 @@ size_t me_conv_chain_blob_bytes(const me_chain_layer* layers, int n_layers) {
   return (bytes + 255) & ~size_t(255);
 }
 
-int me_conv_chain_build(const me_chain_layer* layers, int n_layers, void* host_blob, size_t blob_bytes) {
+int me_conv_chain_verify(const void* host_blob);
+
+static int chain_build_impl(const me_chain_layer* layers, int n_layers, void* host_blob, size_t blob_bytes, bool encode) {
   using namespace me;
   ME_REQUIRE(layers && host_blob && n_layers > 0, "conv_chain: null argument");
   ME_REQUIRE(n_layers < (1 << (31 - kItemShift)), "conv_chain: too many layers");
@@ -700,6 +703,7 @@ int me_conv_chain_build(const me_chain_layer* layers, int n_layers, void* host_b
       L.res_base = CL[a.res_layer].ctr_base;
       L.res_target = 2 * P.tiles_n;
     }
+    if (!encode) continue;     // schedule only (me_conv_chain_plan): no driver needed, the blob cannot be run
     int rc;
     if (L.im2col) {
       rc = encode_im2col_nhwc(&L.tmA, a.x, d.n, d.h, d.w, d.cin, d.in_pitch, d.ksize, pad, d.stride, kBK, kBM,
@@ -732,7 +736,7 @@ int me_conv_chain_build(const me_chain_layer* layers, int n_layers, void* host_b
   // small timing model (K blocks of 512 tensor clocks, a fixed per-tile cost, a tile starts once the m tiles it
   // reads are complete plus a hand-over latency).  Lists stay in global order, which is what makes the waits safe.
   const long long stride = tiles + 1;
-  H->magic = kMagic;
+  H->magic = encode ? kMagic : kMagicPlan;
   H->n_layers = n_layers;
   H->npairs = npairs;
   H->work_stride = static_cast<int>(stride);
@@ -822,6 +826,103 @@ int me_conv_chain_build(const me_chain_layer* layers, int n_layers, void* host_b
     }
   }
   for (int q = 0; q < npairs; ++q) work[static_cast<long long>(q) * stride + pair_n[q]] = -1;
+  // never hand out a schedule that cannot complete: replay it against the rules the kernel waits by
+  return me_conv_chain_verify(host_blob);
+}
+
+int me_conv_chain_build(const me_chain_layer* layers, int n_layers, void* host_blob, size_t blob_bytes) {
+  return chain_build_impl(layers, n_layers, host_blob, blob_bytes, true);
+}
+
+// The same layer table and work lists WITHOUT tensor maps: needs no CUDA driver (tests, inspection); me_conv_chain_run
+// refuses such a blob.
+int me_conv_chain_plan(const me_chain_layer* layers, int n_layers, void* host_blob, size_t blob_bytes) {
+  return chain_build_impl(layers, n_layers, host_blob, blob_bytes, false);
+}
+
+// Replays the work lists of a blob the way the kernel executes them - every pair takes its items in list order; an item
+// can run once the counters of the m tiles it reads (dep_rows) and of its residual tile have reached their targets; a
+// finished item adds 2 to its m tile's counter - and checks that every tile of every layer is listed exactly once, that
+// all lists run to their end (no deadlock whatever the timing, all pairs being co-resident) and that every counter ends
+// at its target.  Pairs are modelled as strictly sequential, which is stricter than the kernel's pipelining.
+int me_conv_chain_verify(const void* host_blob) {
+  using namespace me;
+  ME_REQUIRE(host_blob, "conv_chain_verify: null argument");
+  const unsigned char* base = static_cast<const unsigned char*>(host_blob);
+  const ChainHeader* H = reinterpret_cast<const ChainHeader*>(base);
+  ME_REQUIRE(H->magic == kMagic || H->magic == kMagicPlan, "conv_chain_verify: not a chain blob");
+  const ChainLayer* CL = reinterpret_cast<const ChainLayer*>(base + H->layers_off);
+  const int* work = reinterpret_cast<const int*>(base + H->work_off);
+  const int nl = H->n_layers, np = H->npairs;
+  std::vector<int> counters(H->n_counters, 0);
+  std::vector<std::vector<unsigned char>> seen(nl);
+  std::vector<int> tiles_m(nl);
+  long long total = 0;
+  for (int l = 0; l < nl; ++l) {
+    tiles_m[l] = ceil_div(CL[l].M, 2 * kBM);
+    seen[l].assign(static_cast<size_t>(tiles_m[l]) * CL[l].tiles_n, 0);
+    total += static_cast<long long>(tiles_m[l]) * CL[l].tiles_n;
+  }
+  std::vector<long long> pos(np, 0);
+  long long done = 0;
+  bool progress = true;
+  auto ready = [&](int item, int* why_ctr, int* why_val, int* why_target) {
+    const int l = item >> kItemShift, tile = item & ((1 << kItemShift) - 1);
+    const ChainLayer& L = CL[l];
+    const int tm = tile / L.tiles_n;
+    if (L.dep_kind >= 0) {
+      const int m0 = tm * 2 * kBM;
+      int m1 = m0 + 2 * kBM - 1;
+      if (m1 > L.M - 1) m1 = L.M - 1;
+      int lo, hi;
+      dep_rows(L, m0, m1, &lo, &hi);
+      for (int t = lo / (2 * kBM); t <= hi / (2 * kBM); ++t)
+        if (counters[L.dep_base + t] < L.dep_target) {
+          *why_ctr = L.dep_base + t; *why_val = counters[L.dep_base + t]; *why_target = L.dep_target;
+          return false;
+        }
+    }
+    if (L.has_res && L.res_base >= 0 && counters[L.res_base + tm] < L.res_target) {
+      *why_ctr = L.res_base + tm; *why_val = counters[L.res_base + tm]; *why_target = L.res_target;
+      return false;
+    }
+    return true;
+  };
+  while (progress) {
+    progress = false;
+    for (int q = 0; q < np; ++q) {
+      for (;;) {
+        const int item = work[static_cast<long long>(q) * H->work_stride + pos[q]];
+        if (item < 0) break;
+        const int l = item >> kItemShift, tile = item & ((1 << kItemShift) - 1);
+        ME_REQUIRE(l < nl && tile < static_cast<int>(seen[l].size()), "conv_chain_verify: pair %d lists item %d of layer %d out of range", q, tile, l);
+        int c, v, t;
+        if (!ready(item, &c, &v, &t)) break;
+        ME_REQUIRE(!seen[l][tile], "conv_chain_verify: tile %d of layer %d is listed twice", tile, l);
+        seen[l][tile] = 1;
+        counters[CL[l].ctr_base + tile / CL[l].tiles_n] += 2;
+        ++pos[q];
+        ++done;
+        progress = true;
+      }
+    }
+  }
+  if (done != total) {
+    for (int q = 0; q < np; ++q) {
+      const int item = work[static_cast<long long>(q) * H->work_stride + pos[q]];
+      if (item < 0) continue;
+      int c = -1, v = 0, t = 0;
+      ready(item, &c, &v, &t);
+      return fail(ME_ERR_ARG, "conv_chain_verify: schedule cannot complete (%lld of %lld tiles ran): pair %d is blocked at "
+                  "layer %d tile %d waiting for counter %d = %d < %d", done, total, q, item >> kItemShift,
+                  item & ((1 << kItemShift) - 1), c, v, t);
+    }
+    return fail(ME_ERR_ARG, "conv_chain_verify: %lld of %lld tiles are listed", done, total);
+  }
+  for (int l = 0; l < nl; ++l)
+    for (int tm = 0; tm < tiles_m[l]; ++tm)
+      ME_REQUIRE(counters[CL[l].ctr_base + tm] == 2 * CL[l].tiles_n, "conv_chain_verify: counter of layer %d m tile %d ends at %d, "
+                 "target %d", l, tm, counters[CL[l].ctr_base + tm], 2 * CL[l].tiles_n);
   return ME_OK;
 }
 
@@ -830,6 +931,7 @@ int me_conv_chain_run(const void* host_blob, void* dev_blob, me_stream_t stream_
   cudaStream_t stream = static_cast<cudaStream_t>(stream_);
   ME_REQUIRE(host_blob && dev_blob, "conv_chain: null argument");
   const ChainHeader* H = static_cast<const ChainHeader*>(host_blob);
+  ME_REQUIRE(H->magic != kMagicPlan, "conv_chain: the blob holds a schedule only (me_conv_chain_plan); build it with me_conv_chain_build");
   ME_REQUIRE(H->magic == kMagic, "conv_chain: the host blob was not written by me_conv_chain_build");
   ME_REQUIRE((reinterpret_cast<uintptr_t>(dev_blob) & 255) == 0, "conv_chain: device blob must be 256-byte aligned");
   int rc = conv_ensure_debug_word();

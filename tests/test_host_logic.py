@@ -355,3 +355,100 @@ def test_bench_detection_matcher():
     assert r["rows_only_one_side"]["unexplained"] == 1 and not r["within_tolerance"]
     r = run(base, base + np.array([0.5, 0, 0, 0, 0, 0, 0], np.float32))   # 0.5 px on a 50 px box: 1e-2 > tolerance
     assert r["rows_matched"] == 3 and not r["within_tolerance"]
+
+
+def test_chain_schedules_complete_on_cpu(monkeypatch, built_lib):
+    """The work lists me_conv_chain_build would write for Darknet-53 at batch 32 / 416^2 (three chains) and for a small
+    ragged case, produced WITHOUT a GPU (me_conv_chain_plan: no tensor maps) and replayed by me_conv_chain_verify under the
+    kernel's waiting rules: every tile listed exactly once, no pair ever blocked for good, every counter at its target.
+    A corrupted list (two items of one pair swapped so that a tile precedes the tile it reads) is reported, not run."""
+    import ctypes
+    import torch
+    from millieye_b200 import engine, ops
+
+    def fake_pack(weight, conv_bias=None, bn=None, cout_pad=None):
+        cout, cin, k, _ = weight.shape
+        return ops.PackedConv(torch.zeros(1), torch.zeros(1), cin, cout, cout_pad or ops.round_up(cout, 32), k)
+
+    chains = []
+
+    class FakeChain:
+        def __init__(self, layers, device):
+            self.layers = layers
+            chains.append(self)
+
+        def run(self):
+            pass
+
+    L = _lib.lib()
+    monkeypatch.setattr(ops, "pack_conv", fake_pack)
+    monkeypatch.setattr(ops, "pack_first_conv", lambda w, b=None, bn=None: ops.FirstConv.__new__(ops.FirstConv))
+    monkeypatch.setattr(ops, "ConvChain", FakeChain)
+    monkeypatch.setattr(ops, "_need_cuda", lambda *a: None)
+    net = __import__("millieye_b200.models", fromlist=["Darknet"]).Darknet(configs.cfg_path("yolov3"))
+    tensors = {k: v.detach().float() for k, v in net.state_dict().items() if v.is_floating_point()}
+    plan = engine.DarknetPlan(net._blocks, tensors, 2, 416, torch.device("cpu"), None)   # buffers for 2 frames ...
+    plan._form_chains()
+    assert [len(c.layers) for c in chains[::2]] == [52, 8, 7]
+    BATCH = 32                                                                            # ... schedules for BASELINE's 32
+
+    def plan_blob(layers):
+        n = len(layers)
+        arr = (_lib.ChainLayer * n)()
+        for a, l in zip(arr, layers):
+            a.d = l["desc"]
+            a.d.n = BATCH
+            a.x = a.w_packed = a.bias = a.y = 0x1000          # never dereferenced without tensor maps
+            a.residual = 0x1000 if l.get("residual") is not None else None
+            a.dep_layer, a.res_layer = l.get("dep", -1), l.get("res", -1)
+        nbytes = L.me_conv_chain_blob_bytes(arr, n)
+        assert nbytes > 0
+        raw = (ctypes.c_ubyte * (nbytes + 128))()
+        addr = ctypes.addressof(raw)
+        base = addr + (-addr) % 128
+        _lib.check(L.me_conv_chain_plan(arr, n, ctypes.c_void_p(base), nbytes), "me_conv_chain_plan")
+        return raw, base
+
+    for c in chains[::2]:
+        raw, base = plan_blob(c.layers)
+        assert L.me_conv_chain_verify(ctypes.c_void_p(base)) == 0
+    # corrupt the first chain's schedule: header = magic u64, then n_layers, npairs, work_stride (ints), ..., work_off
+    raw, base = plan_blob(chains[0].layers)
+    hdr = (ctypes.c_int * 8).from_address(base + 8)
+    n_layers, npairs, stride = hdr[0], hdr[1], hdr[2]
+    offs = (ctypes.c_longlong * 4).from_address(base + 8 + 6 * 4)       # layers_off, work_off, counters_off, total_bytes
+    work = (ctypes.c_int * (npairs * stride)).from_address(base + offs[1])
+    # find a pair that owns a layer-1 tile Y (3x3 / stride 2: 104^2 -> 52^2) AND one of the layer-0 m tiles Y reads, and
+    # swap the two items: the pair then reaches Y before the tile Y waits for - a schedule that can never complete
+    d0, d1 = chains[0].layers[0]["desc"], chains[0].layers[1]["desc"]
+    assert (d1.ksize, d1.stride, d1.h, d1.w) == (3, 2, 104, 104) and d0.cout // 128 >= 1
+    tiles_n0, tiles_n1 = (d.cout // (256 if d.cout % 256 == 0 else 128) for d in (d0, d1))   # chain_bn(): 256- or 128-column tiles
+    swapped = False
+    for q in range(npairs):
+        lst, k = [], 0
+        while work[q * stride + k] >= 0:
+            lst.append(work[q * stride + k])
+            k += 1
+        assert lst == sorted(lst)                                     # layer-major lists
+        own0 = {(it & 0xFFFFF) // tiles_n0: j for j, it in enumerate(lst) if it >> 20 == 0}
+        for j, it in enumerate(lst):
+            if it >> 20 != 1:
+                continue
+            tm = (it & 0xFFFFF) // tiles_n1
+            m0, m1 = tm * 256, min(tm * 256 + 255, BATCH * 52 * 52 - 1)
+            n0, y0, n1, y1 = m0 // 2704, (m0 % 2704) // 52, m1 // 2704, (m1 % 2704) // 52
+            lo = (n0 * 104 + max(2 * y0 - 1, 0)) * 104
+            hi = (n1 * 104 + min(2 * y1 + 1, 103)) * 104 + 103
+            hit = [own0[t] for t in range(lo // 256, hi // 256 + 1) if t in own0]
+            if hit:
+                i0 = hit[0]
+                work[q * stride + i0], work[q * stride + j] = work[q * stride + j], work[q * stride + i0]
+                swapped = True
+                break
+        if swapped:
+            break
+    assert swapped
+    assert L.me_conv_chain_verify(ctypes.c_void_p(base)) != 0
+    buf = ctypes.create_string_buffer(512)
+    L.me_last_error(buf, 512)
+    assert b"cannot complete" in buf.value and b"blocked" in buf.value
