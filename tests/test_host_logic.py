@@ -412,6 +412,26 @@ def test_chain_schedules_complete_on_cpu(monkeypatch, built_lib):
     for c in chains[::2]:
         raw, base = plan_blob(c.layers)
         assert L.me_conv_chain_verify(ctypes.c_void_p(base)) == 0
+        # load balance of the static lists in the builder's own cost model (K blocks x 512 clocks + 1500 per tile)
+        hdr = (ctypes.c_int * 8).from_address(base + 8)
+        npairs, stride = hdr[1], hdr[2]
+        offs = (ctypes.c_longlong * 4).from_address(base + 8 + 6 * 4)
+        work = (ctypes.c_int * (npairs * stride)).from_address(base + offs[1])
+        cost_of = [(9 if l["desc"].ksize == 3 else 1) * (l["desc"].cin // 64) * 512 + 1500 for l in c.layers]
+        loads = []
+        for q in range(npairs):
+            t, k = 0, 0
+            while work[q * stride + k] >= 0:
+                t += cost_of[work[q * stride + k] >> 20]
+                k += 1
+            loads.append(t)
+        assert npairs == 74 and max(loads) <= 1.08 * (sum(loads) / npairs), (max(loads), sum(loads) / npairs)
+    # other batch sizes (ragged last m tiles, fewer tiles than pairs) complete too
+    for BATCH in (1, 5, 16):
+        for c in chains[::2]:
+            raw, base = plan_blob(c.layers)
+            assert L.me_conv_chain_verify(ctypes.c_void_p(base)) == 0
+    BATCH = 32
     # corrupt the first chain's schedule: header = magic u64, then n_layers, npairs, work_stride (ints), ..., work_off
     raw, base = plan_blob(chains[0].layers)
     hdr = (ctypes.c_int * 8).from_address(base + 8)
